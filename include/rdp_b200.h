@@ -1,0 +1,118 @@
+/*
+ * rdp_b200.h -- public C-ABI of librdp_b200.so: the drop-in boundary for emulator / FFI integrations.
+ *
+ * One entry point per public method of the reference's RDP::CommandProcessor
+ * (parallel-rdp/rdp_device.hpp:111-197; behaviour: parallel-rdp/rdp_device.cpp).  Plain pointers and sizes
+ * only; no C++ or torch types cross this boundary.  See INTEGRATION.md for the binding a maintainer adds.
+ *
+ * Ownership: `rdram_ptr` is borrowed for the processor's lifetime (reference: integration_example.cpp:459-505);
+ * hidden RDRAM and TMEM are owned by the processor; pointers returned by begin_read_* / get_tmem stay owned by
+ * the processor and are valid while it is idle.
+ * Errors: no error codes (as in the reference); creation failure => rdp_b200_device_is_supported() == 0 and a
+ * message on stderr.  The library never falls back to a CPU renderer.
+ */
+#ifndef RDP_B200_H_
+#define RDP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rdp_b200_processor rdp_b200_processor;
+
+/* CommandProcessorFlagBits, rdp_device.hpp:43-53 */
+enum
+{
+	RDP_B200_FLAG_HOST_VISIBLE_HIDDEN_RDRAM = 1 << 0,
+	RDP_B200_FLAG_HOST_VISIBLE_TMEM = 1 << 1,
+	RDP_B200_FLAG_UPSCALING_2X = 1 << 2,
+	RDP_B200_FLAG_UPSCALING_4X = 1 << 3,
+	RDP_B200_FLAG_UPSCALING_8X = 1 << 4,
+	RDP_B200_FLAG_SUPER_SAMPLED_READ_BACK = 1 << 5,
+	RDP_B200_FLAG_SUPER_SAMPLED_DITHER = 1 << 6
+};
+
+/* VIRegister, rdp_common.hpp:324-341 */
+enum
+{
+	RDP_B200_VI_CONTROL = 0, RDP_B200_VI_ORIGIN, RDP_B200_VI_WIDTH, RDP_B200_VI_INTR, RDP_B200_VI_V_CURRENT_LINE,
+	RDP_B200_VI_TIMING, RDP_B200_VI_V_SYNC, RDP_B200_VI_H_SYNC, RDP_B200_VI_LEAP, RDP_B200_VI_H_START,
+	RDP_B200_VI_V_START, RDP_B200_VI_V_BURST, RDP_B200_VI_X_SCALE, RDP_B200_VI_Y_SCALE
+};
+
+/* ScanoutOptions, video_interface.hpp:31-81 (Vulkan export fields dropped). */
+typedef struct rdp_b200_scanout_options
+{
+	uint32_t crop_overscan_pixels;
+	uint32_t crop_left, crop_right, crop_top, crop_bottom;
+	uint32_t crop_enable;
+	uint32_t downscale_steps;
+	uint32_t persist_frame_on_invalid_input;
+	uint32_t blend_previous_frame;
+	uint32_t upscale_deinterlacing;
+	uint32_t vi_aa, vi_scale, vi_serrate, vi_dither_filter, vi_divot_filter, vi_gamma_dither;
+} rdp_b200_scanout_options;
+
+/* CommandProcessor::CommandProcessor, rdp_device.cpp:44-162.  `cuda_device` replaces Vulkan::Device&. */
+rdp_b200_processor *rdp_b200_create(int cuda_device, void *rdram_ptr, size_t rdram_offset, size_t rdram_size,
+                                    size_t hidden_rdram_size, uint32_t flags);
+/* ~CommandProcessor, rdp_device.cpp:164-167 */
+void rdp_b200_destroy(rdp_b200_processor *p);
+/* device_is_supported, rdp_device.cpp:225-228 */
+int rdp_b200_device_is_supported(const rdp_b200_processor *p);
+
+/* enqueue_command, rdp_device.cpp:874-897 */
+void rdp_b200_enqueue_command(rdp_b200_processor *p, unsigned num_words, const uint32_t *words);
+/* enqueue_command_direct, rdp_device.cpp:899-959 */
+void rdp_b200_enqueue_command_direct(rdp_b200_processor *p, unsigned num_words, const uint32_t *words);
+/* Extension: many back-to-back commands in one call (dump replay / bulk feed). */
+void rdp_b200_enqueue_command_stream(rdp_b200_processor *p, size_t num_words, const uint32_t *words);
+
+/* flush / signal_timeline / wait_for_timeline / idle / begin_frame_context, rdp_device.cpp:169-174,1038-1080 */
+void rdp_b200_flush(rdp_b200_processor *p);
+uint64_t rdp_b200_signal_timeline(rdp_b200_processor *p);
+void rdp_b200_wait_for_timeline(rdp_b200_processor *p, uint64_t index);
+void rdp_b200_idle(rdp_b200_processor *p);
+void rdp_b200_begin_frame_context(rdp_b200_processor *p);
+
+/* set_quirks, rdp_device.cpp:961-968 */
+void rdp_b200_set_quirks(rdp_b200_processor *p, int native_resolution_tex_rect, int native_texture_lod);
+
+/* Memory interaction, rdp_device.cpp:997-1036 */
+void *rdp_b200_begin_read_rdram(rdp_b200_processor *p);
+void rdp_b200_end_write_rdram(rdp_b200_processor *p);
+void *rdp_b200_begin_read_hidden_rdram(rdp_b200_processor *p);
+void rdp_b200_end_write_hidden_rdram(rdp_b200_processor *p);
+size_t rdp_b200_get_rdram_size(const rdp_b200_processor *p);
+size_t rdp_b200_get_hidden_rdram_size(const rdp_b200_processor *p);
+void *rdp_b200_get_tmem(rdp_b200_processor *p);
+
+/* set_vi_register, rdp_device.cpp:970-975 */
+void rdp_b200_set_vi_register(rdp_b200_processor *p, uint32_t reg, uint32_t value);
+/* Per-scanline VI registers, rdp_device.cpp:977-995 */
+void rdp_b200_begin_vi_register_per_scanline(rdp_b200_processor *p, uint32_t flags);
+void rdp_b200_set_vi_register_for_scanline(rdp_b200_processor *p, uint32_t reg_bit, uint32_t value);
+void rdp_b200_latch_vi_register_for_scanline(rdp_b200_processor *p, unsigned vi_line);
+void rdp_b200_end_vi_register_per_scanline(rdp_b200_processor *p);
+
+/* scanout, rdp_device.cpp:1082-1115: returns a device pointer to RGBA8 pixels (NULL when blank). */
+const void *rdp_b200_scanout(rdp_b200_processor *p, const rdp_b200_scanout_options *opts, unsigned *width, unsigned *height);
+/* scanout_sync, rdp_device.cpp:1160-1182: copies up to `capacity_pixels` RGBA8 pixels into `rgba`. */
+void rdp_b200_scanout_sync(rdp_b200_processor *p, const rdp_b200_scanout_options *opts, uint32_t *rgba,
+                           size_t capacity_pixels, unsigned *width, unsigned *height);
+void rdp_b200_default_scanout_options(rdp_b200_scanout_options *opts);
+
+/* Introspection (not in the reference API): backend name, kernels launched, primitives / passes submitted. */
+const char *rdp_b200_backend_name(void);
+uint64_t rdp_b200_launch_count(rdp_b200_processor *p);
+uint64_t rdp_b200_primitive_count(rdp_b200_processor *p);
+uint64_t rdp_b200_pass_count(rdp_b200_processor *p);
+void *rdp_b200_cuda_stream(rdp_b200_processor *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,117 @@
+/*
+ * rdp_b200_backend.h -- the thin C-ABI between the C++ host (command processor, renderer, video interface)
+ * and the CUDA runtime.  It replaces the Granite/Vulkan layer the reference renderer is written against:
+ * every entry point below corresponds to a group of Granite call sites in the reference.
+ *
+ *   buffers / RDRAM mirror   <- Vulkan::Device::create_buffer / map_host_buffer / copy_buffer
+ *                               (parallel-rdp/rdp_device.cpp:54-131,245-261; rdp_renderer.cpp:603-658)
+ *   pass staging + submit    <- RenderBuffersUpdater::upload            (rdp_renderer.cpp:1592-1632)
+ *   rdpb_launch_tmem_update  <- Renderer::update_tmem_instances         (rdp_renderer.cpp:1634-1668)
+ *   rdpb_launch_prim_setup   <- CPU-side decode in the reference        (rdp_device.cpp:268-419, rdp_renderer.cpp:910-925)
+ *   rdpb_launch_span_bin     <- submit_span_setup_jobs + submit_tile_binning_combined (rdp_renderer.cpp:1670-1700,1832-1935)
+ *   rdpb_launch_tiles        <- submit_rasterization + submit_depth_blend (rdp_renderer.cpp:1721-1830,2086-2221)
+ *   rdpb_launch_vi_*         <- VideoInterface::*_stage                 (video_interface.cpp:405-999)
+ *   rdpb_signal / rdpb_wait  <- Vulkan::Fence + timeline                (rdp_renderer.cpp:2404-2466, rdp_device.cpp:1053-1080)
+ *
+ * Barriers of the reference (rdp_renderer.cpp:2251,2259,2271,2347) become CUDA stream order.
+ * Two implementations exist: the product (CUDA, parallel-rdp_b200/csrc/backend_cuda.cu) and a test-only CPU
+ * build of the same device functions (tests/hostsim), selected at link time.  The product never falls back.
+ */
+#ifndef RDP_B200_BACKEND_H_
+#define RDP_B200_BACKEND_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rdpb_device rdpb_device;
+
+/* Host-visible staging area for the pass being recorded.  Pointers stay valid until rdpb_pass_submit(). */
+typedef struct rdpb_pass_buffers
+{
+	uint32_t *words;   /* raw RDP command words of the primitives, capacity rdpb::kMaxPassWords */
+	void *records;     /* rdpb::PrimRecord[kMaxPrimsPerPass] */
+	void *states;      /* rdpb::PassState[kMaxStatesPerPass] */
+	void *uploads;     /* rdpb::TmemUpload[kMaxUploadsPerPass] */
+} rdpb_pass_buffers;
+
+typedef struct rdpb_pass_counts
+{
+	uint32_t num_words;
+	uint32_t num_prims;
+	uint32_t num_states;
+	uint32_t num_uploads;
+	uint32_t num_spans;
+} rdpb_pass_counts;
+
+/* Returns NULL (and logs to stderr) when no usable CUDA device exists. */
+rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t hidden_rdram_size);
+void rdpb_device_destroy(rdpb_device *dev);
+const char *rdpb_backend_name(void);
+const char *rdpb_last_error(rdpb_device *dev);
+
+/* RDRAM / hidden RDRAM / TMEM mirrors.  Copies are asynchronous on the device's stream unless `sync`. */
+int rdpb_register_host_memory(rdpb_device *dev, void *ptr, size_t size);
+int rdpb_unregister_host_memory(rdpb_device *dev, void *ptr);
+int rdpb_rdram_write(rdpb_device *dev, uint32_t offset, const void *src, uint32_t size, int sync);
+int rdpb_rdram_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size, int sync);
+int rdpb_hidden_write(rdpb_device *dev, uint32_t offset, const void *src, uint32_t size, int sync);
+int rdpb_hidden_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size, int sync);
+int rdpb_hidden_fill(rdpb_device *dev, uint8_t value);
+/* TMEM (4 KiB) lives in host-mapped pinned memory: the pointer is coherent whenever the stream is idle. */
+void *rdpb_tmem_host_ptr(rdpb_device *dev);
+void *rdpb_rdram_device_ptr(rdpb_device *dev);
+void *rdpb_hidden_device_ptr(rdpb_device *dev);
+
+/* Pass recording and submission. */
+int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out);
+int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *counts);
+int rdpb_launch_tmem_update(rdpb_device *dev, uint32_t num_uploads);
+int rdpb_launch_prim_setup(rdpb_device *dev, uint32_t num_prims);
+int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo */);
+int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo */);
+int rdpb_pass_end(rdpb_device *dev);
+
+/* VI scan-out.  `regs` is rdpb::ViRegs, `lines` rdpb::ViLine[288]; result is RGBA8 in device memory. */
+typedef struct rdpb_vi_params
+{
+	const void *regs;
+	const void *lines;
+	uint32_t width, height;      /* output size */
+	uint32_t flags;              /* RDPB_VI_* */
+	uint32_t frame_count;
+} rdpb_vi_params;
+
+enum
+{
+	RDPB_VI_BLEND_PREVIOUS = 1u << 0,
+	RDPB_VI_PREV_VALID = 1u << 1,
+	RDPB_VI_DEGENERATE = 1u << 2,
+	RDPB_VI_OPT_AA = 1u << 3,
+	RDPB_VI_OPT_SCALE = 1u << 4,
+	RDPB_VI_OPT_SERRATE = 1u << 5,
+	RDPB_VI_OPT_DITHER_FILTER = 1u << 6,
+	RDPB_VI_OPT_DIVOT = 1u << 7,
+	RDPB_VI_OPT_GAMMA_DITHER = 1u << 8,
+};
+
+int rdpb_launch_vi_scanout(rdpb_device *dev, const rdpb_vi_params *params);
+void *rdpb_vi_output_device_ptr(rdpb_device *dev);
+int rdpb_vi_read_output(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, int sync);
+
+/* Synchronisation. */
+int rdpb_signal(rdpb_device *dev, uint64_t value);   /* records a point in stream order */
+int rdpb_wait(rdpb_device *dev, uint64_t value);     /* blocks the calling thread until that point completed */
+int rdpb_sync(rdpb_device *dev);
+void *rdpb_stream(rdpb_device *dev);                 /* cudaStream_t for interop/benchmark timing */
+
+/* Instrumentation: number of kernels launched since creation. */
+uint64_t rdpb_launch_count(rdpb_device *dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,204 @@
+"""ctypes binding over the C-ABI of librdp_b200.so (include/rdp_b200.h).
+
+This is plumbing for tests and bench.py; the product is the shared library.  The method names mirror
+RDP::CommandProcessor of the reference (parallel-rdp/rdp_device.hpp:111-197) so that tests read like the
+reference's own harness (replayer_driver_parallel.cpp).
+
+There is no CPU fallback: if the CUDA library has not been built, or no CUDA device is usable, construction raises.
+Tests that exercise the host logic without a GPU pass the test-only host simulator's path explicitly
+(tests/hostsim); nothing in this package ever selects it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIBRARY = os.path.join(_HERE, "librdp_b200.so")
+
+VI_REG = {name: i for i, name in enumerate(
+    ["Control", "Origin", "Width", "Intr", "VCurrentLine", "Timing", "VSync", "HSync", "Leap", "HStart", "VStart",
+     "VBurst", "XScale", "YScale"])}
+
+
+class ScanoutOptions(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "crop_overscan_pixels", "crop_left", "crop_right", "crop_top", "crop_bottom", "crop_enable",
+        "downscale_steps", "persist_frame_on_invalid_input", "blend_previous_frame", "upscale_deinterlacing",
+        "vi_aa", "vi_scale", "vi_serrate", "vi_dither_filter", "vi_divot_filter", "vi_gamma_dither")]
+
+
+def _bind(lib):
+    P, U32, U64, SZ = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t
+    sig = {
+        "rdp_b200_create": (P, [C.c_int, P, SZ, SZ, SZ, U32]),
+        "rdp_b200_destroy": (None, [P]),
+        "rdp_b200_device_is_supported": (C.c_int, [P]),
+        "rdp_b200_enqueue_command": (None, [P, C.c_uint, P]),
+        "rdp_b200_enqueue_command_direct": (None, [P, C.c_uint, P]),
+        "rdp_b200_enqueue_command_stream": (None, [P, SZ, P]),
+        "rdp_b200_flush": (None, [P]),
+        "rdp_b200_signal_timeline": (U64, [P]),
+        "rdp_b200_wait_for_timeline": (None, [P, U64]),
+        "rdp_b200_idle": (None, [P]),
+        "rdp_b200_begin_frame_context": (None, [P]),
+        "rdp_b200_set_quirks": (None, [P, C.c_int, C.c_int]),
+        "rdp_b200_begin_read_rdram": (P, [P]),
+        "rdp_b200_end_write_rdram": (None, [P]),
+        "rdp_b200_begin_read_hidden_rdram": (P, [P]),
+        "rdp_b200_end_write_hidden_rdram": (None, [P]),
+        "rdp_b200_get_rdram_size": (SZ, [P]),
+        "rdp_b200_get_hidden_rdram_size": (SZ, [P]),
+        "rdp_b200_get_tmem": (P, [P]),
+        "rdp_b200_set_vi_register": (None, [P, U32, U32]),
+        "rdp_b200_begin_vi_register_per_scanline": (None, [P, U32]),
+        "rdp_b200_set_vi_register_for_scanline": (None, [P, U32, U32]),
+        "rdp_b200_latch_vi_register_for_scanline": (None, [P, C.c_uint]),
+        "rdp_b200_end_vi_register_per_scanline": (None, [P]),
+        "rdp_b200_scanout": (P, [P, P, P, P]),
+        "rdp_b200_scanout_sync": (None, [P, P, P, SZ, P, P]),
+        "rdp_b200_default_scanout_options": (None, [P]),
+        "rdp_b200_backend_name": (C.c_char_p, []),
+        "rdp_b200_launch_count": (U64, [P]),
+        "rdp_b200_primitive_count": (U64, [P]),
+        "rdp_b200_pass_count": (U64, [P]),
+        "rdp_b200_cuda_stream": (P, [P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+EXPORTED_SYMBOLS = None  # filled lazily from the table above for the symbol-presence test
+
+
+def exported_symbol_names():
+    import re
+    header = os.path.join(os.path.dirname(_HERE), "include", "rdp_b200.h")
+    text = open(header).read()
+    return sorted(set(re.findall(r"\b(rdp_b200_[a-z_0-9]+)\s*\(", text)))
+
+
+def load_library(path: str | None = None):
+    path = path or PRODUCT_LIBRARY
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "There is no CPU fallback.")
+    return _bind(C.CDLL(path))
+
+
+class CommandProcessor:
+    """Mirror of RDP::CommandProcessor over the C-ABI.  `rdram` is a caller-owned numpy uint8 array (borrowed)."""
+
+    def __init__(self, rdram: np.ndarray, hidden_rdram_size: int, flags: int = 0, cuda_device: int = 0,
+                 library: str | None = None):
+        assert rdram.dtype == np.uint8 and rdram.flags["C_CONTIGUOUS"]
+        self.lib = load_library(library)
+        self.rdram = rdram
+        self._h = self.lib.rdp_b200_create(cuda_device, rdram.ctypes.data, 0, rdram.size, hidden_rdram_size, flags)
+        if not self._h or not self.lib.rdp_b200_device_is_supported(self._h):
+            raise RuntimeError("rdp_b200: device is not supported (no usable CUDA device / backend init failed)")
+        self.hidden_size = hidden_rdram_size
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.rdp_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- commands -------------------------------------------------------------------------------------------
+    def enqueue_command(self, words):
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        self.lib.rdp_b200_enqueue_command(self._h, w.size, w.ctypes.data)
+
+    def enqueue_command_stream(self, words: np.ndarray):
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        self.lib.rdp_b200_enqueue_command_stream(self._h, w.size, w.ctypes.data)
+
+    def enqueue_command_stream_ptr(self, ptr: int, num_words: int):
+        self.lib.rdp_b200_enqueue_command_stream(self._h, num_words, ptr)
+
+    def flush(self):
+        self.lib.rdp_b200_flush(self._h)
+
+    def signal_timeline(self) -> int:
+        return self.lib.rdp_b200_signal_timeline(self._h)
+
+    def wait_for_timeline(self, value: int):
+        self.lib.rdp_b200_wait_for_timeline(self._h, value)
+
+    def idle(self):
+        self.lib.rdp_b200_idle(self._h)
+
+    def begin_frame_context(self):
+        self.lib.rdp_b200_begin_frame_context(self._h)
+
+    # --- memory ---------------------------------------------------------------------------------------------
+    def begin_read_rdram(self) -> np.ndarray:
+        self.lib.rdp_b200_begin_read_rdram(self._h)
+        return self.rdram
+
+    def end_write_rdram(self):
+        self.lib.rdp_b200_end_write_rdram(self._h)
+
+    def begin_read_hidden_rdram(self) -> np.ndarray:
+        p = self.lib.rdp_b200_begin_read_hidden_rdram(self._h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(self.hidden_size,))
+
+    def end_write_hidden_rdram(self):
+        self.lib.rdp_b200_end_write_hidden_rdram(self._h)
+
+    def get_tmem(self) -> np.ndarray:
+        p = self.lib.rdp_b200_get_tmem(self._h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(4096,))
+
+    # --- VI -------------------------------------------------------------------------------------------------
+    def set_vi_register(self, reg, value: int):
+        self.lib.rdp_b200_set_vi_register(self._h, VI_REG[reg] if isinstance(reg, str) else int(reg), value & 0xffffffff)
+
+    def default_scanout_options(self) -> ScanoutOptions:
+        o = ScanoutOptions()
+        self.lib.rdp_b200_default_scanout_options(C.byref(o))
+        return o
+
+    def scanout_sync(self, opts: ScanoutOptions | None = None, out: np.ndarray | None = None):
+        """Returns (pixels[h, w] uint32 RGBA8 little-endian bytes r,g,b,a, w, h)."""
+        if out is None:
+            out = np.empty(640 * 576 * 4, dtype=np.uint32)
+        w, h = C.c_uint(0), C.c_uint(0)
+        self.lib.rdp_b200_scanout_sync(self._h, C.byref(opts) if opts is not None else None, out.ctypes.data, out.size,
+                                       C.byref(w), C.byref(h))
+        n = w.value * h.value
+        return out[:n].reshape(h.value, w.value) if n else out[:0].reshape(0, 0), w.value, h.value
+
+    def scanout(self, opts: ScanoutOptions | None = None):
+        """Device-pointer scan-out (no host copy).  Returns (device_ptr, w, h)."""
+        w, h = C.c_uint(0), C.c_uint(0)
+        p = self.lib.rdp_b200_scanout(self._h, C.byref(opts) if opts is not None else None, C.byref(w), C.byref(h))
+        return p, w.value, h.value
+
+    # --- introspection ----------------------------------------------------------------------------------------
+    def backend_name(self) -> str:
+        return self.lib.rdp_b200_backend_name().decode()
+
+    def launch_count(self) -> int:
+        return self.lib.rdp_b200_launch_count(self._h)
+
+    def primitive_count(self) -> int:
+        return self.lib.rdp_b200_primitive_count(self._h)
+
+    def pass_count(self) -> int:
+        return self.lib.rdp_b200_pass_count(self._h)
+
+    def cuda_stream(self) -> int:
+        return self.lib.rdp_b200_cuda_stream(self._h) or 0

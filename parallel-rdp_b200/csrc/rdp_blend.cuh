@@ -1,0 +1,547 @@
+// rdp_blend.cuh -- the ordered per-pixel back end: RDRAM framebuffer load/store (colour, depth, hidden bits),
+// depth compare, blender, coverage accumulation, fill and copy pipes.
+//
+// Behavioural reference (bit-exact target): parallel-rdp/shaders/memory_interfacing.h:56-571,
+// depth_test.h:41-144, z_encode.h:28-56, blender.h:55-143, coverage.h:51-79, dither.h:30-38.
+//
+// RDRAM layout: host-endian 32-bit words of big-endian N64 memory, so byte address a lives at a^3 and
+// 16-bit index i at i^1.  "Hidden" RDRAM holds the 9th bit pair of every 16-bit word, one byte per 16-bit index.
+#pragma once
+#include "rdp_shade.cuh"
+
+namespace rdpb
+{
+struct PixelState
+{
+	int r, g, b, a;   // a carries 3-bit coverage in bits 7..5 for 16-bit formats
+	int depth;        // 14-bit compressed Z
+	int dz;           // 4-bit compressed delta-Z
+	bool color_dirty, depth_dirty;
+	uint32_t color_index; // pixel index used by the fill pipe's sub-word select
+};
+
+struct FbView
+{
+	uint8_t *rdram;
+	uint8_t *hidden;
+	const uint8_t *blend_lut; // blender divider table, 0x8000 entries
+	uint32_t fmt;
+	uint32_t rdram_size;
+	bool alias; // colour and depth image share an address
+};
+
+RDP_HD uint16_t *rdram16(uint8_t *p) { return reinterpret_cast<uint16_t *>(p); }
+RDP_HD uint32_t *rdram32(uint8_t *p) { return reinterpret_cast<uint32_t *>(p); }
+
+RDP_HD void load_color(const FbView &fb, PixelState &px, uint32_t index)
+{
+	switch (fb.fmt)
+	{
+	case FB_I4:
+	case FB_I8:
+	{
+		index &= fb.rdram_size - 1u;
+		const int v = fb.rdram[index ^ 3u];
+		px.r = px.g = px.b = v;
+		px.a = fb.hidden[index >> 1];
+		break;
+	}
+	case FB_RGBA5551:
+	{
+		index &= (fb.rdram_size >> 1) - 1u;
+		const uint32_t w = rdram16(fb.rdram)[index ^ 1u];
+		px.r = int((w >> 8) & 0xf8u);
+		px.g = int((w >> 3) & 0xf8u);
+		px.b = int((w << 2) & 0xf8u);
+		px.a = int(((uint32_t(fb.hidden[index]) << 5) | ((w & 1u) << 7)) & 0xffu);
+		break;
+	}
+	case FB_IA88:
+	{
+		index &= (fb.rdram_size >> 1) - 1u;
+		const uint32_t w = rdram16(fb.rdram)[index ^ 1u];
+		px.r = px.g = px.b = int(w >> 8);
+		px.a = int(w & 0xffu);
+		break;
+	}
+	default: // FB_RGBA8888
+	{
+		index &= (fb.rdram_size >> 2) - 1u;
+		const uint32_t w = rdram32(fb.rdram)[index];
+		px.r = int(w >> 24);
+		px.g = int((w >> 16) & 0xffu);
+		px.b = int((w >> 8) & 0xffu);
+		px.a = int(w & 0xffu);
+		break;
+	}
+	}
+}
+
+RDP_HD void load_depth(const FbView &fb, PixelState &px, uint32_t index)
+{
+	index &= (fb.rdram_size >> 1) - 1u;
+	const uint32_t w = rdram16(fb.rdram)[index ^ 1u];
+	px.depth = int(w >> 2);
+	px.dz = int(fb.hidden[index]) | int((w & 3u) << 2);
+}
+
+RDP_HD void store_color(const FbView &fb, const PixelState &px, uint32_t index)
+{
+	if (!px.color_dirty)
+		return;
+	switch (fb.fmt)
+	{
+	case FB_I4:
+		index &= fb.rdram_size - 1u;
+		fb.rdram[index ^ 3u] = 0;
+		if (index & 1u)
+			fb.hidden[index >> 1] = uint8_t(px.a);
+		break;
+	case FB_I8:
+	{
+		index &= fb.rdram_size - 1u;
+		const int v = (index & 1u) ? px.g : px.r;
+		fb.rdram[index ^ 3u] = uint8_t(v);
+		if (index & 1u)
+			fb.hidden[index >> 1] = uint8_t((v & 1) * 3);
+		break;
+	}
+	case FB_RGBA5551:
+	{
+		index &= (fb.rdram_size >> 1) - 1u;
+		const uint32_t cov = uint32_t(px.a & 0xff) >> 5;
+		const uint32_t w = (uint32_t(px.r & 0xf8) << 8) | (uint32_t(px.g & 0xf8) << 3) | (uint32_t(px.b & 0xf8) >> 2) | (cov >> 2);
+		rdram16(fb.rdram)[index ^ 1u] = uint16_t(w);
+		fb.hidden[index] = uint8_t(cov & 3u);
+		break;
+	}
+	case FB_IA88:
+	{
+		index &= (fb.rdram_size >> 1) - 1u;
+		const uint32_t w = (uint32_t(px.r & 0xff) << 8) | uint32_t(px.a & 0xff);
+		rdram16(fb.rdram)[index ^ 1u] = uint16_t(w);
+		fb.hidden[index] = uint8_t((px.a & 1) * 3);
+		break;
+	}
+	default:
+	{
+		index &= (fb.rdram_size >> 2) - 1u;
+		const uint32_t w = (uint32_t(px.r & 0xff) << 24) | (uint32_t(px.g & 0xff) << 16) | (uint32_t(px.b & 0xff) << 8) | uint32_t(px.a & 0xff);
+		rdram32(fb.rdram)[index] = w;
+		fb.hidden[2u * index] = uint8_t((px.g & 1) * 3);
+		fb.hidden[2u * index + 1u] = uint8_t((px.a & 1) * 3);
+		break;
+	}
+	}
+}
+
+RDP_HD void store_depth(const FbView &fb, const PixelState &px, uint32_t index)
+{
+	if (fb.alias || !px.depth_dirty)
+		return;
+	index &= (fb.rdram_size >> 1) - 1u;
+	rdram16(fb.rdram)[index ^ 1u] = uint16_t((uint32_t(px.depth) << 2) | (uint32_t(px.dz) >> 2));
+	fb.hidden[index] = uint8_t(px.dz & 3);
+}
+
+// When colour and depth share one image every write to one is visible through the other:
+// memory_interfacing.h:100-151
+RDP_HD void alias_color_to_depth(const FbView &fb, PixelState &px)
+{
+	if (fb.fmt == FB_RGBA5551)
+	{
+		px.dz = ((px.a & 0xff) >> 3) | (px.b & 8);
+		px.depth = ((px.r & 0xf8) << 6) | ((px.g & 0xf8) << 1) | ((px.b & 0xf8) >> 4);
+	}
+	else if (fb.fmt == FB_IA88)
+	{
+		const uint32_t w = (uint32_t(px.r & 0xff) << 8) | uint32_t(px.a & 0xff);
+		px.depth = int(w >> 2);
+		px.dz = int(((w & 3u) << 2) | ((w & 1u) * 3u));
+	}
+}
+
+RDP_HD void alias_depth_to_color(const FbView &fb, PixelState &px)
+{
+	const uint32_t w = (uint32_t(px.depth) << 4) | uint32_t(px.dz);
+	if (fb.fmt == FB_RGBA5551)
+	{
+		px.r = int((w >> 10) & 0xf8u);
+		px.g = int((w >> 5) & 0xf8u);
+		px.b = int(w & 0xf8u);
+		px.a = int((w & 7u) << 5);
+	}
+	else if (fb.fmt == FB_IA88)
+	{
+		px.r = int((w >> 10) & 0xffu);
+		px.a = int((w >> 2) & 0xffu);
+	}
+	px.color_dirty = true;
+}
+
+RDP_HD void write_color(const FbView &fb, PixelState &px, int r, int g, int b, int a)
+{
+	px.r = r;
+	px.g = g;
+	px.b = b;
+	if (fb.fmt != FB_I4)
+		px.a = a;
+	px.color_dirty = true;
+}
+
+// Fill pipe: memory_interfacing.h:440-486
+RDP_HD void fill_pixel(const FbView &fb, PixelState &px, uint32_t col)
+{
+	switch (fb.fmt)
+	{
+	case FB_RGBA8888:
+		write_color(fb, px, int(col >> 24), int((col >> 16) & 0xffu), int((col >> 8) & 0xffu), int(col & 0xffu));
+		break;
+	case FB_RGBA5551:
+		col >>= ((px.color_index & 1u) ^ 1u) * 16u;
+		write_color(fb, px, int((col >> 8) & 0xf8u), int((col >> 3) & 0xf8u), int((col << 2) & 0xf8u), int((col & 1u) * 0xe0u));
+		break;
+	case FB_IA88:
+	{
+		col >>= ((px.color_index & 1u) ^ 1u) * 16u;
+		col &= 0xffffu;
+		const int i = int(col >> 8);
+		write_color(fb, px, i, i, i, int(col & 0xffu));
+		break;
+	}
+	case FB_I8:
+	{
+		col >>= ((px.color_index & 3u) ^ 3u) * 8u;
+		col &= 0xffu;
+		write_color(fb, px, int(col), int(col), int(col), int(col));
+		break;
+	}
+	default:
+		break;
+	}
+	if (fb.alias)
+		alias_color_to_depth(fb, px);
+}
+
+// Copy pipe: memory_interfacing.h:405-438
+RDP_HD void copy_pixel(const FbView &fb, PixelState &px, uint32_t word)
+{
+	switch (fb.fmt)
+	{
+	case FB_I4:
+		px.r = px.g = px.b = px.a = 0;
+		px.color_dirty = true;
+		break;
+	case FB_I8:
+		word &= 0xffu;
+		write_color(fb, px, int(word), int(word), int(word), int(word));
+		break;
+	case FB_RGBA5551:
+		write_color(fb, px, int((word >> 8) & 0xf8u), int((word >> 3) & 0xf8u), int((word << 2) & 0xf8u), int((word & 1u) * 0xe0u));
+		break;
+	default:
+		break;
+	}
+	if (fb.alias)
+		alias_color_to_depth(fb, px);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Z encode/decode: z_encode.h:28-56
+// ---------------------------------------------------------------------------------------------
+RDP_HD int z_decompress(int z)
+{
+	const int exponent = z >> 11;
+	const int mantissa = z & 0x7ff;
+	const int shift = imax(6 - exponent, 0);
+	const int base = 0x40000 - (0x40000 >> exponent);
+	return (mantissa << shift) + base;
+}
+
+RDP_HD int z_compress(int z)
+{
+	const int inv_z = imax(0x3ffff - z, 1);
+	const int exponent = iclamp(17 - find_msb(uint32_t(inv_z)), 0, 7);
+	const int shift = imax(6 - exponent, 0);
+	const int mantissa = (z >> shift) & 0x7ff;
+	return (exponent << 11) + mantissa;
+}
+
+struct DepthResult
+{
+	bool pass;
+	bool blend_en;
+	bool coverage_wrap;
+	int shift_a, shift_b;
+};
+
+// depth_test.h:41-144
+RDP_HD DepthResult depth_test(int z, int dz, int dz_compressed, int mem_depth, int mem_dz_c, int &coverage,
+                              int mem_coverage, uint32_t bf, int z_mode)
+{
+	DepthResult r;
+	const bool force_blend = (bf & BF_FORCE_BLEND) != 0;
+	const bool aa = (bf & BF_AA) != 0;
+
+	if (bf & BF_Z_COMPARE)
+	{
+		const int memory_z = z_decompress(mem_depth);
+		int memory_dz = 1 << mem_dz_c;
+		const int precision = (mem_depth >> 11) & 0xf;
+		bool coplanar = false;
+
+		r.shift_a = iclamp(dz_compressed - mem_dz_c, 0, 4);
+		r.shift_b = iclamp(mem_dz_c - dz_compressed, 0, 4);
+
+		if (precision < 3)
+		{
+			if (memory_dz != 0x8000)
+				memory_dz = imax(memory_dz << 1, 16 >> precision);
+			else
+			{
+				coplanar = true;
+				memory_dz = 0xffff;
+			}
+		}
+
+		int combined_dz = dz | memory_dz;
+		if (combined_dz != 0)
+			combined_dz = 1 << find_msb(uint32_t(combined_dz));
+		const int combined_dz_ip = combined_dz;
+		combined_dz <<= 3;
+
+		const bool farther = coplanar || ((z + combined_dz) >= memory_z);
+		const bool overflow = (coverage + mem_coverage) >= 8;
+		r.blend_en = force_blend || (!overflow && aa && farther);
+		r.coverage_wrap = overflow;
+
+		const bool max_z = memory_z == 0x3ffff;
+		const bool front = z < memory_z;
+		const bool nearer = coplanar || ((z - combined_dz) <= memory_z);
+
+		switch (z_mode)
+		{
+		case 0: // opaque
+			r.pass = max_z || (overflow ? front : nearer);
+			break;
+		case 1: // interpenetrating
+			if (!front || !farther || !overflow)
+				r.pass = max_z || (overflow ? front : nearer);
+			else
+			{
+				const int sh = imax(find_msb(uint32_t(combined_dz_ip & 0xffff)), 0);
+				const int cvg_coeff = ((memory_z >> sh) - (z >> sh)) & 0xf;
+				coverage = imin((cvg_coeff * coverage) >> 3, 8);
+				r.pass = true;
+			}
+			break;
+		case 2: // transparent
+			r.pass = front || max_z;
+			break;
+		default: // decal
+			r.pass = farther && nearer && !max_z;
+			break;
+		}
+	}
+	else
+	{
+		r.shift_a = 0;
+		r.shift_b = imin(0xf - dz_compressed, 4);
+		const bool overflow = (coverage + mem_coverage) >= 8;
+		r.blend_en = force_blend || (!overflow && aa);
+		r.coverage_wrap = overflow;
+		r.pass = true;
+	}
+	return r;
+}
+
+struct BlendInputs
+{
+	int pr, pg, pb, pa;     // pixel colour (combiner output, or first blender cycle's output)
+	int mr, mg, mb, ma;     // memory colour and coverage (bits 7..5)
+	int shade_alpha;
+};
+
+// One blender cycle: blender.h:55-143
+RDP_HD void blend_cycle(const BlendInputs &in, const PassState &st, const uint8_t *modes, const DepthResult &d,
+                        bool final_cycle, const uint8_t *lut, int &or_, int &og, int &ob)
+{
+	const bool force_blend = (st.blend_flags & BF_FORCE_BLEND) != 0;
+	const bool color_on_cvg = (st.blend_flags & BF_COLOR_ON_CVG) != 0;
+
+	int r1, g1, b1;
+	switch (modes[2])
+	{
+	case 0: r1 = in.pr; g1 = in.pg; b1 = in.pb; break;
+	case 1: r1 = in.mr; g1 = in.mg; b1 = in.mb; break;
+	case 2: r1 = st.blend_color[0]; g1 = st.blend_color[1]; b1 = st.blend_color[2]; break;
+	default: r1 = st.fog_color[0]; g1 = st.fog_color[1]; b1 = st.fog_color[2]; break;
+	}
+
+	if (final_cycle && color_on_cvg && !d.coverage_wrap)
+	{
+		or_ = r1; og = g1; ob = b1;
+		return;
+	}
+
+	int r0, g0, b0;
+	switch (modes[0])
+	{
+	case 0: r0 = in.pr; g0 = in.pg; b0 = in.pb; break;
+	case 1: r0 = in.mr; g0 = in.mg; b0 = in.mb; break;
+	case 2: r0 = st.blend_color[0]; g0 = st.blend_color[1]; b0 = st.blend_color[2]; break;
+	default: r0 = st.fog_color[0]; g0 = st.fog_color[1]; b0 = st.fog_color[2]; break;
+	}
+
+	if (final_cycle && (!d.blend_en || (modes[1] == 0 && modes[3] == 0 && in.pa == 0xff)))
+	{
+		or_ = r0; og = g0; ob = b0;
+		return;
+	}
+
+	int a0, a1;
+	switch (modes[1])
+	{
+	case 0: a0 = in.pa; break;
+	case 1: a0 = st.fog_color[3]; break;
+	case 2: a0 = in.shade_alpha; break;
+	default: a0 = 0; break;
+	}
+	switch (modes[3])
+	{
+	case 0: a1 = ~a0 & 0xff; break;
+	case 1: a1 = in.ma; break;
+	case 2: a1 = 0xff; break;
+	default: a1 = 0; break;
+	}
+
+	a0 >>= 3;
+	a1 >>= 3;
+	if (modes[3] == 1)
+	{
+		a0 = (a0 >> d.shift_a) & 0x3c;
+		a1 = (a1 >> d.shift_b) | 3;
+	}
+
+	int br = r0 * a0 + r1 * (a1 + 1);
+	int bg = g0 * a0 + g1 * (a1 + 1);
+	int bb = b0 * a0 + b1 * (a1 + 1);
+
+	if (!final_cycle || force_blend)
+	{
+		or_ = (br >> 5) & 0xff;
+		og = (bg >> 5) & 0xff;
+		ob = (bb >> 5) & 0xff;
+	}
+	else
+	{
+		// Normalising divider, table-driven exactly like the hardware's odd results.
+		const int sum = (a0 >> 2) + (a1 >> 2) + 1;
+		or_ = lut[(sum << 11) | ((br >> 2) & 0x7ff)];
+		og = lut[(sum << 11) | ((bg >> 2) & 0x7ff)];
+		ob = lut[(sum << 11) | ((bb >> 2) & 0x7ff)];
+	}
+}
+
+// dither.h:30-38
+RDP_HD int dither_channel(int c, int dith)
+{
+	const int rounded = c > 247 ? 255 : ((c & 0xf8) + 8);
+	const int replace = (dith - (c & 7)) >> 31;
+	return (c + ((rounded - c) & replace)) & 0xff;
+}
+
+// coverage.h:51-79
+RDP_HD int blend_coverage(int coverage, int mem_coverage, bool blend_en, int mode)
+{
+	switch (mode)
+	{
+	case 0: return blend_en ? imin(7, mem_coverage + coverage) : ((coverage - 1) & 7);
+	case 1: return (coverage + mem_coverage) & 7;
+	case 2: return 7;
+	default: return mem_coverage;
+	}
+}
+
+// memory_interfacing.h:488-571
+RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup &p, const PassState &st, const Shaded &sh)
+{
+	const uint32_t bf = st.blend_flags;
+	const bool image_read = (bf & BF_IMAGE_READ) != 0;
+	int coverage = sh.coverage;
+
+	// Decode what the blender sees as "memory colour".
+	BlendInputs in;
+	int mem_cvg_bits = image_read ? (px.a & 0xe0) : 0xe0;
+	switch (fb.fmt)
+	{
+	case FB_I4: in.mr = in.mg = in.mb = 0; mem_cvg_bits = 0xe0; break;
+	case FB_I8: in.mr = in.mg = in.mb = px.r; mem_cvg_bits = 0xe0; break;
+	case FB_RGBA5551: in.mr = px.r & 0xf8; in.mg = px.g & 0xf8; in.mb = px.b & 0xf8; break;
+	case FB_IA88: in.mr = in.mg = in.mb = px.r; break;
+	default: in.mr = px.r; in.mg = px.g; in.mb = px.b; break;
+	}
+	in.ma = mem_cvg_bits;
+	const int mem_coverage = mem_cvg_bits >> 5;
+
+	const DepthResult d = depth_test(sh.z, p.dz, p.dz_compressed, px.depth, px.dz, coverage, mem_coverage, bf, st.z_mode);
+	const bool aa = (bf & BF_AA) != 0;
+	if (!d.pass || (aa && coverage == 0))
+		return;
+
+	in.pr = sh.r; in.pg = sh.g; in.pb = sh.b; in.pa = sh.a;
+	in.shade_alpha = sh.shade_alpha;
+
+	int r, g, b;
+	if (bf & BF_TWO_CYCLE)
+	{
+		blend_cycle(in, st, st.blend_modes[0], d, false, fb.blend_lut, r, g, b);
+		in.pr = r; in.pg = g; in.pb = b;
+		blend_cycle(in, st, st.blend_modes[1], d, true, fb.blend_lut, r, g, b);
+	}
+	else
+		blend_cycle(in, st, st.blend_modes[0], d, true, fb.blend_lut, r, g, b);
+
+	if (bf & BF_DITHER)
+	{
+		r = dither_channel(r, sh.dither & 7);
+		g = dither_channel(g, (sh.dither >> 3) & 7);
+		b = dither_channel(b, (sh.dither >> 6) & 7);
+	}
+
+	const int new_coverage = blend_coverage(coverage, mem_coverage, d.blend_en, st.cvg_mode);
+	write_color(fb, px, r & 0xff, g & 0xff, b & 0xff, new_coverage << 5);
+
+	if (bf & BF_Z_UPDATE)
+	{
+		px.depth = z_compress(sh.z);
+		px.dz = p.dz_compressed;
+		px.depth_dirty = true;
+		if (fb.alias)
+			alias_depth_to_color(fb, px);
+	}
+	else if (fb.alias)
+		alias_color_to_depth(fb, px);
+}
+
+// Walk one pixel through one binned primitive (shade, then fill / copy / depth-blend).
+RDP_HD void process_pixel_primitive(const ShadeContext &ctx, const FbView &fb, PixelState &px, int x, int y, uint32_t prim)
+{
+	Shaded sh;
+	if (!shade_pixel(ctx, x, y, prim, sh))
+		return;
+	const PrimSetup &p = ctx.prims[prim];
+	const PassState &st = ctx.states[p.state_id];
+	if (sh.kind == 1)
+		fill_pixel(fb, px, st.fill_color);
+	else if (sh.kind == 2)
+		copy_pixel(fb, px, sh.raw);
+	else
+		depth_blend_pixel(fb, px, p, st, sh);
+}
+
+// Blender divider table (reference data: parallel-rdp/luts.hpp blender_lut, itself generated by the oracle's
+// blender_init_lut, angrylion rdp/blender.c:304).  Regenerated here from the rule rather than stored:
+// entry[(d << 11) | n] = the RDP's 8-bit quotient of n/d with its characteristic truncation.
+void build_blender_lut(uint8_t *lut); // defined in rdp_luts.cpp
+}

@@ -1,0 +1,550 @@
+// rdp_device.cpp -- RDP::CommandProcessor: command word dispatch, RDRAM mirror, timeline.
+//
+// Reference behaviour re-implemented here: parallel-rdp/rdp_device.cpp
+//   construction / buffers :44-162        command dispatch :899-959
+//   state opcodes          :421-711       timeline, idle   :1038-1080
+//   scan-out wrappers      :1082-1182
+// Triangles and rectangles are *not* decoded here: their raw words go to the renderer and are decoded on the GPU.
+#include "rdp_device.hpp"
+#include "rdp_setup.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+using namespace rdpb;
+
+namespace RDP
+{
+CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, size_t rdram_offset, size_t rdram_size_,
+                                   size_t hidden_rdram_size, CommandProcessorFlags flags_)
+	: rdram_size(rdram_size_), hidden_size(hidden_rdram_size), flags(flags_)
+{
+	if (rdram_size == 0 || (rdram_size & (rdram_size - 1)) != 0)
+	{
+		fprintf(stderr, "[rdp-b200] RDRAM size must be a power of two.\n");
+		return;
+	}
+
+	if (flags & (COMMAND_PROCESSOR_FLAG_UPSCALING_2X_BIT | COMMAND_PROCESSOR_FLAG_UPSCALING_4X_BIT |
+	             COMMAND_PROCESSOR_FLAG_UPSCALING_8X_BIT))
+		fprintf(stderr, "[rdp-b200] Internal upscaling is not implemented yet; rendering at native resolution.\n");
+
+	device = rdpb_device_create(config.cuda_device, uint32_t(rdram_size), uint32_t(hidden_rdram_size));
+	if (!device)
+	{
+		fprintf(stderr, "[rdp-b200] Failed to create the CUDA backend device; no fallback exists.\n");
+		return;
+	}
+
+	if (rdram_ptr)
+	{
+		host_rdram = static_cast<uint8_t *>(rdram_ptr) + rdram_offset;
+		host_rdram_registered = rdpb_register_host_memory(device, host_rdram, rdram_size) == 0;
+	}
+	else
+	{
+		owned_rdram.reset(new uint8_t[rdram_size]);
+		memset(owned_rdram.get(), 0, rdram_size);
+		host_rdram = owned_rdram.get();
+		host_rdram_registered = rdpb_register_host_memory(device, host_rdram, rdram_size) == 0;
+	}
+	host_rdram_dirty = true;
+
+	host_hidden.assign(hidden_size, 0x03);
+	rdpb_hidden_fill(device, 0x03);
+	memset(rdpb_tmem_host_ptr(device), 0, kTmemBytes);
+
+	is_supported = renderer.init(device, rdram_size);
+	vi.init(device, rdram_size);
+
+	if (const char *env = getenv("PARALLEL_RDP_SINGLE_THREADED_COMMAND"))
+		single_threaded_processing = strtol(env, nullptr, 0) > 0;
+	else
+		single_threaded_processing = false;
+
+	if (is_supported && !single_threaded_processing)
+		ring.init(this, 64 * 1024);
+}
+
+CommandProcessor::~CommandProcessor()
+{
+	if (device)
+	{
+		idle();
+		ring.shutdown();
+		if (host_rdram_registered)
+			rdpb_unregister_host_memory(device, host_rdram);
+		rdpb_device_destroy(device);
+	}
+}
+
+bool CommandProcessor::device_is_supported() const
+{
+	return is_supported;
+}
+
+void CommandProcessor::set_validation_interface(ValidationInterface *iface)
+{
+	renderer.set_validation_interface(iface);
+}
+
+// ---------------------------------------------------------------------------------------------
+// State opcodes.  Bit layouts are the hardware's.
+// ---------------------------------------------------------------------------------------------
+void CommandProcessor::op_set_color_image(const uint32_t *w)
+{
+	const unsigned fmt = (w[0] >> 21) & 7;
+	const unsigned size = (w[0] >> 19) & 3;
+	const unsigned width = (w[0] & 1023) + 1;
+	const unsigned addr = w[1] & 0xffffff;
+	FBFormat f;
+	switch (size)
+	{
+	case 0: f = FBFormat::I4; break;
+	case 1: f = FBFormat::I8; break;
+	case 2: f = fmt ? FBFormat::IA88 : FBFormat::RGBA5551; break;
+	default: f = FBFormat::RGBA8888; break;
+	}
+	renderer.set_color_framebuffer(addr, width, f);
+}
+
+void CommandProcessor::op_set_mask_image(const uint32_t *w)
+{
+	renderer.set_depth_framebuffer(w[1] & 0xffffff);
+}
+
+void CommandProcessor::op_set_scissor(const uint32_t *w)
+{
+	PassState &r = renderer.registers();
+	r.sc_xlo = (w[0] >> 12) & 0xfff;
+	r.sc_xhi = (w[1] >> 12) & 0xfff;
+	r.sc_ylo = w[0] & 0xfff;
+	r.sc_yhi = w[1] & 0xfff;
+	r.raster_flags &= ~(RF_INTERLACE | RF_KEEP_ODD);
+	if (w[1] & (1u << 25))
+		r.raster_flags |= RF_INTERLACE;
+	if (w[1] & (1u << 24))
+		r.raster_flags |= RF_KEEP_ODD;
+	renderer.mark_state_dirty();
+}
+
+void CommandProcessor::op_set_texture_image(const uint32_t *w)
+{
+	texture_image.fmt = TextureFormat((w[0] >> 21) & 7);
+	texture_image.size = TextureSize((w[0] >> 19) & 3);
+	texture_image.width = (w[0] & 0x3ff) + 1;
+	texture_image.addr = w[1] & 0x00ffffffu;
+}
+
+void CommandProcessor::op_set_tile(const uint32_t *w)
+{
+	TileDesc &t = renderer.registers().tiles[(w[1] >> 24) & 7];
+	t.offset = (w[0] & 511u) << 3;
+	t.stride = ((w[0] >> 9) & 511u) << 3;
+	t.size = (w[0] >> 19) & 3;
+	t.fmt = (w[0] >> 21) & 7;
+	t.palette = (w[1] >> 20) & 15;
+	t.shift_s = w[1] & 15;
+	t.mask_s = (w[1] >> 4) & 15;
+	t.shift_t = (w[1] >> 10) & 15;
+	t.mask_t = (w[1] >> 14) & 15;
+
+	uint8_t f = 0;
+	if (w[1] & (1u << 8)) f |= TF_MIRROR_S;
+	if (w[1] & (1u << 9)) f |= TF_CLAMP_S;
+	if (w[1] & (1u << 18)) f |= TF_MIRROR_T;
+	if (w[1] & (1u << 19)) f |= TF_CLAMP_T;
+
+	// A mask of zero means "clamp always"; masks above 10 behave as 10.
+	if (t.mask_s > 10) t.mask_s = 10;
+	else if (t.mask_s == 0) f |= TF_CLAMP_S;
+	if (t.mask_t > 10) t.mask_t = 10;
+	else if (t.mask_t == 0) f |= TF_CLAMP_T;
+	t.flags = f;
+	renderer.mark_state_dirty();
+}
+
+void CommandProcessor::op_set_tile_size(const uint32_t *w)
+{
+	TileDesc &t = renderer.registers().tiles[(w[1] >> 24) & 7];
+	t.slo = (w[0] >> 12) & 0xfff;
+	t.shi = (w[1] >> 12) & 0xfff;
+	t.tlo = w[0] & 0xfff;
+	t.thi = w[1] & 0xfff;
+	renderer.mark_state_dirty();
+}
+
+void CommandProcessor::op_load(const uint32_t *w, UploadMode mode)
+{
+	LoadTileInfo info = {};
+	info.tex_addr = texture_image.addr;
+	info.tex_width = texture_image.width;
+	info.fmt = texture_image.fmt;
+	info.size = texture_image.size;
+	info.slo = (w[0] >> 12) & 0xfff;
+	info.shi = (w[1] >> 12) & 0xfff;
+	info.tlo = w[0] & 0xfff;
+	info.thi = w[1] & 0xfff;
+	info.mode = mode;
+	renderer.load_tile((w[1] >> 24) & 7, info);
+}
+
+void CommandProcessor::op_set_convert(const uint32_t *w)
+{
+	const uint64_t merged = (uint64_t(w[0]) << 32) | w[1];
+	PassState &r = renderer.registers();
+	const uint32_t k[6] = {
+		uint32_t(merged >> 45) & 0x1ff, uint32_t(merged >> 36) & 0x1ff, uint32_t(merged >> 27) & 0x1ff,
+		uint32_t(merged >> 18) & 0x1ff, uint32_t(merged >> 9) & 0x1ff,  uint32_t(merged >> 0) & 0x1ff,
+	};
+	for (int i = 0; i < 4; i++)
+		r.convert[i] = int16_t(2 * sign_extend<9>(k[i]) + 1);
+	r.convert[4] = int16_t(k[4]);
+	r.convert[5] = int16_t(k[5]);
+	renderer.mark_state_dirty();
+}
+
+void CommandProcessor::op_set_key_gb(const uint32_t *w)
+{
+	PassState &r = renderer.registers();
+	r.key_center[1] = (w[1] >> 24) & 0xff;
+	r.key_scale[1] = (w[1] >> 16) & 0xff;
+	r.key_center[2] = (w[1] >> 8) & 0xff;
+	r.key_scale[2] = w[1] & 0xff;
+	renderer.mark_state_dirty();
+}
+
+void CommandProcessor::op_set_key_r(const uint32_t *w)
+{
+	PassState &r = renderer.registers();
+	r.key_center[0] = (w[1] >> 8) & 0xff;
+	r.key_scale[0] = w[1] & 0xff;
+	renderer.mark_state_dirty();
+}
+
+static void unpack_color(uint8_t *dst, uint32_t c)
+{
+	dst[0] = uint8_t(c >> 24);
+	dst[1] = uint8_t(c >> 16);
+	dst[2] = uint8_t(c >> 8);
+	dst[3] = uint8_t(c);
+}
+
+void CommandProcessor::op_set_prim_color(const uint32_t *w)
+{
+	PassState &r = renderer.registers();
+	r.min_lod = (w[0] >> 8) & 31;
+	r.prim_lod_frac = w[0] & 0xff;
+	unpack_color(r.prim_color, w[1]);
+	renderer.mark_state_dirty();
+}
+
+void CommandProcessor::op_set_prim_depth(const uint32_t *w)
+{
+	PassState &r = renderer.registers();
+	r.prim_depth = int32_t(((w[1] >> 16) & 0x7fffu) << 16);
+	r.prim_dz = uint16_t(w[1] & 0xffff);
+	renderer.mark_state_dirty();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dispatch
+// ---------------------------------------------------------------------------------------------
+void CommandProcessor::enqueue_command_direct(unsigned num_words, const uint32_t *words)
+{
+	const uint32_t op = (words[0] >> 24) & 63u;
+	switch (op)
+	{
+	case OP_META_SIGNAL_TIMELINE:
+	{
+		flush_and_signal();
+		const uint64_t value = words[1] | (uint64_t(words[2]) << 32);
+		readback_gpu_writes(false);
+		rdpb_signal(device, value);
+		signalled_timeline.store(value, std::memory_order_release);
+		break;
+	}
+	case OP_META_FLUSH:
+		flush_and_signal();
+		break;
+	case OP_META_IDLE:
+	{
+		// The producer went quiet: kick recorded work so latency stays bounded (rdp_renderer.cpp:2383-2392).
+		// scanout() drives the renderer from the caller's thread; never race it.
+		std::unique_lock<std::mutex> holder{idle_lock, std::try_to_lock};
+		if (holder.owns_lock())
+			renderer.flush_queues();
+		break;
+	}
+	case OP_META_SET_QUIRKS:
+		quirks.u.words[0] = words[1];
+		break;
+
+	case OP_TRI_FILL: case OP_TRI_FILL_Z: case OP_TRI_TEX: case OP_TRI_TEX_Z:
+	case OP_TRI_SHADE: case OP_TRI_SHADE_Z: case OP_TRI_SHADE_TEX: case OP_TRI_SHADE_TEX_Z:
+	case OP_TEX_RECT: case OP_TEX_RECT_FLIP: case OP_FILL_RECT:
+		sync_host_rdram_to_device();
+		renderer.draw_primitive(words, command_length_words(op));
+		break;
+
+	case OP_SYNC_FULL: flush_and_signal(); break;
+	case OP_SET_KEY_GB: op_set_key_gb(words); break;
+	case OP_SET_KEY_R: op_set_key_r(words); break;
+	case OP_SET_CONVERT: op_set_convert(words); break;
+	case OP_SET_SCISSOR: op_set_scissor(words); break;
+	case OP_SET_PRIM_DEPTH: op_set_prim_depth(words); break;
+	case OP_SET_OTHER_MODES: renderer.set_other_modes(words[0], words[1]); break;
+	case OP_LOAD_TLUT: sync_host_rdram_to_device(); op_load(words, UploadMode::TLUT); break;
+	case OP_SET_TILE_SIZE: op_set_tile_size(words); break;
+	case OP_LOAD_BLOCK: sync_host_rdram_to_device(); op_load(words, UploadMode::Block); break;
+	case OP_LOAD_TILE: sync_host_rdram_to_device(); op_load(words, UploadMode::Tile); break;
+	case OP_SET_TILE: op_set_tile(words); break;
+	case OP_SET_FILL_COLOR: renderer.registers().fill_color = words[1]; renderer.mark_state_dirty(); break;
+	case OP_SET_FOG_COLOR: unpack_color(renderer.registers().fog_color, words[1]); renderer.mark_state_dirty(); break;
+	case OP_SET_BLEND_COLOR: unpack_color(renderer.registers().blend_color, words[1]); renderer.mark_state_dirty(); break;
+	case OP_SET_PRIM_COLOR: op_set_prim_color(words); break;
+	case OP_SET_ENV_COLOR: unpack_color(renderer.registers().env_color, words[1]); renderer.mark_state_dirty(); break;
+	case OP_SET_COMBINE: renderer.set_combine(words[0], words[1]); break;
+	case OP_SET_TEXTURE_IMAGE: op_set_texture_image(words); break;
+	case OP_SET_MASK_IMAGE: op_set_mask_image(words); break;
+	case OP_SET_COLOR_IMAGE: op_set_color_image(words); break;
+	default: break; // Nop, SyncLoad/Pipe/Tile and undefined opcodes
+	}
+	(void)num_words;
+}
+
+void CommandProcessor::enqueue_command_inner(unsigned num_words, const uint32_t *words)
+{
+	if (!is_supported)
+		return;
+	if (single_threaded_processing)
+		enqueue_command_direct(num_words, words);
+	else
+		ring.enqueue_command(num_words, words);
+}
+
+void CommandProcessor::enqueue_command(unsigned num_words, const uint32_t *words)
+{
+	enqueue_command_inner(num_words, words);
+}
+
+void CommandProcessor::enqueue_command_stream(size_t num_words, const uint32_t *words)
+{
+	size_t pos = 0;
+	while (pos < num_words)
+	{
+		const uint32_t len = command_length_words((words[pos] >> 24) & 63u);
+		if (pos + len > num_words)
+			break;
+		enqueue_command_inner(len, words + pos);
+		pos += len;
+	}
+}
+
+void CommandProcessor::set_quirks(const Quirks &q)
+{
+	const uint32_t words[2] = { uint32_t(OP_META_SET_QUIRKS) << 24, q.u.words[0] };
+	enqueue_command_inner(2, words);
+}
+
+// ---------------------------------------------------------------------------------------------
+// RDRAM mirror.  The caller's RDRAM range is the CPU-side copy; the GPU renders into a device buffer.
+// end_write_rdram() marks the CPU copy as newer; it is uploaded before the next GPU access.  Timeline signals
+// copy back what the GPU wrote.  (Replaces VK_EXT_external_memory_host / the reference's incoherent path.)
+// ---------------------------------------------------------------------------------------------
+void CommandProcessor::sync_host_rdram_to_device()
+{
+	if (!host_rdram_dirty)
+		return;
+	if (renderer.has_pending_gpu_writes())
+		readback_gpu_writes(true);
+	rdpb_rdram_write(device, 0, host_rdram, uint32_t(rdram_size), host_rdram_registered ? 0 : 1);
+	host_rdram_dirty = false;
+}
+
+void CommandProcessor::readback_gpu_writes(bool wait)
+{
+	if (renderer.has_pending_gpu_writes())
+	{
+		uint32_t lo, hi;
+		renderer.get_pending_gpu_write_range(lo, hi);
+		lo &= ~63u;
+		hi = (hi + 63u) & ~63u;
+		if (hi > rdram_size)
+			hi = uint32_t(rdram_size);
+		rdpb_rdram_read(device, lo, host_rdram + lo, hi - lo, (wait || !host_rdram_registered) ? 1 : 0);
+		renderer.clear_pending_gpu_writes();
+	}
+	else if (wait)
+		rdpb_sync(device);
+}
+
+void CommandProcessor::flush_and_signal()
+{
+	renderer.flush_queues();
+}
+
+void *CommandProcessor::begin_read_rdram()
+{
+	return host_rdram;
+}
+
+void CommandProcessor::end_write_rdram()
+{
+	// Only meaningful while idle (as in the reference, where it unmaps the buffer).
+	drain_command_ring();
+	host_rdram_dirty = true;
+}
+
+void *CommandProcessor::begin_read_hidden_rdram()
+{
+	drain_command_ring();
+	if (device)
+		rdpb_hidden_read(device, 0, host_hidden.data(), uint32_t(hidden_size), 1);
+	return host_hidden.data();
+}
+
+void CommandProcessor::end_write_hidden_rdram()
+{
+	drain_command_ring();
+	if (device)
+		rdpb_hidden_write(device, 0, host_hidden.data(), uint32_t(hidden_size), 1);
+}
+
+size_t CommandProcessor::get_rdram_size() const
+{
+	return rdram_size;
+}
+
+size_t CommandProcessor::get_hidden_rdram_size() const
+{
+	return hidden_size;
+}
+
+void *CommandProcessor::get_tmem()
+{
+	// TMEM lives in host-mapped pinned memory the GPU reads and writes in place, so this pointer is coherent
+	// whenever the processor is idle (the reference's HOST_VISIBLE_TMEM behaviour).
+	renderer.invalidate_tmem_snapshot();
+	return device ? rdpb_tmem_host_ptr(device) : nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Timeline
+// ---------------------------------------------------------------------------------------------
+void CommandProcessor::drain_command_ring()
+{
+	if (!single_threaded_processing && ring.is_running())
+		ring.drain();
+}
+
+void CommandProcessor::flush()
+{
+	const uint32_t words[1] = { uint32_t(OP_META_FLUSH) << 24 };
+	enqueue_command_inner(1, words);
+}
+
+uint64_t CommandProcessor::signal_timeline()
+{
+	timeline_value++;
+	const uint32_t words[3] = { uint32_t(OP_META_SIGNAL_TIMELINE) << 24, uint32_t(timeline_value), uint32_t(timeline_value >> 32) };
+	enqueue_command_inner(3, words);
+	return timeline_value;
+}
+
+void CommandProcessor::wait_for_timeline(uint64_t index)
+{
+	if (!is_supported)
+		return;
+	// The command thread records the timeline point in stream order; wait for it to be recorded, then for the GPU.
+	while (signalled_timeline.load(std::memory_order_acquire) < index)
+	{
+		if (single_threaded_processing)
+			break;
+		std::this_thread::yield();
+	}
+	rdpb_wait(device, index);
+}
+
+void CommandProcessor::idle()
+{
+	flush();
+	wait_for_timeline(signal_timeline());
+}
+
+void CommandProcessor::begin_frame_context()
+{
+	flush();
+	drain_command_ring();
+}
+
+// ---------------------------------------------------------------------------------------------
+// VI
+// ---------------------------------------------------------------------------------------------
+void CommandProcessor::set_vi_register(VIRegister reg, uint32_t value)
+{
+	vi.set_vi_register(reg, value);
+}
+
+void CommandProcessor::begin_vi_register_per_scanline(VideoInterface::PerScanlineRegisterFlags f)
+{
+	vi.begin_vi_register_per_scanline(f);
+}
+
+void CommandProcessor::set_vi_register_for_scanline(VideoInterface::PerScanlineRegisterBits reg, uint32_t value)
+{
+	vi.set_vi_register_for_scanline(reg, value);
+}
+
+void CommandProcessor::latch_vi_register_for_scanline(unsigned vi_line)
+{
+	vi.latch_vi_register_for_scanline(vi_line);
+}
+
+void CommandProcessor::end_vi_register_per_scanline()
+{
+	vi.end_vi_register_per_scanline();
+}
+
+ScanoutImage CommandProcessor::scanout(const ScanoutOptions &opts)
+{
+	if (!is_supported)
+		return {};
+	drain_command_ring();
+	// The command thread is idle now, so the renderer can be driven from this thread.
+	std::lock_guard<std::mutex> holder{idle_lock};
+	renderer.flush_queues();
+	sync_host_rdram_to_device();
+	return vi.scanout(opts);
+}
+
+void CommandProcessor::scanout_async_buffer(VIScanoutBuffer &buffer, const ScanoutOptions &opts)
+{
+	ScanoutImage img = scanout(opts);
+	if (!img)
+	{
+		buffer.width = buffer.height = 0;
+		buffer.pixels.clear();
+		return;
+	}
+	buffer.width = img.width;
+	buffer.height = img.height;
+	buffer.pixels.resize(size_t(img.width) * img.height);
+	rdpb_vi_read_output(device, buffer.pixels.data(), img.width, img.height, 1);
+}
+
+void CommandProcessor::scanout_sync(std::vector<RGBA> &colors, unsigned &width, unsigned &height, const ScanoutOptions &opts)
+{
+	ScanoutImage img = scanout(opts);
+	if (!img)
+	{
+		width = height = 0;
+		colors.clear();
+		return;
+	}
+	width = img.width;
+	height = img.height;
+	colors.resize(size_t(width) * height);
+	rdpb_vi_read_output(device, colors.data(), width, height, 1);
+}
+}

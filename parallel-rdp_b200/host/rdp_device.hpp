@@ -1,0 +1,168 @@
+// rdp_device.hpp -- RDP::CommandProcessor, the drop-in boundary.
+//
+// Same public surface as the reference class (parallel-rdp/rdp_device.hpp:111-197): same method names,
+// argument meaning, ownership and error behaviour.  The two Vulkan-typed spots change:
+//   * the constructor takes a CUDA device selection (RDP::DeviceConfig) instead of Vulkan::Device&,
+//   * scanout() returns RDP::ScanoutImage {device pointer, width, height} instead of Vulkan::ImageHandle,
+//     and VIScanoutBuffer holds a host vector instead of Vulkan::Buffer + Fence.
+// rdram_ptr is borrowed (caller frees after destroying the processor); hidden RDRAM and TMEM are owned here.
+// No exceptions, no error codes: failure => device_is_supported() == false plus a line on stderr.
+#pragma once
+#include "command_ring.hpp"
+#include "rdp_renderer.hpp"
+#include "video_interface.hpp"
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+namespace RDP
+{
+struct RGBA
+{
+	uint8_t r, g, b, a;
+};
+
+enum CommandProcessorFlagBits
+{
+	COMMAND_PROCESSOR_FLAG_HOST_VISIBLE_HIDDEN_RDRAM_BIT = 1 << 0,
+	COMMAND_PROCESSOR_FLAG_HOST_VISIBLE_TMEM_BIT = 1 << 1,
+	COMMAND_PROCESSOR_FLAG_UPSCALING_2X_BIT = 1 << 2,
+	COMMAND_PROCESSOR_FLAG_UPSCALING_4X_BIT = 1 << 3,
+	COMMAND_PROCESSOR_FLAG_UPSCALING_8X_BIT = 1 << 4,
+	COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_READ_BACK_BIT = 1 << 5,
+	COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_DITHER_BIT = 1 << 6
+};
+using CommandProcessorFlags = uint32_t;
+
+struct Quirks
+{
+	Quirks()
+	{
+		u.options.native_resolution_tex_rect = true;
+		u.options.native_texture_lod = false;
+	}
+	void set_native_resolution_tex_rect(bool enable) { u.options.native_resolution_tex_rect = enable; }
+	void set_native_texture_lod(bool enable) { u.options.native_texture_lod = enable; }
+
+	union
+	{
+		struct Opts
+		{
+			bool native_resolution_tex_rect;
+			bool native_texture_lod;
+		} options;
+		uint32_t words[1];
+	} u;
+};
+
+// Replaces Vulkan::Device& in the constructor.
+struct DeviceConfig
+{
+	int cuda_device = 0;
+};
+
+class CommandProcessor
+{
+public:
+	CommandProcessor(const DeviceConfig &device, void *rdram_ptr, size_t rdram_offset, size_t rdram_size,
+	                 size_t hidden_rdram_size, CommandProcessorFlags flags);
+	~CommandProcessor();
+	CommandProcessor(const CommandProcessor &) = delete;
+	void operator=(const CommandProcessor &) = delete;
+
+	void set_validation_interface(ValidationInterface *iface);
+	bool device_is_supported() const;
+
+	// Synchronization.
+	void flush();
+	uint64_t signal_timeline();
+	void wait_for_timeline(uint64_t index);
+	void idle();
+	void begin_frame_context();
+
+	// Queues up state and drawing commands.
+	void enqueue_command(unsigned num_words, const uint32_t *words);
+	void enqueue_command_direct(unsigned num_words, const uint32_t *words);
+	// Extension: a packed stream of back-to-back commands (dump replay, benchmarking).
+	void enqueue_command_stream(size_t num_words, const uint32_t *words);
+
+	void set_quirks(const Quirks &quirks);
+
+	// Interact with memory.  Pointers are valid while the processor is idle.
+	void *begin_read_rdram();
+	void end_write_rdram();
+	void *begin_read_hidden_rdram();
+	void end_write_hidden_rdram();
+	size_t get_rdram_size() const;
+	size_t get_hidden_rdram_size() const;
+	void *get_tmem();
+
+	void set_vi_register(VIRegister reg, uint32_t value);
+
+	ScanoutImage scanout(const ScanoutOptions &opts = {});
+	void scanout_sync(std::vector<RGBA> &colors, unsigned &width, unsigned &height, const ScanoutOptions &opts = {});
+	void scanout_async_buffer(VIScanoutBuffer &buffer, const ScanoutOptions &opts = {});
+
+	void begin_vi_register_per_scanline(VideoInterface::PerScanlineRegisterFlags flags);
+	void set_vi_register_for_scanline(VideoInterface::PerScanlineRegisterBits reg, uint32_t value);
+	void latch_vi_register_for_scanline(unsigned vi_line);
+	void end_vi_register_per_scanline();
+
+	// Introspection for benchmarks / tests (not part of the reference surface).
+	rdpb_device *get_backend_device() { return device; }
+	uint64_t get_primitive_counter() const { return renderer.get_primitive_counter(); }
+	uint64_t get_pass_counter() const { return renderer.get_pass_counter(); }
+
+private:
+	rdpb_device *device = nullptr;
+	uint8_t *host_rdram = nullptr;      // borrowed (or owned_rdram)
+	std::unique_ptr<uint8_t[]> owned_rdram;
+	bool host_rdram_registered = false;
+	std::vector<uint8_t> host_hidden;
+	size_t rdram_size = 0;
+	size_t hidden_size = 0;
+	CommandProcessorFlags flags = 0;
+	bool is_supported = false;
+	bool single_threaded_processing = true;
+
+	std::atomic<bool> host_rdram_dirty{true}; // CPU wrote RDRAM since the last upload
+	std::mutex idle_lock;
+
+	Renderer renderer;
+	VideoInterface vi;
+	CommandRing ring;
+
+	struct
+	{
+		uint32_t addr = 0, width = 0;
+		TextureFormat fmt = TextureFormat::RGBA;
+		TextureSize size = TextureSize::Bpp4;
+	} texture_image;
+
+	uint64_t timeline_value = 0;
+	std::atomic<uint64_t> signalled_timeline{0};
+	Quirks quirks;
+
+	void enqueue_command_inner(unsigned num_words, const uint32_t *words);
+	void drain_command_ring();
+	void sync_host_rdram_to_device();
+	void readback_gpu_writes(bool wait);
+	void flush_and_signal();
+
+	void op_set_color_image(const uint32_t *w);
+	void op_set_mask_image(const uint32_t *w);
+	void op_set_scissor(const uint32_t *w);
+	void op_set_texture_image(const uint32_t *w);
+	void op_set_tile(const uint32_t *w);
+	void op_set_tile_size(const uint32_t *w);
+	void op_load(const uint32_t *w, UploadMode mode);
+	void op_set_convert(const uint32_t *w);
+	void op_set_key_gb(const uint32_t *w);
+	void op_set_key_r(const uint32_t *w);
+	void op_set_prim_color(const uint32_t *w);
+	void op_set_prim_depth(const uint32_t *w);
+
+	friend class CommandRing;
+};
+}

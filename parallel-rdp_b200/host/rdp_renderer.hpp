@@ -1,0 +1,139 @@
+// rdp_renderer.hpp -- render-pass recording and submission (host half of the hot path).
+//
+// Role mirrors parallel-rdp/rdp_renderer.{hpp,cpp}: tracks RDP state, batches primitives into render passes,
+// applies the semantic flush rules, decomposes texture loads and sequences the GPU stages.  What differs by
+// design: primitives are forwarded as raw command words (decode runs on the GPU), state is snapshotted by a
+// dirty flag instead of memcmp-searched caches, and a pass holds up to 16 Ki primitives.
+#pragma once
+#include "rdp_b200_backend.h"
+#include "rdp_types.h"
+#include <stddef.h>
+#include <stdint.h>
+
+namespace RDP
+{
+enum class FBFormat : uint32_t
+{
+	I4 = 0,
+	I8 = 1,
+	RGBA5551 = 2,
+	IA88 = 3,
+	RGBA8888 = 4
+};
+
+enum class TextureSize : uint8_t
+{
+	Bpp4 = 0,
+	Bpp8 = 1,
+	Bpp16 = 2,
+	Bpp32 = 3
+};
+
+enum class TextureFormat : uint8_t
+{
+	RGBA = 0,
+	YUV = 1,
+	CI = 2,
+	IA = 3,
+	I = 4
+};
+
+enum class UploadMode : uint32_t
+{
+	Tile = 0,
+	TLUT = 1,
+	Block = 2
+};
+
+struct LoadTileInfo
+{
+	uint32_t tex_addr;
+	uint32_t tex_width;
+	TextureFormat fmt;
+	TextureSize size;
+	uint32_t slo, tlo, shi, thi;
+	UploadMode mode;
+};
+
+// Conditions under which real hardware locks up (reference: rdp_renderer.hpp:75-95).
+enum class ValidationError
+{
+	Fill4bpp,
+	FillDepthTest,
+	FillDepthWrite,
+	FillImageReadEnable,
+	Copy32bpp,
+	LoadTile4bpp,
+	InvalidMultilineLoadTlut
+};
+
+struct ValidationInterface
+{
+	virtual ~ValidationInterface() = default;
+	// May be called from the command thread.
+	virtual void report_rdp_crash(ValidationError err, const char *msg) = 0;
+};
+
+class Renderer
+{
+public:
+	bool init(rdpb_device *device, size_t rdram_size);
+	void set_validation_interface(ValidationInterface *iface) { validation = iface; }
+
+	// Register state.  Callers mutate `regs` then call mark_state_dirty().
+	rdpb::PassState &registers() { return regs; }
+	void mark_state_dirty() { state_dirty = true; }
+	void set_other_modes(uint32_t w0, uint32_t w1);
+	void set_combine(uint32_t w0, uint32_t w1);
+
+	void set_color_framebuffer(uint32_t addr, uint32_t width, FBFormat fmt);
+	void set_depth_framebuffer(uint32_t addr);
+
+	void draw_primitive(const uint32_t *words, unsigned num_words);
+	void load_tile(uint32_t tile, const LoadTileInfo &info);
+
+	void flush_queues();
+	bool has_pending_gpu_writes() const { return gpu_dirty_hi > gpu_dirty_lo; }
+	void get_pending_gpu_write_range(uint32_t &lo, uint32_t &hi) const { lo = gpu_dirty_lo; hi = gpu_dirty_hi; }
+	void clear_pending_gpu_writes() { gpu_dirty_lo = ~0u; gpu_dirty_hi = 0; }
+	void invalidate_tmem_snapshot() { tmem_snapshot_valid = false; }
+
+	uint64_t get_primitive_counter() const { return base_primitive_index; }
+	uint64_t get_pass_counter() const { return pass_counter; }
+
+private:
+	rdpb_device *device = nullptr;
+	ValidationInterface *validation = nullptr;
+	size_t rdram_size = 0;
+
+	rdpb::PassState regs = {};
+	bool state_dirty = true;
+	uint32_t other_modes[2] = {};
+
+	struct
+	{
+		uint32_t addr = 0, depth_addr = 0, width = 0;
+		FBFormat fmt = FBFormat::I4;
+		uint32_t deduced_height = 0;
+		bool color_write_pending = false, depth_write_pending = false;
+	} fb;
+
+	// Pass being recorded.
+	rdpb_pass_buffers pass = {};
+	bool pass_open = false;
+	uint32_t num_words = 0, num_prims = 0, num_states = 0, num_uploads = 0, num_spans = 0;
+	uint32_t base_primitive_index = 0;
+	uint64_t pass_counter = 0;
+	bool tmem_snapshot_valid = false;
+
+	uint32_t gpu_dirty_lo = ~0u, gpu_dirty_hi = 0;
+
+	void ensure_pass();
+	void snapshot_state();
+	void finalize_state(rdpb::PassState &st) const;
+	void validate_draw_state() const;
+	bool tmem_upload_needs_flush(uint32_t addr) const;
+	void load_tile_iteration(uint32_t tile, const LoadTileInfo &info, uint32_t tmem_offset);
+	void note_gpu_write(uint32_t addr, uint32_t bytes);
+};
+}

@@ -1,0 +1,260 @@
+// tests/hostsim/backend_cpu.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// A CPU build of the *same* device functions the CUDA kernels execute (parallel-rdp_b200/csrc/*.cuh compiled
+// with g++), behind the same backend C-ABI (include/rdp_b200_backend.h).  It exists so the host logic and the
+// integer pixel pipeline can be diffed against the Angrylion oracle in a container without a GPU
+// (`pytest -m "not gpu"`).  It is never linked into librdp_b200.so and is not a fallback: the product
+// library fails loudly when CUDA is unavailable.
+#include "rdp_b200_backend.h"
+#include "rdp_pass.cuh"
+#include "rdp_vi.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace rdpb;
+
+struct rdpb_device
+{
+	uint32_t rdram_size = 0, hidden_size = 0;
+	std::vector<uint8_t> rdram, hidden, tmem, tmem_instances, blend_lut, gamma_lut;
+	std::vector<uint32_t> words;
+	std::vector<PrimRecord> records;
+	std::vector<PassState> states;
+	std::vector<TmemUpload> uploads;
+	std::vector<PrimSetup> prims;
+	std::vector<Span> spans;
+	std::vector<uint32_t> fine, coarse;
+	rdpb_pass_counts counts = {};
+	std::vector<uint32_t> vi_stage[3];
+	std::vector<uint32_t> vi_out, vi_prev;
+	uint64_t launches = 0;
+	std::string error;
+
+	PassBuffers buffers()
+	{
+		PassBuffers b;
+		b.words = words.data();
+		b.records = records.data();
+		b.states = states.data();
+		b.uploads = uploads.data();
+		b.prims = prims.data();
+		b.spans = spans.data();
+		b.fine_mask = fine.data();
+		b.coarse_mask = coarse.data();
+		b.tmem = tmem.data();
+		b.tmem_instances = tmem_instances.data();
+		b.rdram = rdram.data();
+		b.hidden = hidden.data();
+		b.blend_lut = blend_lut.data();
+		return b;
+	}
+};
+
+extern "C" {
+
+const char *rdpb_backend_name(void) { return "hostsim-cpu (test only)"; }
+
+rdpb_device *rdpb_device_create(int, uint32_t rdram_size, uint32_t hidden_size)
+{
+	auto *d = new rdpb_device;
+	d->rdram_size = rdram_size;
+	d->hidden_size = hidden_size;
+	d->rdram.assign(rdram_size, 0);
+	d->hidden.assign(hidden_size, 0);
+	d->tmem.assign(kTmemBytes, 0);
+	d->tmem_instances.assign(size_t(kTmemBytes) * (kMaxUploadsPerPass + 1), 0);
+	d->blend_lut.resize(0x8000);
+	build_blender_lut(d->blend_lut.data());
+	d->gamma_lut.resize(256 + 256 * 64);
+	build_gamma_lut(d->gamma_lut.data());
+	d->words.resize(kMaxPassWords);
+	d->records.resize(kMaxPrimsPerPass);
+	d->states.resize(kMaxStatesPerPass);
+	d->uploads.resize(kMaxUploadsPerPass);
+	d->prims.resize(kMaxPrimsPerPass);
+	d->spans.resize(kMaxSpansPerPass);
+	d->fine.assign(size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 32), 0);
+	d->coarse.assign(size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 1024), 0);
+	return d;
+}
+
+void rdpb_device_destroy(rdpb_device *dev) { delete dev; }
+const char *rdpb_last_error(rdpb_device *dev) { return dev->error.c_str(); }
+int rdpb_register_host_memory(rdpb_device *, void *, size_t) { return 0; }
+int rdpb_unregister_host_memory(rdpb_device *, void *) { return 0; }
+
+int rdpb_rdram_write(rdpb_device *dev, uint32_t offset, const void *src, uint32_t size, int)
+{
+	memcpy(dev->rdram.data() + offset, src, size);
+	return 0;
+}
+int rdpb_rdram_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size, int)
+{
+	memcpy(dst, dev->rdram.data() + offset, size);
+	return 0;
+}
+int rdpb_hidden_write(rdpb_device *dev, uint32_t offset, const void *src, uint32_t size, int)
+{
+	memcpy(dev->hidden.data() + offset, src, size);
+	return 0;
+}
+int rdpb_hidden_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size, int)
+{
+	memcpy(dst, dev->hidden.data() + offset, size);
+	return 0;
+}
+int rdpb_hidden_fill(rdpb_device *dev, uint8_t value)
+{
+	memset(dev->hidden.data(), value, dev->hidden.size());
+	return 0;
+}
+void *rdpb_tmem_host_ptr(rdpb_device *dev) { return dev->tmem.data(); }
+void *rdpb_rdram_device_ptr(rdpb_device *dev) { return dev->rdram.data(); }
+void *rdpb_hidden_device_ptr(rdpb_device *dev) { return dev->hidden.data(); }
+
+int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
+{
+	out->words = dev->words.data();
+	out->records = dev->records.data();
+	out->states = dev->states.data();
+	out->uploads = dev->uploads.data();
+	return 0;
+}
+
+int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *counts)
+{
+	dev->counts = *counts;
+	return 0;
+}
+
+int rdpb_launch_tmem_update(rdpb_device *dev, uint32_t num_uploads)
+{
+	PassBuffers b = dev->buffers();
+	for (int slot = 0; slot < int(kTmemBytes / 2); slot++)
+		pass_tmem_word(b, num_uploads, dev->rdram_size, slot);
+	dev->launches++;
+	return 0;
+}
+
+int rdpb_launch_prim_setup(rdpb_device *dev, uint32_t num_prims)
+{
+	PassBuffers b = dev->buffers();
+	for (uint32_t i = 0; i < num_prims; i++)
+		pass_setup_prim(b, i);
+	dev->launches++;
+	return 0;
+}
+
+int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
+{
+	const FbInfo fb = *static_cast<const FbInfo *>(fb_info);
+	PassBuffers b = dev->buffers();
+	auto or_fn = [](uint32_t *p, uint32_t v) { *p |= v; };
+	for (uint32_t i = 0; i < fb.num_prims; i++)
+	{
+		const PrimSetup &p = b.prims[i];
+		if (p.flags & SF_NO_PIXELS)
+			continue;
+		for (int y = p.line_lo; y <= p.line_hi + 1; y++)
+		{
+			int lo, hi;
+			pass_span_line(b, fb, p, y, lo, hi);
+			if (lo <= hi)
+				pass_bin_row(fb, i, y >> 3, lo, hi, or_fn, b.fine_mask, b.coarse_mask);
+		}
+	}
+	dev->launches++;
+	return 0;
+}
+
+int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info)
+{
+	const FbInfo fb = *static_cast<const FbInfo *>(fb_info);
+	PassBuffers b = dev->buffers();
+	for (uint32_t ty = 0; ty < fb.tiles_y; ty++)
+	{
+		for (uint32_t tx = 0; tx < fb.tiles_x; tx++)
+		{
+			const uint32_t tile = ty * fb.tiles_x + tx;
+			bool any = false;
+			for (uint32_t cw = 0; cw < fb.coarse_stride; cw++)
+				any = any || b.coarse_mask[size_t(tile) * fb.coarse_stride + cw] != 0;
+			if (!any)
+				continue;
+			for (int ly = 0; ly < 8; ly++)
+			{
+				for (int lx = 0; lx < 8; lx++)
+				{
+					const int x = int(tx) * 8 + lx, y = int(ty) * 8 + ly;
+					if (x >= int(fb.width) || y >= int(fb.height))
+						continue;
+					FbView view;
+					PixelState px;
+					pass_pixel_begin(b, fb, view, px, x, y);
+					pass_pixel_walk(b, fb, view, px, x, y, tile);
+					pass_pixel_end(fb, view, px, x, y);
+				}
+			}
+			pass_tile_clear_masks(b, fb, tile);
+		}
+	}
+	dev->launches++;
+	return 0;
+}
+
+int rdpb_pass_end(rdpb_device *) { return 0; }
+
+int rdpb_launch_vi_scanout(rdpb_device *dev, const rdpb_vi_params *params)
+{
+	ViContext vi;
+	vi.rdram = dev->rdram.data();
+	vi.hidden = dev->hidden.data();
+	vi.rdram_size = dev->rdram_size;
+	vi.gamma_lut = dev->gamma_lut.data();
+	vi.regs = *static_cast<const ViRegs *>(params->regs);
+	vi.lines = static_cast<const ViLine *>(params->lines);
+	vi.flags = params->flags;
+	vi.frame_count = params->frame_count;
+	vi.out_width = params->width;
+	vi.out_height = params->height;
+
+	const size_t stage_pixels = size_t(kViStageWidth) * kViStageHeight;
+	for (auto &s : dev->vi_stage)
+		s.assign(stage_pixels * 2, 0);
+	const size_t out_pixels = size_t(params->width) * params->height;
+	if (dev->vi_out.size() != out_pixels)
+	{
+		dev->vi_out.assign(out_pixels, 0);
+		dev->vi_prev.assign(out_pixels, 0);
+	}
+	std::swap(dev->vi_out, dev->vi_prev);
+
+	vi.stage0 = dev->vi_stage[0].data();
+	vi.stage1 = dev->vi_stage[1].data();
+	vi.stage2 = dev->vi_stage[2].data();
+	vi.out = dev->vi_out.data();
+	vi.prev = dev->vi_prev.data();
+
+	vi_run_all_stages_serial(vi);
+	dev->launches += 4;
+	return 0;
+}
+
+void *rdpb_vi_output_device_ptr(rdpb_device *dev) { return dev->vi_out.data(); }
+
+int rdpb_vi_read_output(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, int)
+{
+	memcpy(dst, dev->vi_out.data(), size_t(width) * height * 4);
+	return 0;
+}
+
+int rdpb_signal(rdpb_device *, uint64_t) { return 0; }
+int rdpb_wait(rdpb_device *, uint64_t) { return 0; }
+int rdpb_sync(rdpb_device *) { return 0; }
+void *rdpb_stream(rdpb_device *) { return nullptr; }
+uint64_t rdpb_launch_count(rdpb_device *dev) { return dev->launches; }
+}
