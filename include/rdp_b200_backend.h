@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct rdpb_device rdpb_device;
 
-/* Host-visible staging area for the pass being recorded.  Pointers stay valid until rdpb_pass_submit(). */
+/* Host-visible staging area for the pass being recorded.  Pointers stay valid until the pass is uploaded. */
 typedef struct rdpb_pass_buffers
 {
 	uint32_t *words;   /* raw RDP command words of the primitives, capacity rdpb::kMaxPassWords */

@@ -1,0 +1,530 @@
+// backend_cuda.cu -- the product backend: CUDA kernels for sm_100a and the C-ABI of include/rdp_b200_backend.h.
+//
+// Kernels (one per render-pass stage, launched in stream order; see rdp_pass.cuh for the per-thread bodies):
+//   k_tmem_update  2048 threads, one per TMEM word            (replaces shaders/tmem_update.comp)
+//   k_prim_setup   one thread per primitive                    (replaces CPU decode, rdp_device.cpp:268-419)
+//   k_span_bin     one warp per primitive, lanes = scanlines   (replaces span_setup.comp + tile_binning_combined.comp;
+//                  warp shuffles reduce each 8-line tile row's X range, lanes then atomicOr the tile masks)
+//   k_tiles        one 8x8 block per tile, one thread per pixel (replaces rasterizer.comp + depth_blend.comp, fused)
+//   k_vi_*         VI scan-out stages                          (replaces extract_vram.comp, vi_fetch/divot/scale.frag)
+// Nothing here is a dense contraction, so no tensor-core path exists; the work is integer ALU + coalesced
+// RDRAM loads/stores.  There is no CPU fallback: creation fails when no CUDA device is usable.
+#include "rdp_b200_backend.h"
+#include "rdp_pass.cuh"
+#include "rdp_vi.cuh"
+
+#include <cuda_runtime.h>
+#include <deque>
+#include <mutex>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <utility>
+
+using namespace rdpb;
+
+namespace
+{
+constexpr unsigned kStagingSlots = 4;
+
+struct StagingLayout
+{
+	static constexpr size_t words_off = 0;
+	static constexpr size_t records_off = words_off + size_t(kMaxPassWords) * 4;
+	static constexpr size_t states_off = records_off + size_t(kMaxPrimsPerPass) * sizeof(PrimRecord);
+	static constexpr size_t uploads_off = states_off + size_t(kMaxStatesPerPass) * sizeof(PassState);
+	static constexpr size_t total = uploads_off + size_t(kMaxUploadsPerPass) * sizeof(TmemUpload);
+};
+
+__global__ void k_tmem_update(PassBuffers b, uint32_t num_uploads, uint32_t rdram_size)
+{
+	const int slot = int(blockIdx.x * blockDim.x + threadIdx.x);
+	if (slot < int(kTmemBytes / 2))
+		pass_tmem_word(b, num_uploads, rdram_size, slot);
+}
+
+__global__ void k_prim_setup(PassBuffers b, uint32_t num_prims)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < num_prims)
+		pass_setup_prim(b, i);
+}
+
+struct AtomicOr
+{
+	__device__ void operator()(uint32_t *p, uint32_t v) const { atomicOr(p, v); }
+};
+
+__global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
+{
+	const uint32_t prim = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = int(threadIdx.x & 31u);
+	if (prim >= fb.num_prims)
+		return;
+	const PrimSetup &p = b.prims[prim];
+	if (p.flags & SF_NO_PIXELS)
+		return;
+
+	const int first = int(p.line_lo) & ~7; // keep 8-lane groups aligned with tile rows
+	const int last = int(p.line_hi) + 1;
+	const int sub = lane & 7;
+	for (int y0 = first; y0 <= last; y0 += 32)
+	{
+		const int y = y0 + lane;
+		int lo, hi;
+		pass_span_line(b, fb, p, y, lo, hi);
+		int mn = lo <= hi ? lo : 0x7fffffff;
+		int mx = lo <= hi ? hi : -1;
+#pragma unroll
+		for (int off = 1; off < 8; off <<= 1)
+		{
+			mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+			mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+		}
+		if (mn <= mx)
+		{
+			// The eight lanes of a tile row split the row's tiles between them.
+			const uint32_t group = prim >> 5, bit = 1u << (prim & 31u);
+			const uint32_t cgroup = group >> 5, cbit = 1u << (group & 31u);
+			const uint32_t row = uint32_t(y >> 3) * fb.tiles_x;
+			for (int tx = (mn >> 3) + sub; tx <= (mx >> 3); tx += 8)
+			{
+				const size_t tile = row + uint32_t(tx);
+				atomicOr(&b.fine_mask[tile * fb.mask_stride + group], bit);
+				atomicOr(&b.coarse_mask[tile * fb.coarse_stride + cgroup], cbit);
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(64) k_tiles(PassBuffers b, FbInfo fb)
+{
+	const uint32_t tile = blockIdx.y * fb.tiles_x + blockIdx.x;
+	const uint32_t *coarse = b.coarse_mask + size_t(tile) * fb.coarse_stride;
+	uint32_t any = 0;
+	for (uint32_t cw = 0; cw < fb.coarse_stride; cw++)
+		any |= coarse[cw];
+	if (!any)
+		return;
+
+	const int x = int(blockIdx.x * kTileW + (threadIdx.x & 7u));
+	const int y = int(blockIdx.y * kTileH + (threadIdx.x >> 3));
+	if (x < int(fb.width) && y < int(fb.height))
+	{
+		FbView view;
+		PixelState px;
+		pass_pixel_begin(b, fb, view, px, x, y);
+		pass_pixel_walk(b, fb, view, px, x, y, tile);
+		pass_pixel_end(fb, view, px, x, y);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+		pass_tile_clear_masks(b, fb, tile);
+}
+}
+
+struct rdpb_device
+{
+	int ordinal = 0;
+	cudaStream_t stream = nullptr;
+	uint32_t rdram_size = 0, hidden_size = 0;
+
+	uint8_t *rdram = nullptr, *hidden = nullptr;
+	uint8_t *tmem_host = nullptr, *tmem_dev = nullptr; // same mapped pinned allocation
+	uint8_t *tmem_instances = nullptr;
+	uint8_t *blend_lut = nullptr, *gamma_lut = nullptr;
+
+	uint8_t *staging[kStagingSlots] = {};
+	cudaEvent_t staging_done[kStagingSlots] = {};
+	bool staging_in_flight[kStagingSlots] = {};
+	unsigned staging_index = 0;
+
+	uint32_t *d_words = nullptr;
+	PrimRecord *d_records = nullptr;
+	PassState *d_states = nullptr;
+	TmemUpload *d_uploads = nullptr;
+	PrimSetup *d_prims = nullptr;
+	Span *d_spans = nullptr;
+	uint32_t *d_fine = nullptr, *d_coarse = nullptr;
+
+	uint32_t *vi_stage[3] = {};
+	uint32_t *vi_out[2] = {};
+	unsigned vi_out_index = 0;
+	uint32_t vi_out_pixels = 0;
+	ViRegs *d_vi_regs = nullptr;
+	ViLine *d_vi_lines = nullptr;
+	uint8_t *vi_host_staging = nullptr;
+
+	std::mutex timeline_lock;
+	std::deque<std::pair<uint64_t, cudaEvent_t>> timeline;
+	std::deque<cudaEvent_t> free_events;
+
+	uint64_t launches = 0;
+	std::string error;
+
+	PassBuffers buffers() const
+	{
+		PassBuffers b;
+		b.words = d_words;
+		b.records = d_records;
+		b.states = d_states;
+		b.uploads = d_uploads;
+		b.prims = d_prims;
+		b.spans = d_spans;
+		b.fine_mask = d_fine;
+		b.coarse_mask = d_coarse;
+		b.tmem = tmem_dev;
+		b.tmem_instances = tmem_instances;
+		b.rdram = rdram;
+		b.hidden = hidden;
+		b.blend_lut = blend_lut;
+		return b;
+	}
+};
+
+static bool check(rdpb_device *dev, cudaError_t err, const char *what)
+{
+	if (err == cudaSuccess)
+		return true;
+	char buf[512];
+	snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(err));
+	if (dev)
+		dev->error = buf;
+	fprintf(stderr, "[rdp-b200] CUDA error: %s\n", buf);
+	return false;
+}
+
+#define CK(call) do { if (!check(dev, (call), #call)) return -1; } while (0)
+
+extern "C" {
+
+const char *rdpb_backend_name(void) { return "cuda-sm_100a"; }
+
+rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t hidden_size)
+{
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+	{
+		fprintf(stderr, "[rdp-b200] No CUDA device available.\n");
+		return nullptr;
+	}
+	if (cuda_ordinal < 0 || cuda_ordinal >= count)
+	{
+		fprintf(stderr, "[rdp-b200] CUDA device %d out of range (%d devices).\n", cuda_ordinal, count);
+		return nullptr;
+	}
+
+	auto *dev = new rdpb_device;
+	dev->ordinal = cuda_ordinal;
+	dev->rdram_size = rdram_size;
+	dev->hidden_size = hidden_size;
+
+	bool ok = true;
+	auto need = [&](cudaError_t e, const char *what) { ok = ok && check(dev, e, what); };
+
+	need(cudaSetDevice(cuda_ordinal), "cudaSetDevice");
+	need(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	need(cudaMalloc(&dev->rdram, rdram_size), "cudaMalloc rdram");
+	need(cudaMalloc(&dev->hidden, hidden_size), "cudaMalloc hidden");
+	need(cudaHostAlloc(&dev->tmem_host, kTmemBytes, cudaHostAllocMapped), "cudaHostAlloc tmem");
+	if (ok)
+		need(cudaHostGetDevicePointer(&dev->tmem_dev, dev->tmem_host, 0), "cudaHostGetDevicePointer tmem");
+	need(cudaMalloc(&dev->tmem_instances, size_t(kTmemBytes) * (kMaxUploadsPerPass + 1)), "cudaMalloc tmem instances");
+	need(cudaMalloc(&dev->blend_lut, 0x8000), "cudaMalloc blend lut");
+	need(cudaMalloc(&dev->gamma_lut, 256 + 256 * 64), "cudaMalloc gamma lut");
+	need(cudaMalloc(&dev->d_words, size_t(kMaxPassWords) * 4), "cudaMalloc words");
+	need(cudaMalloc(&dev->d_records, size_t(kMaxPrimsPerPass) * sizeof(PrimRecord)), "cudaMalloc records");
+	need(cudaMalloc(&dev->d_states, size_t(kMaxStatesPerPass) * sizeof(PassState)), "cudaMalloc states");
+	need(cudaMalloc(&dev->d_uploads, size_t(kMaxUploadsPerPass) * sizeof(TmemUpload)), "cudaMalloc uploads");
+	need(cudaMalloc(&dev->d_prims, size_t(kMaxPrimsPerPass) * sizeof(PrimSetup)), "cudaMalloc prims");
+	need(cudaMalloc(&dev->d_spans, size_t(kMaxSpansPerPass) * sizeof(Span)), "cudaMalloc spans");
+	const size_t fine_bytes = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 32) * 4;
+	const size_t coarse_bytes = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 1024) * 4;
+	need(cudaMalloc(&dev->d_fine, fine_bytes), "cudaMalloc fine masks");
+	need(cudaMalloc(&dev->d_coarse, coarse_bytes), "cudaMalloc coarse masks");
+	for (auto &s : dev->vi_stage)
+		need(cudaMalloc(&s, size_t(kViStageWidth) * kViStageHeight * 2 * 4), "cudaMalloc vi stage");
+	need(cudaMalloc(&dev->d_vi_regs, sizeof(ViRegs)), "cudaMalloc vi regs");
+	need(cudaMalloc(&dev->d_vi_lines, sizeof(ViLine) * 288), "cudaMalloc vi lines");
+	need(cudaHostAlloc(&dev->vi_host_staging, sizeof(ViRegs) + sizeof(ViLine) * 288, cudaHostAllocDefault), "cudaHostAlloc vi staging");
+	for (unsigned i = 0; i < kStagingSlots; i++)
+	{
+		need(cudaHostAlloc(&dev->staging[i], StagingLayout::total, cudaHostAllocDefault), "cudaHostAlloc staging");
+		need(cudaEventCreateWithFlags(&dev->staging_done[i], cudaEventDisableTiming), "cudaEventCreate");
+	}
+
+	if (ok)
+	{
+		need(cudaMemsetAsync(dev->rdram, 0, rdram_size, dev->stream), "memset rdram");
+		need(cudaMemsetAsync(dev->hidden, 0, hidden_size, dev->stream), "memset hidden");
+		need(cudaMemsetAsync(dev->d_fine, 0, fine_bytes, dev->stream), "memset fine");
+		need(cudaMemsetAsync(dev->d_coarse, 0, coarse_bytes, dev->stream), "memset coarse");
+		need(cudaMemsetAsync(dev->tmem_instances, 0, size_t(kTmemBytes) * (kMaxUploadsPerPass + 1), dev->stream), "memset tmem instances");
+		memset(dev->tmem_host, 0, kTmemBytes);
+
+		static uint8_t lut[256 + 256 * 64];
+		build_blender_lut(lut);
+		need(cudaMemcpy(dev->blend_lut, lut, 0x8000, cudaMemcpyHostToDevice), "upload blend lut");
+		build_gamma_lut(lut);
+		need(cudaMemcpy(dev->gamma_lut, lut, 256 + 256 * 64, cudaMemcpyHostToDevice), "upload gamma lut");
+		need(cudaStreamSynchronize(dev->stream), "initial sync");
+	}
+
+	if (!ok)
+	{
+		fprintf(stderr, "[rdp-b200] Backend initialisation failed: %s\n", dev->error.c_str());
+		rdpb_device_destroy(dev);
+		return nullptr;
+	}
+	return dev;
+}
+
+void rdpb_device_destroy(rdpb_device *dev)
+{
+	if (!dev)
+		return;
+	cudaSetDevice(dev->ordinal);
+	if (dev->stream)
+		cudaStreamSynchronize(dev->stream);
+	cudaFree(dev->rdram);
+	cudaFree(dev->hidden);
+	cudaFreeHost(dev->tmem_host);
+	cudaFree(dev->tmem_instances);
+	cudaFree(dev->blend_lut);
+	cudaFree(dev->gamma_lut);
+	cudaFree(dev->d_words);
+	cudaFree(dev->d_records);
+	cudaFree(dev->d_states);
+	cudaFree(dev->d_uploads);
+	cudaFree(dev->d_prims);
+	cudaFree(dev->d_spans);
+	cudaFree(dev->d_fine);
+	cudaFree(dev->d_coarse);
+	for (auto &s : dev->vi_stage)
+		cudaFree(s);
+	for (auto &s : dev->vi_out)
+		cudaFree(s);
+	cudaFree(dev->d_vi_regs);
+	cudaFree(dev->d_vi_lines);
+	cudaFreeHost(dev->vi_host_staging);
+	for (unsigned i = 0; i < kStagingSlots; i++)
+	{
+		cudaFreeHost(dev->staging[i]);
+		if (dev->staging_done[i])
+			cudaEventDestroy(dev->staging_done[i]);
+	}
+	for (auto &t : dev->timeline)
+		cudaEventDestroy(t.second);
+	for (auto &e : dev->free_events)
+		cudaEventDestroy(e);
+	if (dev->stream)
+		cudaStreamDestroy(dev->stream);
+	delete dev;
+}
+
+const char *rdpb_last_error(rdpb_device *dev) { return dev->error.c_str(); }
+
+int rdpb_register_host_memory(rdpb_device *dev, void *ptr, size_t size)
+{
+	cudaSetDevice(dev->ordinal);
+	cudaError_t e = cudaHostRegister(ptr, size, cudaHostRegisterDefault);
+	if (e != cudaSuccess)
+	{
+		cudaGetLastError();
+		return -1; // not fatal: copies fall back to synchronous pageable transfers
+	}
+	return 0;
+}
+
+int rdpb_unregister_host_memory(rdpb_device *dev, void *ptr)
+{
+	cudaSetDevice(dev->ordinal);
+	cudaHostUnregister(ptr);
+	cudaGetLastError();
+	return 0;
+}
+
+static int copy_common(rdpb_device *dev, void *dst, const void *src, size_t size, cudaMemcpyKind kind, int sync)
+{
+	cudaSetDevice(dev->ordinal);
+	CK(cudaMemcpyAsync(dst, src, size, kind, dev->stream));
+	if (sync)
+		CK(cudaStreamSynchronize(dev->stream));
+	return 0;
+}
+
+int rdpb_rdram_write(rdpb_device *dev, uint32_t offset, const void *src, uint32_t size, int sync)
+{
+	return copy_common(dev, dev->rdram + offset, src, size, cudaMemcpyHostToDevice, sync);
+}
+int rdpb_rdram_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size, int sync)
+{
+	return copy_common(dev, dst, dev->rdram + offset, size, cudaMemcpyDeviceToHost, sync);
+}
+int rdpb_hidden_write(rdpb_device *dev, uint32_t offset, const void *src, uint32_t size, int sync)
+{
+	return copy_common(dev, dev->hidden + offset, src, size, cudaMemcpyHostToDevice, sync);
+}
+int rdpb_hidden_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size, int sync)
+{
+	return copy_common(dev, dst, dev->hidden + offset, size, cudaMemcpyDeviceToHost, sync);
+}
+int rdpb_hidden_fill(rdpb_device *dev, uint8_t value)
+{
+	cudaSetDevice(dev->ordinal);
+	CK(cudaMemsetAsync(dev->hidden, value, dev->hidden_size, dev->stream));
+	return 0;
+}
+void *rdpb_tmem_host_ptr(rdpb_device *dev) { return dev->tmem_host; }
+void *rdpb_rdram_device_ptr(rdpb_device *dev) { return dev->rdram; }
+void *rdpb_hidden_device_ptr(rdpb_device *dev) { return dev->hidden; }
+
+int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
+{
+	cudaSetDevice(dev->ordinal);
+	dev->staging_index = (dev->staging_index + 1) % kStagingSlots;
+	const unsigned i = dev->staging_index;
+	if (dev->staging_in_flight[i])
+	{
+		CK(cudaEventSynchronize(dev->staging_done[i]));
+		dev->staging_in_flight[i] = false;
+	}
+	uint8_t *base = dev->staging[i];
+	out->words = reinterpret_cast<uint32_t *>(base + StagingLayout::words_off);
+	out->records = base + StagingLayout::records_off;
+	out->states = base + StagingLayout::states_off;
+	out->uploads = base + StagingLayout::uploads_off;
+	return 0;
+}
+
+int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
+{
+	cudaSetDevice(dev->ordinal);
+	const unsigned i = dev->staging_index;
+	const uint8_t *base = dev->staging[i];
+	if (c->num_words)
+		CK(cudaMemcpyAsync(dev->d_words, base + StagingLayout::words_off, size_t(c->num_words) * 4, cudaMemcpyHostToDevice, dev->stream));
+	if (c->num_prims)
+		CK(cudaMemcpyAsync(dev->d_records, base + StagingLayout::records_off, size_t(c->num_prims) * sizeof(PrimRecord), cudaMemcpyHostToDevice, dev->stream));
+	if (c->num_states)
+		CK(cudaMemcpyAsync(dev->d_states, base + StagingLayout::states_off, size_t(c->num_states) * sizeof(PassState), cudaMemcpyHostToDevice, dev->stream));
+	if (c->num_uploads)
+		CK(cudaMemcpyAsync(dev->d_uploads, base + StagingLayout::uploads_off, size_t(c->num_uploads) * sizeof(TmemUpload), cudaMemcpyHostToDevice, dev->stream));
+	CK(cudaEventRecord(dev->staging_done[i], dev->stream));
+	dev->staging_in_flight[i] = true;
+	return 0;
+}
+
+int rdpb_launch_tmem_update(rdpb_device *dev, uint32_t num_uploads)
+{
+	cudaSetDevice(dev->ordinal);
+	k_tmem_update<<<kTmemBytes / 2 / 256, 256, 0, dev->stream>>>(dev->buffers(), num_uploads, dev->rdram_size);
+	dev->launches++;
+	CK(cudaGetLastError());
+	return 0;
+}
+
+int rdpb_launch_prim_setup(rdpb_device *dev, uint32_t num_prims)
+{
+	cudaSetDevice(dev->ordinal);
+	if (!num_prims)
+		return 0;
+	k_prim_setup<<<(num_prims + 127) / 128, 128, 0, dev->stream>>>(dev->buffers(), num_prims);
+	dev->launches++;
+	CK(cudaGetLastError());
+	return 0;
+}
+
+int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
+{
+	cudaSetDevice(dev->ordinal);
+	const FbInfo fb = *static_cast<const FbInfo *>(fb_info);
+	if (!fb.num_prims)
+		return 0;
+	const uint32_t warps_per_block = 4;
+	k_span_bin<<<(fb.num_prims + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(), fb);
+	dev->launches++;
+	CK(cudaGetLastError());
+	return 0;
+}
+
+int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info)
+{
+	cudaSetDevice(dev->ordinal);
+	const FbInfo fb = *static_cast<const FbInfo *>(fb_info);
+	if (!fb.tiles_x || !fb.tiles_y)
+		return 0;
+	k_tiles<<<dim3(fb.tiles_x, fb.tiles_y), 64, 0, dev->stream>>>(dev->buffers(), fb);
+	dev->launches++;
+	CK(cudaGetLastError());
+	return 0;
+}
+
+int rdpb_pass_end(rdpb_device *) { return 0; }
+
+int rdpb_launch_vi_scanout(rdpb_device *dev, const rdpb_vi_params *)
+{
+	dev->error = "VI scan-out is not implemented in the CUDA backend yet";
+	return -1;
+}
+
+void *rdpb_vi_output_device_ptr(rdpb_device *dev) { return dev->vi_out[dev->vi_out_index]; }
+
+int rdpb_vi_read_output(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, int sync)
+{
+	return copy_common(dev, dst, dev->vi_out[dev->vi_out_index], size_t(width) * height * 4, cudaMemcpyDeviceToHost, sync);
+}
+
+int rdpb_signal(rdpb_device *dev, uint64_t value)
+{
+	cudaSetDevice(dev->ordinal);
+	std::lock_guard<std::mutex> holder{dev->timeline_lock};
+	cudaEvent_t ev;
+	if (!dev->free_events.empty())
+	{
+		ev = dev->free_events.front();
+		dev->free_events.pop_front();
+	}
+	else
+		CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
+	CK(cudaEventRecord(ev, dev->stream));
+	dev->timeline.emplace_back(value, ev);
+	return 0;
+}
+
+int rdpb_wait(rdpb_device *dev, uint64_t value)
+{
+	cudaSetDevice(dev->ordinal);
+	for (;;)
+	{
+		cudaEvent_t ev = nullptr;
+		{
+			std::lock_guard<std::mutex> holder{dev->timeline_lock};
+			// Retire everything up to and including `value`; the last one retired is the one to wait on.
+			while (!dev->timeline.empty() && dev->timeline.front().first <= value)
+			{
+				if (ev)
+					dev->free_events.push_back(ev);
+				ev = dev->timeline.front().second;
+				dev->timeline.pop_front();
+			}
+		}
+		if (!ev)
+			return 0;
+		CK(cudaEventSynchronize(ev));
+		std::lock_guard<std::mutex> holder{dev->timeline_lock};
+		dev->free_events.push_back(ev);
+		return 0;
+	}
+}
+
+int rdpb_sync(rdpb_device *dev)
+{
+	cudaSetDevice(dev->ordinal);
+	CK(cudaStreamSynchronize(dev->stream));
+	return 0;
+}
+
+void *rdpb_stream(rdpb_device *dev) { return dev->stream; }
+uint64_t rdpb_launch_count(rdpb_device *dev) { return dev->launches; }
+}

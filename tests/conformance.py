@@ -138,8 +138,9 @@ def apply_ym_offsets(tri_words: np.ndarray, deltas: np.ndarray):
     return tri
 
 
-def run_rasterization(sbs, v: Variant, iterations: int, seed: int = 1337, first: int = 0):
-    """Returns a list of error strings (empty = pass)."""
+def run_rasterization(sbs, v: Variant, iterations: int, seed: int = 1337, first: int = 0, digests=None):
+    """Returns a list of error strings (empty = pass).  With `digests` (a list) the SHA-256 of RDRAM + hidden RDRAM
+    after every iteration is appended (taken from the oracle when present, else from the GPU side)."""
     rng = Rng(seed)
     b = Builder()
     om = b.om
@@ -281,7 +282,9 @@ def run_rasterization(sbs, v: Variant, iterations: int, seed: int = 1337, first:
             sbs.run(words)
             continue
         sbs.run(words)
-        errs = sbs.compare_rdram()
+        if digests is not None:
+            digests.append(sbs.digest())
+        errs = sbs.compare_rdram() if sbs.oracle else []
         if errs:
             errors.append(f"iteration {index}: " + "; ".join(errs))
             break

@@ -120,6 +120,19 @@ class SideBySide:
         return ref, pix.copy(), w, h
 
     # --- compare --------------------------------------------------------------------------------------------
+    def digest(self) -> str:
+        """SHA-256 over RDRAM and the two meaningful bits of hidden RDRAM (oracle side when present)."""
+        import hashlib
+        h = hashlib.sha256()
+        if self.oracle:
+            h.update(self.oracle.rdram.tobytes())
+            h.update((self.oracle.hidden[: self.hidden_size] & 3).tobytes())
+        else:
+            self.gpu.idle()
+            h.update(self.gpu.begin_read_rdram().tobytes())
+            h.update((self.gpu.begin_read_hidden_rdram() & 3).tobytes())
+        return h.hexdigest()
+
     def compare_rdram(self) -> list[str]:
         self.gpu.idle()
         errs = []

@@ -1,0 +1,36 @@
+"""GPU parity tests proper: every conformance suite through librdp_b200.so (CUDA, via the C-ABI) against the
+Angrylion oracle (when oracle/_ref travelled to the box) and against the committed golden digests."""
+import json
+import os
+
+import pytest
+
+import conformance as cf
+from oracle import angrylion
+from sidebyside import SideBySide
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "rdp_digests.json")))
+
+pytestmark = pytest.mark.gpu
+
+ALL = sorted(cf.SUITES)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_gpu_matches_oracle(name):
+    v = cf.SUITES[name]
+    iters = 2 if v.primitive_count > 1 else 12
+    sbs = SideBySide("cuda", with_oracle=angrylion.available())
+    try:
+        assert sbs.gpu.backend_name() == "cuda-sm_100a"
+        digests = []
+        errs = cf.run_rasterization(sbs, v, iters, digests=digests)
+        launches = sbs.gpu.launch_count()
+    finally:
+        sbs.close()
+    assert not errs, errs
+    assert launches > 0
+    if name in GOLDEN["digests"]:
+        n = GOLDEN["iterations"]
+        assert digests[:n] == GOLDEN["digests"][name]
