@@ -262,7 +262,8 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		need(cudaMemsetAsync(dev->tmem_instances, 0, size_t(kTmemBytes) * (kMaxUploadsPerPass + 1), dev->stream), "memset tmem instances");
 		memset(dev->tmem_host, 0, kTmemBytes);
 
-		static uint8_t lut[256 + 256 * 64];
+		static uint8_t lut[0x8000]; // large enough for both tables (32768 >= 256 + 256 * 64)
+		static_assert(sizeof(lut) >= 256 + 256 * 64, "LUT staging too small");
 		build_blender_lut(lut);
 		need(cudaMemcpy(dev->blend_lut, lut, 0x8000, cudaMemcpyHostToDevice), "upload blend lut");
 		build_gamma_lut(lut);

@@ -429,3 +429,96 @@ def _suites():
 
 
 SUITES = _suites()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Texture load tests (reference: run_conformance_load_tile, rdp_conformance.cpp:609-971): known byte ramp in RDRAM,
+# one LoadTile / LoadBlock / LoadTLUT, then all 2,048 TMEM words must match the oracle.
+# ---------------------------------------------------------------------------------------------------------------------
+OP_TILE, OP_BLOCK, OP_TLUT = "tile", "block", "tlut"
+
+
+def _load_case(sbs, width, height, tmem_offset, tmem_stride, rdram_offset, op, vram_size, tile_size, dxt, yuv):
+    sbs.write_tmem(np.zeros(4096, dtype=np.uint8))
+    if op == OP_TLUT:
+        height = 1
+    # byte ramp 0,1,2,... in big-endian memory order == this uint32 pattern in RDRAM storage order
+    i = np.arange(64 * 1024, dtype=np.uint64)
+    ramp = ((((4 * i + 0) & 0xFF) << 24) | (((4 * i + 1) & 0xFF) << 16) | (((4 * i + 2) & 0xFF) << 8) | ((4 * i + 3) & 0xFF)).astype(np.uint32)
+    sbs.write_rdram(2 * 1024 * 1024, ramp)
+
+    b = Builder()
+    b.set_texture_image(2 * 1024 * 1024 + rdram_offset, FMT_RGBA, vram_size, width)
+    b.set_tile(0, FMT_YUV if yuv else FMT_RGBA, tile_size, tmem_stride, tmem_offset)
+    if op == OP_TLUT:
+        b.load_tlut(0, 1, 1, width, height)
+    elif op == OP_TILE:
+        b.load_tile_subpixels(0, (width & 3) + 8, (height & 3) + 8, (width << 2) | (height & 3), (height << 2) | (width & 3))
+    else:
+        b.load_block(0, 1, 3, width, dxt if dxt else ((1 << 10) >> (height & 3)))
+    sbs.run(b.words())
+    errs = sbs.compare_tmem()
+    if errs:
+        return [f"load {op} w={width} h={height} off={tmem_offset} stride={tmem_stride} rdram+{rdram_offset} "
+                f"vram_size={vram_size} tile_size={tile_size} dxt={dxt} yuv={yuv}: {errs[0]}"]
+    return []
+
+
+def run_load_cases(sbs, op, vram_size, tile_size, yuv=False, thorough=True):
+    errs = []
+
+    def case(w, h, off, stride, roff, dxt=0):
+        if not errs:
+            errs.extend(_load_case(sbs, w, h, off, stride, roff, op, vram_size, tile_size, dxt, yuv))
+
+    case(32, 7, 0, 128, 0)
+    if tile_size == SIZE_16:
+        case(64, 32, 0, 128, 0)
+    if op == OP_TILE:
+        case(128, 64, 0, 128 + 8, 0)
+        case(4, 1024, 0, 8, 0)
+        case(4, 1023, 0, 8, 0)
+    if op == OP_BLOCK:
+        if tile_size == SIZE_16 and not yuv:
+            case(1600, 1, 0, 0, 0, 103)
+            case(1600, 1, 0, 8, 0, 103)
+        if (vram_size == SIZE_32 and tile_size == SIZE_32 and not yuv) or (vram_size == SIZE_16 and tile_size == SIZE_16 and yuv):
+            case(799, 1, 0, 0, 0, 872)
+            case(100, 1, 0, 32, 0, 872)
+    case(32, 7, 0x800, 128, 0)
+    case(32, 7, 128, 128, 0)
+    case(32, 9, 0, 128, 1)
+    step = 1 if thorough else 5
+    for width in range(9, 32, step):
+        for height in range(1, 4):
+            case(width, height, 0, 0, height & 3)
+    for width in range(8, 32, step):
+        case(width, 3, 0, 256, width & 3)
+    for stride in (8, 16, 24):
+        for width in range(8, 64, step):
+            case(width, 3, 0, stride, 0)
+    return errs
+
+
+LOAD_SUITES = {
+    "texture-load-tile-16-yuv": [(OP_TILE, SIZE_16, SIZE_16, True)],
+    "texture-load-block-16-yuv": [(OP_BLOCK, SIZE_16, SIZE_16, True)],
+    "texture-load-tile-4": [(OP_TILE, SIZE_8, SIZE_4, False)],
+    "texture-load-tile-8": [(OP_TILE, SIZE_8, SIZE_8, False), (OP_TILE, SIZE_16, SIZE_8, False)],
+    "texture-load-tile-16": [(OP_TILE, SIZE_16, SIZE_16, False), (OP_TILE, SIZE_8, SIZE_16, False), (OP_TILE, SIZE_32, SIZE_16, False)],
+    "texture-load-tile-32": [(OP_TILE, SIZE_32, SIZE_32, False), (OP_TILE, SIZE_16, SIZE_32, False), (OP_TILE, SIZE_8, SIZE_32, False)],
+    "texture-load-block-8": [(OP_BLOCK, SIZE_8, SIZE_8, False)],
+    "texture-load-block-16": [(OP_BLOCK, SIZE_16, SIZE_16, False), (OP_BLOCK, SIZE_8, SIZE_16, False)],
+    "texture-load-block-32": [(OP_BLOCK, SIZE_32, SIZE_32, False), (OP_BLOCK, SIZE_16, SIZE_32, False), (OP_BLOCK, SIZE_8, SIZE_32, False)],
+    "texture-load-tlut-4": [(OP_TLUT, SIZE_16, SIZE_4, False), (OP_TLUT, SIZE_8, SIZE_4, False), (OP_TLUT, SIZE_32, SIZE_4, False)],
+    "texture-load-tlut-8": [(OP_TLUT, SIZE_16, SIZE_8, False), (OP_TLUT, SIZE_8, SIZE_8, False), (OP_TLUT, SIZE_32, SIZE_8, False)],
+    "texture-load-tlut-16": [(OP_TLUT, SIZE_16, SIZE_16, False), (OP_TLUT, SIZE_8, SIZE_16, False), (OP_TLUT, SIZE_32, SIZE_16, False)],
+}
+
+
+def run_load_suite(sbs, name, thorough=True):
+    for op, vram_size, tile_size, yuv in LOAD_SUITES[name]:
+        errs = run_load_cases(sbs, op, vram_size, tile_size, yuv, thorough)
+        if errs:
+            return errs
+    return []
