@@ -75,30 +75,10 @@ int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo *
 int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo */);
 int rdpb_pass_end(rdpb_device *dev);
 
-/* VI scan-out.  `regs` is rdpb::ViRegs, `lines` rdpb::ViLine[288]; result is RGBA8 in device memory. */
-typedef struct rdpb_vi_params
-{
-	const void *regs;
-	const void *lines;
-	uint32_t width, height;      /* output size */
-	uint32_t flags;              /* RDPB_VI_* */
-	uint32_t frame_count;
-} rdpb_vi_params;
-
-enum
-{
-	RDPB_VI_BLEND_PREVIOUS = 1u << 0,
-	RDPB_VI_PREV_VALID = 1u << 1,
-	RDPB_VI_DEGENERATE = 1u << 2,
-	RDPB_VI_OPT_AA = 1u << 3,
-	RDPB_VI_OPT_SCALE = 1u << 4,
-	RDPB_VI_OPT_SERRATE = 1u << 5,
-	RDPB_VI_OPT_DITHER_FILTER = 1u << 6,
-	RDPB_VI_OPT_DIVOT = 1u << 7,
-	RDPB_VI_OPT_GAMMA_DITHER = 1u << 8,
-};
-
-int rdpb_launch_vi_scanout(rdpb_device *dev, const rdpb_vi_params *params);
+/* VI scan-out.  `frame` is rdpb::ViFrame (built by the host from the VI registers), `lines` rdpb::ViLine[288].
+ * Two kernels: filter (AA / dither reconstruction / divot straight from RDRAM) and scale (+gamma, field merge).
+ * The result is RGBA8 in device memory, double-buffered so the previous field can be merged. */
+int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame /* rdpb::ViFrame */, const void *lines /* rdpb::ViLine[288] */);
 void *rdpb_vi_output_device_ptr(rdpb_device *dev);
 int rdpb_vi_read_output(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, int sync);
 

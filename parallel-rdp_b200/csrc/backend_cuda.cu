@@ -121,6 +121,22 @@ __global__ void __launch_bounds__(64) k_tiles(PassBuffers b, FbInfo fb)
 	if (threadIdx.x == 0)
 		pass_tile_clear_masks(b, fb, tile);
 }
+
+__global__ void __launch_bounds__(256) k_vi_filter(ViFrame f, ViBuffers b)
+{
+	const int x = int(blockIdx.x * blockDim.x + threadIdx.x);
+	const int y = int(blockIdx.y * blockDim.y + threadIdx.y);
+	if (x < f.filt_width && y < f.filt_height)
+		vi_filter_thread(f, b, x, y, int(blockIdx.z));
+}
+
+__global__ void __launch_bounds__(256) k_vi_scale(ViFrame f, ViBuffers b)
+{
+	const int x = int(blockIdx.x * blockDim.x + threadIdx.x);
+	const int y = int(blockIdx.y * blockDim.y + threadIdx.y);
+	if (x < f.out_width && y < f.out_height)
+		vi_scale_thread(f, b, x, y);
+}
 }
 
 struct rdpb_device
@@ -151,9 +167,10 @@ struct rdpb_device
 	uint32_t *vi_out[2] = {};
 	unsigned vi_out_index = 0;
 	uint32_t vi_out_pixels = 0;
-	ViRegs *d_vi_regs = nullptr;
 	ViLine *d_vi_lines = nullptr;
 	uint8_t *vi_host_staging = nullptr;
+	cudaEvent_t vi_lines_done[2] = {};
+	bool vi_lines_in_flight[2] = {};
 
 	std::mutex timeline_lock;
 	std::deque<std::pair<uint64_t, cudaEvent_t>> timeline;
@@ -242,11 +259,11 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	const size_t coarse_bytes = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 1024) * 4;
 	need(cudaMalloc(&dev->d_fine, fine_bytes), "cudaMalloc fine masks");
 	need(cudaMalloc(&dev->d_coarse, coarse_bytes), "cudaMalloc coarse masks");
-	for (auto &s : dev->vi_stage)
-		need(cudaMalloc(&s, size_t(kViStageWidth) * kViStageHeight * 2 * 4), "cudaMalloc vi stage");
-	need(cudaMalloc(&dev->d_vi_regs, sizeof(ViRegs)), "cudaMalloc vi regs");
-	need(cudaMalloc(&dev->d_vi_lines, sizeof(ViLine) * 288), "cudaMalloc vi lines");
-	need(cudaHostAlloc(&dev->vi_host_staging, sizeof(ViRegs) + sizeof(ViLine) * 288, cudaHostAllocDefault), "cudaHostAlloc vi staging");
+	need(cudaMalloc(&dev->vi_stage[0], size_t(kViStageWidth) * kViStageHeight * 2 * 4), "cudaMalloc vi stage");
+	need(cudaMalloc(&dev->d_vi_lines, sizeof(ViLine) * kViMaxLines), "cudaMalloc vi lines");
+	need(cudaHostAlloc(&dev->vi_host_staging, sizeof(ViLine) * kViMaxLines * 2, cudaHostAllocDefault), "cudaHostAlloc vi staging");
+	for (auto &e : dev->vi_lines_done)
+		need(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
 	for (unsigned i = 0; i < kStagingSlots; i++)
 	{
 		need(cudaHostAlloc(&dev->staging[i], StagingLayout::total, cudaHostAllocDefault), "cudaHostAlloc staging");
@@ -305,8 +322,10 @@ void rdpb_device_destroy(rdpb_device *dev)
 		cudaFree(s);
 	for (auto &s : dev->vi_out)
 		cudaFree(s);
-	cudaFree(dev->d_vi_regs);
 	cudaFree(dev->d_vi_lines);
+	for (auto &e : dev->vi_lines_done)
+		if (e)
+			cudaEventDestroy(e);
 	cudaFreeHost(dev->vi_host_staging);
 	for (unsigned i = 0; i < kStagingSlots; i++)
 	{
@@ -463,10 +482,59 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info)
 
 int rdpb_pass_end(rdpb_device *) { return 0; }
 
-int rdpb_launch_vi_scanout(rdpb_device *dev, const rdpb_vi_params *)
+int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *lines)
 {
-	dev->error = "VI scan-out is not implemented in the CUDA backend yet";
-	return -1;
+	cudaSetDevice(dev->ordinal);
+	const ViFrame f = *static_cast<const ViFrame *>(frame);
+
+	const size_t max_out = size_t(640) * 576;
+	if (!dev->vi_out[0])
+	{
+		CK(cudaMalloc(&dev->vi_out[0], max_out * 4));
+		CK(cudaMalloc(&dev->vi_out[1], max_out * 4));
+		CK(cudaMemsetAsync(dev->vi_out[0], 0, max_out * 4, dev->stream));
+		CK(cudaMemsetAsync(dev->vi_out[1], 0, max_out * 4, dev->stream));
+	}
+	dev->vi_out_index ^= 1u;
+
+	// Per-line parameters go through a small pinned staging block (re-used once the previous copy has landed).
+	const unsigned slot = dev->vi_out_index;
+	if (dev->vi_lines_in_flight[slot])
+	{
+		CK(cudaEventSynchronize(dev->vi_lines_done[slot]));
+		dev->vi_lines_in_flight[slot] = false;
+	}
+	ViLine *h_lines = reinterpret_cast<ViLine *>(dev->vi_host_staging) + size_t(slot) * kViMaxLines;
+	memcpy(h_lines, lines, sizeof(ViLine) * kViMaxLines);
+	CK(cudaMemcpyAsync(dev->d_vi_lines, h_lines, sizeof(ViLine) * kViMaxLines, cudaMemcpyHostToDevice, dev->stream));
+	CK(cudaEventRecord(dev->vi_lines_done[slot], dev->stream));
+	dev->vi_lines_in_flight[slot] = true;
+
+	ViBuffers b;
+	b.rdram = dev->rdram;
+	b.hidden = dev->hidden;
+	b.gamma_lut = dev->gamma_lut;
+	b.lines = dev->d_vi_lines;
+	b.filtered = dev->vi_stage[0];
+	b.out = dev->vi_out[dev->vi_out_index];
+	b.prev = dev->vi_out[dev->vi_out_index ^ 1u];
+
+	if (f.filt_width > 0 && f.filt_height > 0)
+	{
+		const dim3 block(32, 8);
+		const dim3 grid((f.filt_width + 31) / 32, (f.filt_height + 7) / 8, f.fetch_bug ? 2 : 1);
+		k_vi_filter<<<grid, block, 0, dev->stream>>>(f, b);
+		dev->launches++;
+		CK(cudaGetLastError());
+	}
+	{
+		const dim3 block(32, 8);
+		const dim3 grid((f.out_width + 31) / 32, (f.out_height + 7) / 8);
+		k_vi_scale<<<grid, block, 0, dev->stream>>>(f, b);
+		dev->launches++;
+		CK(cudaGetLastError());
+	}
+	return 0;
 }
 
 void *rdpb_vi_output_device_ptr(rdpb_device *dev) { return dev->vi_out[dev->vi_out_index]; }

@@ -69,3 +69,30 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_vi_golden():
+    import vi_conformance as vc
+
+    class OracleOnlyVI(OracleOnly):
+        def set_vi_register(self, reg, value):
+            self.oracle.set_vi_register(reg, value)
+
+        def end_frame(self, opts=None):
+            return self.oracle.update_screen(), None, 0, 0
+
+    out = {}
+    for name, variant in vc.VI_SUITES.items():
+        sbs = OracleOnlyVI()
+        digests = []
+        vc.run_vi(sbs, variant, GOLDEN_ITERATIONS, digests=digests)
+        sbs.close()
+        out[name] = digests
+    path = os.path.join(ROOT, "tests", "golden", "vi_digests.json")
+    with open(path, "w") as f:
+        json.dump({"iterations": GOLDEN_ITERATIONS, "seed": 1337, "digests": out}, f, indent=0, sort_keys=True)
+    print("wrote", path, len(out), "suites")
+
+
+if __name__ == "__main__":
+    make_vi_golden()

@@ -208,39 +208,35 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info)
 
 int rdpb_pass_end(rdpb_device *) { return 0; }
 
-int rdpb_launch_vi_scanout(rdpb_device *dev, const rdpb_vi_params *params)
+int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *lines)
 {
-	ViContext vi;
-	vi.rdram = dev->rdram.data();
-	vi.hidden = dev->hidden.data();
-	vi.rdram_size = dev->rdram_size;
-	vi.gamma_lut = dev->gamma_lut.data();
-	vi.regs = *static_cast<const ViRegs *>(params->regs);
-	vi.lines = static_cast<const ViLine *>(params->lines);
-	vi.flags = params->flags;
-	vi.frame_count = params->frame_count;
-	vi.out_width = params->width;
-	vi.out_height = params->height;
-
-	const size_t stage_pixels = size_t(kViStageWidth) * kViStageHeight;
-	for (auto &s : dev->vi_stage)
-		s.assign(stage_pixels * 2, 0);
-	const size_t out_pixels = size_t(params->width) * params->height;
-	if (dev->vi_out.size() != out_pixels)
+	const ViFrame f = *static_cast<const ViFrame *>(frame);
+	const size_t max_out = size_t(640) * 576;
+	if (dev->vi_out.size() != max_out)
 	{
-		dev->vi_out.assign(out_pixels, 0);
-		dev->vi_prev.assign(out_pixels, 0);
+		dev->vi_out.assign(max_out, 0);
+		dev->vi_prev.assign(max_out, 0);
+		dev->vi_stage[0].assign(size_t(kViStageWidth) * kViStageHeight * 2, 0);
 	}
 	std::swap(dev->vi_out, dev->vi_prev);
 
-	vi.stage0 = dev->vi_stage[0].data();
-	vi.stage1 = dev->vi_stage[1].data();
-	vi.stage2 = dev->vi_stage[2].data();
-	vi.out = dev->vi_out.data();
-	vi.prev = dev->vi_prev.data();
+	ViBuffers b;
+	b.rdram = dev->rdram.data();
+	b.hidden = dev->hidden.data();
+	b.gamma_lut = dev->gamma_lut.data();
+	b.lines = static_cast<const ViLine *>(lines);
+	b.filtered = dev->vi_stage[0].data();
+	b.out = dev->vi_out.data();
+	b.prev = dev->vi_prev.data();
 
-	vi_run_all_stages_serial(vi);
-	dev->launches += 4;
+	for (int layer = 0; layer < (f.fetch_bug ? 2 : 1); layer++)
+		for (int y = 0; y < f.filt_height; y++)
+			for (int x = 0; x < f.filt_width; x++)
+				vi_filter_thread(f, b, x, y, layer);
+	for (int y = 0; y < f.out_height; y++)
+		for (int x = 0; x < f.out_width; x++)
+			vi_scale_thread(f, b, x, y);
+	dev->launches += 2;
 	return 0;
 }
 

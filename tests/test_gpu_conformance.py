@@ -34,3 +34,33 @@ def test_gpu_matches_oracle(name):
     if name in GOLDEN["digests"]:
         n = GOLDEN["iterations"]
         assert digests[:n] == GOLDEN["digests"][name]
+
+
+@pytest.mark.parametrize("name", sorted(cf.LOAD_SUITES))
+def test_gpu_texture_loads(name):
+    if not angrylion.available():
+        pytest.skip("texture load suites compare TMEM against the oracle")
+    sbs = SideBySide("cuda")
+    try:
+        errs = cf.run_load_suite(sbs, name, thorough=True)
+    finally:
+        sbs.close()
+    assert not errs, errs
+
+
+import vi_conformance as vc  # noqa: E402
+
+VI_GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "vi_digests.json")))
+
+
+@pytest.mark.parametrize("name", sorted(vc.VI_SUITES))
+def test_gpu_vi_matches_oracle(name):
+    sbs = SideBySide("cuda", with_oracle=angrylion.available())
+    try:
+        digests = []
+        errs = vc.run_vi(sbs, vc.VI_SUITES[name], 16, digests=digests)
+    finally:
+        sbs.close()
+    assert not errs, errs
+    n = VI_GOLDEN["iterations"]
+    assert digests[:n] == VI_GOLDEN["digests"][name]

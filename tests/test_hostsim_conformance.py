@@ -65,3 +65,34 @@ def test_many_primitives_single_pass():
         sbs.close()
     assert not errs, errs
     assert passes <= 4
+
+
+# --- texture loads -----------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", sorted(cf.LOAD_SUITES))
+def test_hostsim_texture_loads(name):
+    sbs = SideBySide("hostsim")
+    try:
+        errs = cf.run_load_suite(sbs, name, thorough=False)
+    finally:
+        sbs.close()
+    assert not errs, errs
+
+
+# --- VI ----------------------------------------------------------------------------------------------------------
+import vi_conformance as vc  # noqa: E402
+
+VI_GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "vi_digests.json")))
+
+
+@pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", sorted(vc.VI_SUITES))
+def test_hostsim_vi_matches_oracle(name):
+    sbs = SideBySide("hostsim")
+    try:
+        digests = []
+        errs = vc.run_vi(sbs, vc.VI_SUITES[name], VI_GOLDEN["iterations"], digests=digests)
+    finally:
+        sbs.close()
+    assert not errs, errs
+    assert digests == VI_GOLDEN["digests"][name]
