@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- VI frames/s (and shaded Mpix/s) of the RDP hot path on the C2 workload of BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step is one frame of the synthetic C2 stream (640x480 RGBA32, ~5,000 textured Gouraud Z-buffered triangles,
+2-cycle combiner, bilinear TMEM sampling, fill-rect clears, 8 texture loads, SyncFull, 480i weave scan-out).
+
+  value    frames/s with the command stream already resident in HBM (record/replay: kernels only, no PCIe traffic)
+  e2e      frames/s through the public C-ABI with HOST buffers: command words are fed from pinned host memory and
+           every frame's 640x480 RGBA8 scan-out is read back to pinned host memory inside the timed region
+  roofline the tile kernel's algorithmic framebuffer bytes / its CUDA-event time vs the measured HBM peak
+  cpu_baseline  the reference's own CPU renderer (Angrylion, oracle/_ref) on a bounded sample, rank 0, N=1 only
+
+N>1: one process per GPU (torchrun), each rank renders its own independent stream (no collective on the data
+path: a command stream is serial through RDRAM, streams are the natural shard); value = total frames / max time.
+--impl reference times the reference's CPU renderer with all host threads on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from harness import workloads as wl  # noqa: E402
+
+METRIC = "vi_frames_per_s"
+UNIT = "frames/s"
+VI_REG = {n: i for i, n in enumerate(["Control", "Origin", "Width", "Intr", "VCurrentLine", "Timing", "VSync", "HSync", "Leap",
+                                       "HStart", "VStart", "VBurst", "XScale", "YScale"])}
+L2_BYTES = 126 << 20
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_frames(seed: int, count: int, triangles: int):
+    rng = np.random.RandomState(seed)
+    return [wl.c2_frame(rng, triangles) for _ in range(count)]
+
+
+def tile_kernel_algorithmic_bytes(tiles_processed: int, frames: int):
+    """Framebuffer bytes the tile kernel must move, per SURVEY 8d: per touched 8x8 tile colour R+W and its hidden bits
+    R+W, plus depth R+W and its hidden byte R+W where the pass uses depth.  Per C2 frame: the Z clear touches
+    640x480 16-bit colour (64*(2*2 + 2*1) B/tile), the main pass 32-bit colour + depth (64*(2*4 + 2*2 + 2*2 + 2*1) B/tile)."""
+    tiles_per_pass = (wl.WIDTH // 8) * (wl.HEIGHT // 8)
+    per_frame = tiles_per_pass * 64 * (2 * 2 + 2 * 1) + tiles_per_pass * 64 * (2 * 4 + 2 * 2 + 2 * 2 + 2 * 1)
+    return per_frame * frames, per_frame
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    rdp = importlib.import_module("parallel-rdp_b200")
+    lib = rdp.load_library()
+    lib.rdp_b200_backend_device.restype = C.c_void_p
+    lib.rdp_b200_backend_device.argtypes = [C.c_void_p]
+    for name, argt, rest in (("rdpb_profile_enable", [C.c_void_p, C.c_int, C.c_uint32], C.c_int),
+                             ("rdpb_profile_read", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p], C.c_int),
+                             ("rdpb_counters_read", [C.c_void_p, C.c_void_p, C.c_int], C.c_int),
+                             ("rdpb_record_begin", [C.c_void_p, C.c_size_t], C.c_int), ("rdpb_record_mark", [C.c_void_p], C.c_int),
+                             ("rdpb_record_end", [C.c_void_p], C.c_int), ("rdpb_record_steps", [C.c_void_p], C.c_uint32),
+                             ("rdpb_replay_step", [C.c_void_p, C.c_uint32], C.c_int), ("rdpb_sync", [C.c_void_p], C.c_int)):
+        getattr(lib, name).argtypes = argt
+        getattr(lib, name).restype = rest
+
+    # Enough distinct frames that the command stream exceeds L2 (the "inputs larger than L2" timing rule).
+    probe = build_frames(1000 + rank if world > 1 else 2, 1, args.triangles)[0]
+    frame_bytes = probe.size * 4
+    n_frames = max(8, int(np.ceil(1.12 * L2_BYTES / frame_bytes)))
+    n_frames = min(n_frames, max(args.steps, 8)) if args.small else n_frames
+    frames = build_frames(1000 + rank if world > 1 else 2, n_frames, args.triangles)
+    prims_per_frame, _ = wl.frame_stats(frames[0])
+
+    # Pinned host copies of the frames (the e2e leg feeds the API from these).
+    pinned = [torch.from_numpy(f.view(np.int32)).pin_memory() for f in frames]
+    frames = [p.numpy().view(np.uint32) for p in pinned]
+
+    rdram_t = torch.zeros(wl.RDRAM_SIZE, dtype=torch.uint8)
+    rdram = rdram_t.numpy()
+    rdram[wl.TEX_ADDR:wl.TEX_ADDR + 8 * 2048] = wl.c2_textures()
+    proc = rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, cuda_device=local_rank)
+    proc.begin_read_hidden_rdram()[:] = 0
+    proc.end_write_hidden_rdram()
+    proc.end_write_rdram()
+    dev = lib.rdp_b200_backend_device(proc._h)
+    stream = torch.cuda.ExternalStream(proc.cuda_stream(), device=torch.device("cuda", local_rank))
+
+    opts = proc.default_scanout_options()
+    opts.blend_previous_frame = 1
+    opts.upscale_deinterlacing = 0
+    out_t = torch.empty(640 * 576, dtype=torch.int32).pin_memory()
+    out = out_t.numpy().view(np.uint32)
+
+    def api_frame(i, readback=True):
+        proc.enqueue_command_stream(frames[i % n_frames])
+        for k, v in wl.c2_vi_registers(i & 1).items():
+            proc.set_vi_register(VI_REG[k], v)
+        if readback:
+            return proc.scanout_sync(opts, out)
+        return proc.scanout(opts)
+
+    # --- parity spot check against the oracle (rank 0): frame 0, RDRAM + scan-out ----------------------------------
+    parity = "not checked"
+    if rank == 0 and not args.no_parity:
+        try:
+            from oracle import angrylion
+            if angrylion.available():
+                o = angrylion.Oracle(wl.RDRAM_SIZE)
+                o.rdram[:] = 0
+                o.hidden[:] = 0
+                o.rdram[wl.TEX_ADDR:wl.TEX_ADDR + 8 * 2048] = wl.c2_textures()
+                o.command_stream(frames[0])
+                for k, v in wl.c2_vi_registers(0).items():
+                    o.set_vi_register(VI_REG[k], v)
+                ref_img = o.update_screen()
+                pix, w, h = api_frame(0)
+                proc.idle()
+                ok = np.array_equal(proc.begin_read_rdram(), o.rdram) and \
+                    np.array_equal(proc.begin_read_hidden_rdram() & 3, o.hidden[:wl.HIDDEN_SIZE] & 3) and \
+                    ref_img is not None and ref_img.shape == pix.shape and np.array_equal(ref_img & 0xFFFFFF, pix & 0xFFFFFF)
+                o.close()
+                parity = "bit-exact vs oracle (frame 0: RDRAM, hidden RDRAM, scan-out)" if ok else "MISMATCH vs oracle on frame 0"
+                if not ok:
+                    raise SystemExit("bench.py: GPU output differs from the oracle; refusing to report a number")
+        except ImportError:
+            pass
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # --- warm-up through the API, then record every distinct frame with device-resident inputs ----------------------
+    for i in range(max(args.warmup, 3)):
+        api_frame(i)
+    proc.idle()
+    if lib.rdpb_record_begin(dev, int(n_frames * (frame_bytes * 1.25 + (1 << 18)) + (8 << 20))) != 0:
+        raise SystemExit("record_begin failed")
+    for i in range(n_frames):
+        api_frame(i, readback=False)
+        proc.idle()
+        lib.rdpb_record_mark(dev)
+    lib.rdpb_record_end(dev)
+    assert lib.rdpb_record_steps(dev) >= n_frames
+
+    def replay_steps(first, count):
+        for s in range(first, first + count):
+            if lib.rdpb_replay_step(dev, s % n_frames) != 0:
+                raise SystemExit("replay failed")
+
+    # --- value: K steps, device-resident inputs, CUDA events on the launching stream --------------------------------
+    replay_steps(0, max(args.warmup, 3))
+    lib.rdpb_sync(dev)
+    counters = (C.c_uint64 * 8)()
+    lib.rdpb_counters_read(dev, counters, 1)
+    launches0 = proc.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    replay_steps(0, args.steps)
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    value_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    launches = proc.launch_count() - launches0
+    lib.rdpb_counters_read(dev, counters, 1)
+    tiles_processed, shaded_pairs = int(counters[0]), int(counters[1])
+
+    # --- roofline: same replay with per-kernel events -----------------------------------------------------------------
+    lib.rdpb_profile_enable(dev, 1, 16 * args.steps + 64)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    replay_steps(0, args.steps)
+    p1.record(stream)
+    p1.synchronize()
+    profiled_ms = p0.elapsed_time(p1)
+    kernel_ms = {}
+    names = ["tmem_update", "prim_setup", "span_bin", "tiles", "vi_filter", "vi_scale"]
+    for kid, kname in enumerate(names):
+        n, total = C.c_uint32(0), C.c_double(0.0)
+        lib.rdpb_profile_read(dev, kid, C.byref(n), C.byref(total))
+        kernel_ms[kname] = {"launches": int(n.value), "total_ms": round(total.value, 4)}
+    lib.rdpb_profile_enable(dev, 0, 0)
+    lib.rdpb_counters_read(dev, counters, 1)
+
+    tiles_ms = kernel_ms["tiles"]["total_ms"]
+    tiles_launches = max(kernel_ms["tiles"]["launches"], 1)
+    alg_total, alg_per_frame = tile_kernel_algorithmic_bytes(tiles_processed, args.steps)
+    peak, peak_src = measured_peaks()
+    achieved = (alg_total / 1e9) / (tiles_ms / 1e3) if tiles_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_tiles", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_total / tiles_launches),
+                "avg_launch_us": round(1e3 * tiles_ms / tiles_launches, 3),
+                "kernel_share_of_step": round(tiles_ms / profiled_ms, 4) if profiled_ms > 0 else None,
+                "note": "native-resolution RDP work is integer-ALU / latency bound, not HBM bound (SURVEY 8d); see DESIGN.md"}
+
+    # --- e2e: K steps through the public API with host buffers ---------------------------------------------------------
+    proc.idle()
+    for i in range(3):
+        api_frame(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        api_frame(i)
+    proc.idle()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+
+    result = None
+    if rank == 0:
+        total_frames = args.steps * world
+        fps = total_frames / (value_ms / 1e3)
+        result = {
+            "metric": METRIC, "value": round(fps, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(value_ms / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "C2: 640x480 RGBA32, %d triangle commands/frame (textured, Gouraud, Z-buffered, 2-cycle, "
+                                   "bilinear), fill-rect clears, 8 LoadTile, SyncFull + 480i weave scan-out" % prims_per_frame,
+                       "streams_per_gpu": 1, "distinct_frames": n_frames, "command_bytes_per_frame": frame_bytes,
+                       "l2": "inputs larger than L2: %d distinct frames = %.0f MB of command words cycled (> 126 MB L2)"
+                             % (n_frames, n_frames * frame_bytes / 1e6),
+                       "parallelism": "independent streams, 1 per GPU, no collective", "parity": parity},
+            "mpix_shaded_per_s": round(shaded_pairs / (value_ms / 1e3) / 1e6 * world, 2),
+            "shaded_pixels_per_frame": int(shaded_pairs / max(args.steps, 1)),
+            "e2e": {"value": round(total_frames / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": frame_bytes + 288 * 32,
+                    "d2h_bytes_per_step": 640 * 480 * 4, "ms_per_step": round(e2e_ms / args.steps, 5),
+                    "path": "rdp_b200_enqueue_command_stream + rdp_b200_set_vi_register + rdp_b200_scanout_sync (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "kernel_ms": kernel_ms, "profiled_ms_per_step": round(profiled_ms / args.steps, 5),
+            "clocks": clocks,
+        }
+
+    # --- CPU baseline (rank 0, N=1 only): the reference's own CPU renderer, single thread, bounded sample -----------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        result["cpu_baseline"] = cpu_reference(frames, threads=1, budget_s=args.cpu_budget, max_frames=64)
+
+    proc.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(result))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference(frames, threads: int, budget_s: float, max_frames: int, steps: int | None = None, warmup: int = 0):
+    """Times the reference's CPU renderer (Angrylion via oracle/_ref) on the same frames.
+    threads == 1: rdp_cmd per command, exactly how the reference harness drives it.
+    threads  > 1: the oracle's scanline-parallel worker pool, fed through an in-RDRAM display list."""
+    from oracle import angrylion
+    if not angrylion.available():
+        return {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "oracle/_ref not built"}
+    parallel = threads > 1
+    o = angrylion.Oracle(wl.RDRAM_SIZE, parallel=parallel, num_workers=threads if parallel else 0)
+    o.rdram[:] = 0
+    o.hidden[:] = 0
+    o.rdram[wl.TEX_ADDR:wl.TEX_ADDR + 8 * 2048] = wl.c2_textures()
+
+    def one(i):
+        f = frames[i % len(frames)]
+        if parallel:
+            o.process_list(f, wl.LIST_ADDR)
+        else:
+            o.command_stream(f)
+        for k, v in wl.c2_vi_registers(i & 1).items():
+            o.set_vi_register(VI_REG[k], v)
+        o.update_screen()
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    done = 0
+    if steps is None:
+        while done < max_frames and (time.perf_counter() - t0) < budget_s:
+            one(done)
+            done += 1
+    else:
+        for i in range(steps):
+            one(i)
+        done = steps
+    dt = time.perf_counter() - t0
+    o.close()
+    return {"value": round(done / dt, 3), "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": f"{done} frames of the C2 stream through Angrylion ({'process_list + worker pool' if parallel else 'rdp_cmd per command'}"
+                      f" + n64video_update_screen), {dt:.1f} s", "seconds": round(dt, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    frames = build_frames(2, 8, args.triangles)
+    prims_per_frame, frame_bytes = wl.frame_stats(frames[0])
+    # Keep the whole run inside a few minutes: time one frame first, then bound K.
+    probe = cpu_reference(frames, threads, budget_s=5.0, max_frames=2)
+    per_frame = 1.0 / probe["value"] if probe["value"] else 1.0
+    steps = args.steps
+    if steps * per_frame > 150.0:
+        steps = max(1, int(150.0 / per_frame))
+    res = cpu_reference(frames, threads, budget_s=0, max_frames=0, steps=steps, warmup=min(args.warmup, 3))
+    fps = res["value"]
+    out = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": steps, "warmup": args.warmup, "ms_per_step": round(1e3 / fps, 4) if fps else None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "C2: 640x480 RGBA32, %d triangle commands/frame (textured, Gouraud, Z-buffered, 2-cycle, bilinear), "
+                               "fill-rect clears, 8 LoadTile, SyncFull + 480i weave scan-out" % prims_per_frame,
+                   "command_bytes_per_frame": frame_bytes, "requested_steps": args.steps,
+                   "renderer": "Angrylion-Plus (reference's bundled CPU renderer), scanline-parallel worker pool"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "reference", "sample": res["sample"]},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=320)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--triangles", type=int, default=5000)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--small", action="store_true", help="fewer distinct frames (quick functional run; violates the L2 rule)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,32 @@ void *rdpb_stream(rdpb_device *dev);                 /* cudaStream_t for interop
 /* Instrumentation: number of kernels launched since creation. */
 uint64_t rdpb_launch_count(rdpb_device *dev);
 
+/* ---- Measurement plumbing (bench.py / profiling only; not used by the host renderer) ------------------------ */
+enum
+{
+	RDPB_KERNEL_TMEM_UPDATE = 0,
+	RDPB_KERNEL_PRIM_SETUP = 1,
+	RDPB_KERNEL_SPAN_BIN = 2,
+	RDPB_KERNEL_TILES = 3,
+	RDPB_KERNEL_VI_FILTER = 4,
+	RDPB_KERNEL_VI_SCALE = 5,
+	RDPB_KERNEL_COUNT = 6
+};
+
+/* Per-kernel device time from CUDA events recorded around every launch on the launching stream. */
+int rdpb_profile_enable(rdpb_device *dev, int on, uint32_t max_launches);
+int rdpb_profile_read(rdpb_device *dev, int kernel, uint32_t *launches, double *total_ms);
+/* out8[0] = non-empty tiles processed by the tile kernel, out8[1] = shaded (pixel, primitive) pairs. */
+int rdpb_counters_read(rdpb_device *dev, uint64_t *out8, int reset);
+/* Record the GPU work of everything submitted between begin/end while keeping its inputs resident in device
+ * memory; rdpb_record_mark() separates steps (frames).  rdpb_replay_step() re-issues one step's kernel launches
+ * from those resident inputs: no host->device traffic at all. */
+int rdpb_record_begin(rdpb_device *dev, size_t arena_bytes);
+int rdpb_record_mark(rdpb_device *dev);
+int rdpb_record_end(rdpb_device *dev);
+uint32_t rdpb_record_steps(rdpb_device *dev);
+int rdpb_replay_step(rdpb_device *dev, uint32_t step);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,14 @@ class Oracle:
         w = np.ascontiguousarray(words, dtype=np.uint32)
         return self.lib.ref_command_stream(w.ctypes.data, w.size)
 
+    def process_list(self, words: np.ndarray, list_addr: int) -> None:
+        """Run a packed stream as an in-RDRAM display list (engages the oracle's worker pool when parallel=True)."""
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        self.lib.ref_process_list.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        self.lib.ref_process_list.restype = C.c_int
+        if self.lib.ref_process_list(w.ctypes.data, w.size, list_addr) != 0:
+            raise RuntimeError("ref_process_list: display list does not fit in RDRAM")
+
     def set_vi_register(self, reg: int, value: int):
         self.lib.ref_set_vi_register(reg, value & 0xffffffff)
 

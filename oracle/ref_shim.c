@@ -155,6 +155,23 @@ uint32_t ref_command_stream(const uint32_t *words, uint32_t num_words)
     return n;
 }
 
+/* Feed a packed command stream the way real hardware does: as a display list in RDRAM consumed by
+ * n64video_process_list() (reference: angrylion n64video.c:230-310).  This is the only route that engages the
+ * oracle's scanline-parallel worker pool (config.parallel), so the multi-core CPU baseline uses it.
+ * `list_addr` must be 8-byte aligned and the list must fit below rdram_size. */
+int ref_process_list(const uint32_t *words, uint32_t num_words, uint32_t list_addr)
+{
+    if ((list_addr & 7u) || (uint64_t)list_addr + (uint64_t)num_words * 4u > g_rdram_size)
+        return -1;
+    memcpy(g_rdram + list_addr, words, (size_t)num_words * 4u); /* RDRAM is stored as host-endian 32-bit words */
+    g_dp_regs[DP_STATUS] = 0; /* no XBUS DMA: read the list from RDRAM */
+    g_dp_regs[DP_START] = list_addr;
+    g_dp_regs[DP_CURRENT] = list_addr;
+    g_dp_regs[DP_END] = list_addr + num_words * 4u;
+    n64video_process_list();
+    return 0;
+}
+
 void ref_set_vi_register(uint32_t reg, uint32_t value)
 {
     if (reg < VI_NUM_REG)

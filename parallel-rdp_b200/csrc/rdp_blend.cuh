@@ -525,11 +525,12 @@ RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup 
 }
 
 // Walk one pixel through one binned primitive (shade, then fill / copy / depth-blend).
-RDP_HD void process_pixel_primitive(const ShadeContext &ctx, const FbView &fb, PixelState &px, int x, int y, uint32_t prim)
+// Returns true when the pixel was shaded (a "shaded pixel" of the Mpix/s metric: shade_pixel returned true).
+RDP_HD bool process_pixel_primitive(const ShadeContext &ctx, const FbView &fb, PixelState &px, int x, int y, uint32_t prim)
 {
 	Shaded sh;
 	if (!shade_pixel(ctx, x, y, prim, sh))
-		return;
+		return false;
 	const PrimSetup &p = ctx.prims[prim];
 	const PassState &st = ctx.states[p.state_id];
 	if (sh.kind == 1)
@@ -538,6 +539,7 @@ RDP_HD void process_pixel_primitive(const ShadeContext &ctx, const FbView &fb, P
 		copy_pixel(fb, px, sh.raw);
 	else
 		depth_blend_pixel(fb, px, p, st, sh);
+	return true;
 }
 
 // Blender divider table (reference data: parallel-rdp/luts.hpp blender_lut, itself generated by the oracle's

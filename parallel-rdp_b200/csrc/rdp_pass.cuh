@@ -30,6 +30,7 @@ struct PassBuffers
 	uint8_t *rdram;
 	uint8_t *hidden;
 	const uint8_t *blend_lut;
+	unsigned long long *counters; // [0] non-empty tiles processed, [1] shaded (pixel, primitive) pairs
 };
 
 // ---- stage 1 -------------------------------------------------------------------------------------
@@ -128,9 +129,11 @@ RDP_HD void pass_pixel_end(const FbInfo &fb, const FbView &view, PixelState &px,
 	store_depth(view, px, (fb.depth_addr >> 1) + pix);
 }
 
-RDP_HD void pass_pixel_walk(const PassBuffers &b, const FbInfo &fb, const FbView &view, PixelState &px, int x, int y,
-                            uint32_t tile)
+// Returns the number of primitives that shaded this pixel.
+RDP_HD uint32_t pass_pixel_walk(const PassBuffers &b, const FbInfo &fb, const FbView &view, PixelState &px, int x, int y,
+                                uint32_t tile)
 {
+	uint32_t shaded = 0;
 	ShadeContext ctx;
 	ctx.prims = b.prims;
 	ctx.states = b.states;
@@ -154,10 +157,12 @@ RDP_HD void pass_pixel_walk(const PassBuffers &b, const FbInfo &fb, const FbView
 			{
 				const int i = find_lsb(bits);
 				bits &= bits - 1u;
-				process_pixel_primitive(ctx, view, px, x, y, group * 32u + uint32_t(i));
+				if (process_pixel_primitive(ctx, view, px, x, y, group * 32u + uint32_t(i)))
+					shaded++;
 			}
 		}
 	}
+	return shaded;
 }
 
 // Zero the mask words of one tile after its pixels are done, so the next pass starts from clean masks.

@@ -219,9 +219,12 @@ RDP_HD ViColor vi_fetch_pixel(const ViFrame &f, const ViBuffers &b, int x, int y
 				acc[2] += vi_clamp1((c.b >> 3) - base[2]);
 			}
 		}
-		out.r = (mid.r & 0xf8) + acc[0];
-		out.g = (mid.g & 0xf8) + acc[1];
-		out.b = (mid.b & 0xf8) + acc[2];
+		// The reference shader masks the centre to 5 bits here (vi_fetch.frag:144); that is a no-op for 16-bit
+		// framebuffers but differs from the oracle for 32-bit ones (angrylion vi/restore.c:98-140 keeps all 8
+		// bits).  We follow the oracle.
+		out.r = mid.r + acc[0];
+		out.g = mid.g + acc[1];
+		out.b = mid.b + acc[2];
 	}
 	out.a = mid.a;
 	return out;

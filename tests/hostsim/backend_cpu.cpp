@@ -32,6 +32,7 @@ struct rdpb_device
 	std::vector<uint32_t> vi_stage[3];
 	std::vector<uint32_t> vi_out, vi_prev;
 	uint64_t launches = 0;
+	unsigned long long counters[8] = {};
 	std::string error;
 
 	PassBuffers buffers()
@@ -50,6 +51,7 @@ struct rdpb_device
 		b.rdram = rdram.data();
 		b.hidden = hidden.data();
 		b.blend_lut = blend_lut.data();
+		b.counters = counters;
 		return b;
 	}
 };
@@ -195,11 +197,12 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info)
 					FbView view;
 					PixelState px;
 					pass_pixel_begin(b, fb, view, px, x, y);
-					pass_pixel_walk(b, fb, view, px, x, y, tile);
+					dev->counters[1] += pass_pixel_walk(b, fb, view, px, x, y, tile);
 					pass_pixel_end(fb, view, px, x, y);
 				}
 			}
 			pass_tile_clear_masks(b, fb, tile);
+			dev->counters[0]++;
 		}
 	}
 	dev->launches++;
@@ -253,4 +256,26 @@ int rdpb_wait(rdpb_device *, uint64_t) { return 0; }
 int rdpb_sync(rdpb_device *) { return 0; }
 void *rdpb_stream(rdpb_device *) { return nullptr; }
 uint64_t rdpb_launch_count(rdpb_device *dev) { return dev->launches; }
+
+// Measurement plumbing: only the counters exist on the simulator; timing and replay are CUDA-only.
+int rdpb_profile_enable(rdpb_device *, int, uint32_t) { return -1; }
+int rdpb_profile_read(rdpb_device *, int, uint32_t *launches, double *total_ms)
+{
+	*launches = 0;
+	*total_ms = 0.0;
+	return -1;
+}
+int rdpb_counters_read(rdpb_device *dev, uint64_t *out8, int reset)
+{
+	for (int i = 0; i < 8; i++)
+		out8[i] = dev->counters[i];
+	if (reset)
+		memset(dev->counters, 0, sizeof(dev->counters));
+	return 0;
+}
+int rdpb_record_begin(rdpb_device *, size_t) { return -1; }
+int rdpb_record_mark(rdpb_device *) { return -1; }
+int rdpb_record_end(rdpb_device *) { return -1; }
+uint32_t rdpb_record_steps(rdpb_device *) { return 0; }
+int rdpb_replay_step(rdpb_device *, uint32_t) { return -1; }
 }
