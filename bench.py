@@ -266,8 +266,8 @@ def run_ours(args):
     p1.synchronize()
     profiled_ms = p0.elapsed_time(p1)
     kernel_ms = {}
-    names = ["tmem_update", "prim_setup", "span_bin", "tiles", "vi_filter", "vi_scale"]
-    for kid, kname in enumerate(names):
+    names = {0: "front", 2: "span_bin", 3: "tiles", 4: "vi_filter", 5: "vi_scale"}
+    for kid, kname in names.items():
         n, total = C.c_uint32(0), C.c_double(0.0)
         lib.rdpb_profile_read(dev, kid, C.byref(n), C.byref(total))
         kernel_ms[kname] = {"launches": int(n.value), "total_ms": round(total.value, 4)}

@@ -6,8 +6,8 @@
  *   buffers / RDRAM mirror   <- Vulkan::Device::create_buffer / map_host_buffer / copy_buffer
  *                               (parallel-rdp/rdp_device.cpp:54-131,245-261; rdp_renderer.cpp:603-658)
  *   pass staging + submit    <- RenderBuffersUpdater::upload            (rdp_renderer.cpp:1592-1632)
- *   rdpb_launch_tmem_update  <- Renderer::update_tmem_instances         (rdp_renderer.cpp:1634-1668)
- *   rdpb_launch_prim_setup   <- CPU-side decode in the reference        (rdp_device.cpp:268-419, rdp_renderer.cpp:910-925)
+ *   rdpb_launch_front        <- Renderer::update_tmem_instances         (rdp_renderer.cpp:1634-1668)
+ *                               + CPU-side decode in the reference      (rdp_device.cpp:268-419, rdp_renderer.cpp:910-925)
  *   rdpb_launch_span_bin     <- submit_span_setup_jobs + submit_tile_binning_combined (rdp_renderer.cpp:1670-1700,1832-1935)
  *   rdpb_launch_tiles        <- submit_rasterization + submit_depth_blend (rdp_renderer.cpp:1721-1830,2086-2221)
  *   rdpb_launch_vi_*         <- VideoInterface::*_stage                 (video_interface.cpp:405-999)
@@ -69,8 +69,9 @@ void *rdpb_hidden_device_ptr(rdpb_device *dev);
 /* Pass recording and submission. */
 int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out);
 int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *counts);
-int rdpb_launch_tmem_update(rdpb_device *dev, uint32_t num_uploads);
-int rdpb_launch_prim_setup(rdpb_device *dev, uint32_t num_prims);
+/* Front end of a pass in one launch: replay `num_uploads` texture loads into TMEM snapshots (when update_tmem),
+ * decode `num_prims` primitives from their raw command words and allocate their span jobs. */
+int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims);
 int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo */);
 int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo */);
 int rdpb_pass_end(rdpb_device *dev);
@@ -94,8 +95,8 @@ uint64_t rdpb_launch_count(rdpb_device *dev);
 /* ---- Measurement plumbing (bench.py / profiling only; not used by the host renderer) ------------------------ */
 enum
 {
-	RDPB_KERNEL_TMEM_UPDATE = 0,
-	RDPB_KERNEL_PRIM_SETUP = 1,
+	RDPB_KERNEL_FRONT = 0, /* texture-load replay + primitive set-up, one launch */
+	RDPB_KERNEL_RESERVED = 1,
 	RDPB_KERNEL_SPAN_BIN = 2,
 	RDPB_KERNEL_TILES = 3,
 	RDPB_KERNEL_VI_FILTER = 4,

@@ -44,65 +44,101 @@ struct StagingLayout
 	static constexpr size_t total = uploads_off + size_t(kMaxUploadsPerPass) * sizeof(TmemUpload);
 };
 
-__global__ void k_tmem_update(PassBuffers b, uint32_t num_uploads, uint32_t rdram_size)
-{
-	const int slot = int(blockIdx.x * blockDim.x + threadIdx.x);
-	if (slot < int(kTmemBytes / 2))
-		pass_tmem_word(b, num_uploads, rdram_size, slot);
-}
+// Front end of a pass, one launch: the first `tmem_blocks` blocks replay the pass's texture loads (one thread per
+// TMEM word), the remaining blocks decode one primitive per thread and allocate its span jobs.
+constexpr uint32_t kFrontThreads = 256;
+constexpr uint32_t kTmemBlocks = kTmemBytes / 2 / kFrontThreads;
 
-__global__ void k_prim_setup(PassBuffers b, uint32_t num_prims)
+__global__ void __launch_bounds__(kFrontThreads) k_front(PassBuffers b, uint32_t tmem_blocks, uint32_t num_uploads,
+                                                         uint32_t rdram_size, uint32_t num_prims)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (blockIdx.x < tmem_blocks)
+	{
+		pass_tmem_word(b, num_uploads, rdram_size, int(blockIdx.x * kFrontThreads + threadIdx.x));
+		return;
+	}
+
+	const uint32_t i = (blockIdx.x - tmem_blocks) * kFrontThreads + threadIdx.x;
+	uint32_t njobs = 0;
 	if (i < num_prims)
+	{
 		pass_setup_prim(b, i);
+		const PrimRecord rec = b.records[i];
+		njobs = span_job_count(rec.line_lo, rec.line_hi);
+	}
+
+	// Warp-wide exclusive scan of the job counts, one atomic per warp, then every lane writes its own jobs.
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t incl = njobs;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1)
+	{
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+		if (lane >= uint32_t(off))
+			incl += v;
+	}
+	const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+	uint32_t base = 0;
+	if (lane == 31 && total)
+		base = atomicAdd(b.job_counter, total);
+	base = __shfl_sync(0xffffffffu, base, 31) + incl - njobs;
+	for (uint32_t k = 0; k < njobs; k++)
+		b.jobs[base + k] = span_job_pack(i, k);
 }
 
+// One warp per span job (primitive, 32-line chunk); lane = scanline.  Each 4-lane group is one tile row: the
+// group shuffle-reduces the row's X range, then its lanes split the row's tiles and OR the primitive's bit in.
 __global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
 {
-	const uint32_t prim = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t job_index = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = int(threadIdx.x & 31u);
-	if (prim >= fb.num_prims)
+	if (job_index >= fb.num_jobs)
 		return;
+	const uint32_t job = b.jobs[job_index];
+	const uint32_t prim = job & 0xffffu;
 	const PrimSetup &p = b.prims[prim];
-	if (p.flags & SF_NO_PIXELS)
-		return;
 
-	const int first = int(p.line_lo) & ~7; // keep 8-lane groups aligned with tile rows
-	const int last = int(p.line_hi) + 1;
-	const int sub = lane & 7;
-	for (int y0 = first; y0 <= last; y0 += 32)
-	{
-		const int y = y0 + lane;
-		int lo, hi;
-		pass_span_line(b, fb, p, y, lo, hi);
-		int mn = lo <= hi ? lo : 0x7fffffff;
-		int mx = lo <= hi ? hi : -1;
+	const int first = int(p.line_lo) & ~int(kTileH - 1);
+	const int y = first + int(job >> 16) * int(kSpanJobLines) + lane;
+	const int sub = lane & int(kTileH - 1);
+
+	int lo, hi;
+	pass_span_line(b, fb, p, y, lo, hi);
+	int mn = lo <= hi ? lo : 0x7fffffff;
+	int mx = lo <= hi ? hi : -1;
 #pragma unroll
-		for (int off = 1; off < 8; off <<= 1)
+	for (int off = 1; off < int(kTileH); off <<= 1)
+	{
+		mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+		mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+	}
+	if (mn <= mx)
+	{
+		const uint32_t group = prim >> 5, bit = 1u << (prim & 31u);
+		const uint32_t cgroup = group >> 5, cbit = 1u << (group & 31u);
+		const uint32_t row = uint32_t(y / int(kTileH)) * fb.tiles_x;
+		for (int tx = (mn >> 3) + sub; tx <= (mx >> 3); tx += int(kTileH))
 		{
-			mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-			mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-		}
-		if (mn <= mx)
-		{
-			// The eight lanes of a tile row split the row's tiles between them.
-			const uint32_t group = prim >> 5, bit = 1u << (prim & 31u);
-			const uint32_t cgroup = group >> 5, cbit = 1u << (group & 31u);
-			const uint32_t row = uint32_t(y >> 3) * fb.tiles_x;
-			for (int tx = (mn >> 3) + sub; tx <= (mx >> 3); tx += 8)
-			{
-				const size_t tile = row + uint32_t(tx);
-				atomicOr(&b.fine_mask[tile * fb.mask_stride + group], bit);
-				atomicOr(&b.coarse_mask[tile * fb.coarse_stride + cgroup], cbit);
-			}
+			const size_t tile = row + uint32_t(tx);
+			atomicOr(&b.fine_mask[tile * fb.mask_stride + group], bit);
+			atomicOr(&b.coarse_mask[tile * fb.coarse_stride + cgroup], cbit);
 		}
 	}
 }
 
-__global__ void __launch_bounds__(64) k_tiles(PassBuffers b, FbInfo fb)
+// One warp per 8x4 tile, one thread per pixel; warps never synchronise with each other.  A block is four
+// horizontally adjacent tiles (they mostly see the same primitives, which keeps L1 warm).
+constexpr uint32_t kTileWarpsPerBlock = 4;
+
+__global__ void __launch_bounds__(kTileWarpsPerBlock * 32) k_tiles(PassBuffers b, FbInfo fb)
 {
-	const uint32_t tile = blockIdx.y * fb.tiles_x + blockIdx.x;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t tile = blockIdx.x * kTileWarpsPerBlock + (threadIdx.x >> 5);
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		*b.job_counter = 0; // the span jobs of this pass are consumed; the next pass allocates from zero
+	if (tile >= fb.tiles_x * fb.tiles_y)
+		return;
+
 	const uint32_t *coarse = b.coarse_mask + size_t(tile) * fb.coarse_stride;
 	uint32_t any = 0;
 	for (uint32_t cw = 0; cw < fb.coarse_stride; cw++)
@@ -110,8 +146,9 @@ __global__ void __launch_bounds__(64) k_tiles(PassBuffers b, FbInfo fb)
 	if (!any)
 		return;
 
-	const int x = int(blockIdx.x * kTileW + (threadIdx.x & 7u));
-	const int y = int(blockIdx.y * kTileH + (threadIdx.x >> 3));
+	const uint32_t tx = tile % fb.tiles_x, ty = tile / fb.tiles_x;
+	const int x = int(tx * kTileW + (lane & 7u));
+	const int y = int(ty * kTileH + (lane >> 3));
 	uint32_t shaded = 0;
 	if (x < int(fb.width) && y < int(fb.height))
 	{
@@ -123,12 +160,12 @@ __global__ void __launch_bounds__(64) k_tiles(PassBuffers b, FbInfo fb)
 	}
 	// One atomic per warp keeps the "shaded pixels" metric essentially free.
 	const uint32_t warp_total = __reduce_add_sync(0xffffffffu, shaded);
-	if ((threadIdx.x & 31u) == 0 && warp_total)
-		atomicAdd(&b.counters[1], (unsigned long long)warp_total);
-	__syncthreads();
-	if (threadIdx.x == 0)
+	__syncwarp();
+	if (lane == 0)
 	{
 		pass_tile_clear_masks(b, fb, tile);
+		if (warp_total)
+			atomicAdd(&b.counters[1], (unsigned long long)warp_total);
 		atomicAdd(&b.counters[0], 1ull);
 	}
 }
@@ -152,8 +189,7 @@ __global__ void __launch_bounds__(256) k_vi_scale(ViFrame f, ViBuffers b)
 // One GPU-side operation, as issued live or replayed from the log.
 enum OpKind
 {
-	GOP_TMEM = RDPB_KERNEL_TMEM_UPDATE,
-	GOP_SETUP = RDPB_KERNEL_PRIM_SETUP,
+	GOP_FRONT = RDPB_KERNEL_FRONT,
 	GOP_SPAN = RDPB_KERNEL_SPAN_BIN,
 	GOP_TILES = RDPB_KERNEL_TILES,
 	GOP_VI = RDPB_KERNEL_VI_FILTER, // issues filter + scale
@@ -162,7 +198,7 @@ enum OpKind
 struct GpuOp
 {
 	int kind;
-	uint32_t count;
+	uint32_t count, count2, flag;
 	FbInfo fb;
 	ViFrame vi;
 	// device-resident inputs (live buffers, or arena slices when recorded)
@@ -198,6 +234,7 @@ struct rdpb_device
 	PrimSetup *d_prims = nullptr;
 	Span *d_spans = nullptr;
 	uint32_t *d_fine = nullptr, *d_coarse = nullptr;
+	uint32_t *d_jobs = nullptr, *d_job_counter = nullptr;
 
 	uint32_t *vi_filtered = nullptr;
 	uint32_t *vi_out[2] = {};
@@ -242,6 +279,8 @@ struct rdpb_device
 		b.spans = d_spans;
 		b.fine_mask = d_fine;
 		b.coarse_mask = d_coarse;
+		b.jobs = d_jobs;
+		b.job_counter = d_job_counter;
 		b.tmem = tmem_dev;
 		b.tmem_instances = tmem_instances;
 		b.rdram = rdram;
@@ -288,18 +327,16 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 {
 	switch (op.kind)
 	{
-	case GOP_TMEM:
+	case GOP_FRONT:
 	{
-		const int s = prof_begin(dev, RDPB_KERNEL_TMEM_UPDATE);
-		k_tmem_update<<<kTmemBytes / 2 / 256, 256, 0, dev->stream>>>(dev->buffers(op), op.count, dev->rdram_size);
-		prof_end(dev, s);
-		dev->launches++;
-		break;
-	}
-	case GOP_SETUP:
-	{
-		const int s = prof_begin(dev, RDPB_KERNEL_PRIM_SETUP);
-		k_prim_setup<<<(op.count + 127) / 128, 128, 0, dev->stream>>>(dev->buffers(op), op.count);
+		// op.count = primitives, op.count2 = uploads, op.flag = replay texture loads / re-snapshot TMEM
+		const uint32_t tmem_blocks = op.flag ? kTmemBlocks : 0u;
+		const uint32_t setup_blocks = (op.count + kFrontThreads - 1) / kFrontThreads;
+		if (tmem_blocks + setup_blocks == 0)
+			break;
+		const int s = prof_begin(dev, RDPB_KERNEL_FRONT);
+		k_front<<<tmem_blocks + setup_blocks, kFrontThreads, 0, dev->stream>>>(dev->buffers(op), tmem_blocks, op.count2,
+		                                                                     dev->rdram_size, op.count);
 		prof_end(dev, s);
 		dev->launches++;
 		break;
@@ -308,7 +345,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	{
 		const uint32_t warps_per_block = 4;
 		const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN);
-		k_span_bin<<<(op.fb.num_prims + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
+		k_span_bin<<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
 		prof_end(dev, s);
 		dev->launches++;
 		break;
@@ -316,7 +353,8 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	case GOP_TILES:
 	{
 		const int s = prof_begin(dev, RDPB_KERNEL_TILES);
-		k_tiles<<<dim3(op.fb.tiles_x, op.fb.tiles_y), 64, 0, dev->stream>>>(dev->buffers(op), op.fb);
+		const uint32_t tiles = op.fb.tiles_x * op.fb.tiles_y;
+		k_tiles<<<(tiles + kTileWarpsPerBlock - 1) / kTileWarpsPerBlock, kTileWarpsPerBlock * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
 		prof_end(dev, s);
 		dev->launches++;
 		break;
@@ -427,6 +465,8 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	const size_t coarse_bytes = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 1024) * 4;
 	need(cudaMalloc(&dev->d_fine, fine_bytes), "cudaMalloc fine masks");
 	need(cudaMalloc(&dev->d_coarse, coarse_bytes), "cudaMalloc coarse masks");
+	need(cudaMalloc(&dev->d_jobs, size_t(kMaxJobsPerPass) * 4), "cudaMalloc span jobs");
+	need(cudaMalloc(&dev->d_job_counter, 256), "cudaMalloc job counter");
 	need(cudaMalloc(&dev->vi_filtered, size_t(kViStageWidth) * kViStageHeight * 2 * 4), "cudaMalloc vi filtered");
 	const size_t max_out = size_t(640) * 576 * 4;
 	need(cudaMalloc(&dev->vi_out[0], max_out), "cudaMalloc vi out");
@@ -447,6 +487,7 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		need(cudaMemsetAsync(dev->hidden, 0, hidden_size, dev->stream), "memset hidden");
 		need(cudaMemsetAsync(dev->d_fine, 0, fine_bytes, dev->stream), "memset fine");
 		need(cudaMemsetAsync(dev->d_coarse, 0, coarse_bytes, dev->stream), "memset coarse");
+		need(cudaMemsetAsync(dev->d_job_counter, 0, 256, dev->stream), "memset job counter");
 		need(cudaMemsetAsync(dev->d_counters, 0, 8 * sizeof(unsigned long long), dev->stream), "memset counters");
 		need(cudaMemsetAsync(dev->vi_out[0], 0, max_out, dev->stream), "memset vi out");
 		need(cudaMemsetAsync(dev->vi_out[1], 0, max_out, dev->stream), "memset vi out");
@@ -498,6 +539,8 @@ void rdpb_device_destroy(rdpb_device *dev)
 	cudaFree(dev->d_spans);
 	cudaFree(dev->d_fine);
 	cudaFree(dev->d_coarse);
+	cudaFree(dev->d_jobs);
+	cudaFree(dev->d_job_counter);
 	cudaFree(dev->vi_filtered);
 	for (auto &s : dev->vi_out)
 		cudaFree(s);
@@ -644,23 +687,16 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 	return 0;
 }
 
-int rdpb_launch_tmem_update(rdpb_device *dev, uint32_t num_uploads)
+int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims)
 {
 	cudaSetDevice(dev->ordinal);
-	GpuOp op = {};
-	op.kind = GOP_TMEM;
-	op.count = num_uploads;
-	return submit(dev, op);
-}
-
-int rdpb_launch_prim_setup(rdpb_device *dev, uint32_t num_prims)
-{
-	cudaSetDevice(dev->ordinal);
-	if (!num_prims)
+	if (!update_tmem && !num_prims)
 		return 0;
 	GpuOp op = {};
-	op.kind = GOP_SETUP;
+	op.kind = GOP_FRONT;
 	op.count = num_prims;
+	op.count2 = num_uploads;
+	op.flag = update_tmem ? 1u : 0u;
 	return submit(dev, op);
 }
 
@@ -670,7 +706,7 @@ int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 	GpuOp op = {};
 	op.kind = GOP_SPAN;
 	op.fb = *static_cast<const FbInfo *>(fb_info);
-	if (!op.fb.num_prims)
+	if (!op.fb.num_jobs)
 		return 0;
 	return submit(dev, op);
 }

@@ -8,6 +8,7 @@
 // against the Angrylion oracle (tests/hostsim) and runs in the CUDA tile kernel.
 #pragma once
 #include "rdp_setup.cuh"
+#include "rdp_spec.h"
 
 namespace rdpb
 {
@@ -263,24 +264,6 @@ RDP_HD Vec4 expand_ia16(uint32_t word)
 	return vec4(i, i, i, a);
 }
 
-// Texel fetch kinds, resolved once per sample from (format, size, tlut).
-enum TexelKind
-{
-	TK_I4,     // 4-bit replicated (RGBA4 / I4)
-	TK_IA4,
-	TK_CI4,    // 4-bit index | palette, no TLUT
-	TK_I8,     // 8-bit replicated (RGBA8 / CI8 / I8)
-	TK_IA8,
-	TK_RGBA16,
-	TK_IA16,
-	TK_RAW16,  // 16-bit word split into two bytes, replicated (the "32-bit CI/IA/I" oddities)
-	TK_RGBA32,
-	TK_YUV16,
-	TK_CI4_TLUT,
-	TK_CI8_TLUT,
-	TK_CI16_TLUT,
-};
-
 RDP_HD int resolve_texel_kind(int fmt, int size, bool tlut)
 {
 	if (tlut)
@@ -456,9 +439,14 @@ RDP_HD int bilerp3(int base, int t10, int t01, int f0, int f1)
 }
 
 // Full texture sample for one cycle: texture.h:498-923
+// TK_MASK: bit k set when texel kind k can occur (~0u in the generic kernel).
+template <uint32_t TK_MASK>
 RDP_HD Vec4 sample_texture(const TileDesc &tile, const uint8_t *tmem, int s, int t, uint32_t rf, bool bilerp,
                            bool convert_one, const int16_t *k, const Vec4 &prev_cycle)
 {
+	constexpr bool kind_is_static = ct_single_bit(TK_MASK);
+	constexpr int static_kind = int(ct_log2(TK_MASK));
+	constexpr bool may_be_yuv = (TK_MASK & (1u << TK_YUV16)) != 0;
 	const bool tlut = (rf & RF_TLUT) != 0;
 	const bool tlut_ia = (rf & RF_TLUT_IA) != 0;
 	const bool sample_quad = (rf & RF_SAMPLE_QUAD) != 0;
@@ -492,13 +480,13 @@ RDP_HD Vec4 sample_texture(const TileDesc &tile, const uint8_t *tmem, int s, int
 	if (mid_texel)
 		sum_frac = 0; // forces all four texels to be fetched
 
-	const bool yuv = !tlut && tile.fmt == 1;
+	const bool yuv = may_be_yuv && !tlut && tile.fmt == 1;
 	const bool upper = sum_frac >= 0x20;
 	int base_s = upper ? s1 : s0;
 	int base_t = upper ? t1 : t0;
 	const int chroma_frac = ((s0 & 1) << 4) | (frac_s >> 1);
 
-	const int kind = resolve_texel_kind(tile.fmt, tile.size, tlut);
+	const int kind = kind_is_static ? static_kind : resolve_texel_kind(tile.fmt, tile.size, tlut);
 	Vec4 tb, t10 = splat4(0), t01 = splat4(0), t11 = splat4(0);
 
 	if (tlut)
@@ -877,10 +865,10 @@ RDP_HD int combine_channel(int a, int b, int c, int d)
 	return (((a - b) * c + 0x80) >> 8) + d;
 }
 
-RDP_HD Vec4 run_combiner_equation(const CombinerRegs &in, const PassState &st, int cycle)
+RDP_HD Vec4 run_combiner_equation(const CombinerRegs &in, const PassState &st, const StaticModes &m, int cycle)
 {
-	const uint8_t *rs = st.comb_rgb[cycle];
-	const uint8_t *as = st.comb_alpha[cycle];
+	const int *rs = m.comb_rgb[cycle];
+	const int *as = m.comb_alpha[cycle];
 	int ar, ag, ab, br, bg, bb, cr, cg, cb, dr, dg, db;
 	bool hit;
 
@@ -942,10 +930,10 @@ RDP_HD Vec4 run_combiner_equation(const CombinerRegs &in, const PassState &st, i
 }
 
 // First cycle of 2-cycle mode: result stays unclamped; yields the alpha-test reference.
-RDP_HD Vec4 combiner_first_cycle(const CombinerRegs &in, const PassState &st, int alpha_dith, int coverage, uint32_t rf,
-                                 int &alpha_ref)
+RDP_HD Vec4 combiner_first_cycle(const CombinerRegs &in, const PassState &st, const StaticModes &m, int alpha_dith,
+                                 int coverage, uint32_t rf, int &alpha_ref)
 {
-	Vec4 c = run_combiner_equation(in, st, 0);
+	Vec4 c = run_combiner_equation(in, st, m, 0);
 	if (rf & RF_ALPHA_TEST)
 	{
 		const int clamped = clamp_9bit(c.w);
@@ -962,9 +950,10 @@ RDP_HD Vec4 combiner_first_cycle(const CombinerRegs &in, const PassState &st, in
 }
 
 // Last (or only) cycle: clamps, and may fold coverage into alpha.
-RDP_HD Vec4 combiner_last_cycle(const CombinerRegs &in, const PassState &st, int alpha_dith, int &coverage, uint32_t rf)
+RDP_HD Vec4 combiner_last_cycle(const CombinerRegs &in, const PassState &st, const StaticModes &m, int alpha_dith,
+                                int &coverage, uint32_t rf)
 {
-	Vec4 c = run_combiner_equation(in, st, 1);
+	Vec4 c = run_combiner_equation(in, st, m, 1);
 	c.x = clamp_9bit(c.x);
 	c.y = clamp_9bit(c.y);
 	c.z = clamp_9bit(c.z);

@@ -34,7 +34,7 @@ enum : uint32_t
 	kMaxFbWidth = 1024,
 	kMaxFbHeight = 1024,
 	kTileW = 8,
-	kTileH = 8,
+	kTileH = 4, // one warp = one 8x4 tile: 8 pixels x 4 B = one 32-byte sector per row of an RGBA32 target
 	kMaxTilesX = kMaxFbWidth / kTileW,
 	kMaxTilesY = kMaxFbHeight / kTileH,
 	kTmemBytes = 4096,
@@ -264,7 +264,21 @@ struct FbInfo
 	uint32_t mask_stride;   // 32-bit words of fine mask per tile = ceil(num_prims/32)
 	uint32_t coarse_stride; // 32-bit words of coarse mask per tile = ceil(mask_stride/32)
 	uint32_t tiles_x, tiles_y;
+	uint32_t num_jobs; // span jobs = sum over primitives of span_job_count()
+	uint32_t pad[3];
 };
+
+// A span job is one (primitive, 32-scanline chunk): one warp of the span/bin kernel.  Chunks start at the
+// primitive's first tile row so that every 4-lane group of a warp owns exactly one tile row.
+enum : uint32_t { kSpanJobLines = 32, kMaxJobsPerPass = (kMaxSpansPerPass / kSpanJobLines) + kMaxPrimsPerPass };
+RDP_HD uint32_t span_job_count(int line_lo, int line_hi)
+{
+	if (line_hi < line_lo)
+		return 0;
+	const int first = line_lo & ~int(kTileH - 1);
+	return uint32_t((line_hi + 2 - first + int(kSpanJobLines) - 1) / int(kSpanJobLines));
+}
+RDP_HD uint32_t span_job_pack(uint32_t prim, uint32_t chunk) { return prim | (chunk << 16); }
 
 // ---------------------------------------------------------------------------------------------
 // VI

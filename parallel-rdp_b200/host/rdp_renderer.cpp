@@ -183,7 +183,8 @@ void Renderer::ensure_pass()
 		return;
 	rdpb_pass_begin(device, &pass);
 	pass_open = true;
-	num_words = num_prims = num_states = num_uploads = num_spans = 0;
+	num_words = num_prims = num_states = num_uploads = num_spans = num_jobs = 0;
+	pass_reads_tmem = false;
 	state_dirty = true;
 }
 
@@ -266,9 +267,12 @@ void Renderer::draw_primitive(const uint32_t *words, unsigned count)
 	if (line_hi >= line_lo)
 	{
 		num_spans += uint32_t(line_hi - line_lo + 2);
+		num_jobs += span_job_count(line_lo, line_hi);
 		fb.deduced_height = std::max(fb.deduced_height, uint32_t(line_hi + 1));
 	}
 
+	if (!(st.raster_flags & RF_FILL))
+		pass_reads_tmem = true;
 	fb.color_write_pending = true;
 	if (st.blend_flags & BF_Z_UPDATE)
 		fb.depth_write_pending = true;
@@ -314,11 +318,12 @@ void Renderer::flush_queues()
 
 	const bool need_render = fb.width != 0 && fb.deduced_height != 0 && num_spans != 0;
 
-	if (num_uploads != 0 || (need_render && !tmem_snapshot_valid))
-	{
-		rdpb_launch_tmem_update(device, num_uploads);
+	// Snapshot 0 must equal live TMEM at pass start; it is stale after a pass with uploads (or a host TMEM poke).
+	// A pass that never samples TMEM (fill-only clears) leaves it stale for the next one.
+	const bool update_tmem = num_uploads != 0 || (need_render && pass_reads_tmem && !tmem_snapshot_valid);
+	if (update_tmem)
 		tmem_snapshot_valid = num_uploads == 0;
-	}
+	rdpb_launch_front(device, update_tmem ? 1 : 0, num_uploads, need_render ? num_prims : 0);
 
 	if (need_render)
 	{
@@ -336,7 +341,7 @@ void Renderer::flush_queues()
 		info.tiles_x = (info.width + kTileW - 1) / kTileW;
 		info.tiles_y = (info.height + kTileH - 1) / kTileH;
 
-		rdpb_launch_prim_setup(device, num_prims);
+		info.num_jobs = num_jobs;
 		rdpb_launch_span_bin(device, &info);
 		rdpb_launch_tiles(device, &info);
 
@@ -352,7 +357,8 @@ void Renderer::flush_queues()
 
 	base_primitive_index += num_prims;
 	pass_open = false;
-	num_words = num_prims = num_states = num_uploads = num_spans = 0;
+	num_words = num_prims = num_states = num_uploads = num_spans = num_jobs = 0;
+	pass_reads_tmem = false;
 	fb.deduced_height = 0;
 	fb.color_write_pending = false;
 	fb.depth_write_pending = false;

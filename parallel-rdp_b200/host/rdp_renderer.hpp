@@ -121,7 +121,8 @@ private:
 	// Pass being recorded.
 	rdpb_pass_buffers pass = {};
 	bool pass_open = false;
-	uint32_t num_words = 0, num_prims = 0, num_states = 0, num_uploads = 0, num_spans = 0;
+	uint32_t num_words = 0, num_prims = 0, num_states = 0, num_uploads = 0, num_spans = 0, num_jobs = 0;
+	bool pass_reads_tmem = false;
 	uint32_t base_primitive_index = 0;
 	uint64_t pass_counter = 0;
 	bool tmem_snapshot_valid = false;

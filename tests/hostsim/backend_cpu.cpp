@@ -46,6 +46,8 @@ struct rdpb_device
 		b.spans = spans.data();
 		b.fine_mask = fine.data();
 		b.coarse_mask = coarse.data();
+		b.jobs = nullptr;
+		b.job_counter = nullptr;
 		b.tmem = tmem.data();
 		b.tmem_instances = tmem_instances.data();
 		b.rdram = rdram.data();
@@ -133,18 +135,12 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *counts)
 	return 0;
 }
 
-int rdpb_launch_tmem_update(rdpb_device *dev, uint32_t num_uploads)
+int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims)
 {
 	PassBuffers b = dev->buffers();
-	for (int slot = 0; slot < int(kTmemBytes / 2); slot++)
-		pass_tmem_word(b, num_uploads, dev->rdram_size, slot);
-	dev->launches++;
-	return 0;
-}
-
-int rdpb_launch_prim_setup(rdpb_device *dev, uint32_t num_prims)
-{
-	PassBuffers b = dev->buffers();
+	if (update_tmem)
+		for (int slot = 0; slot < int(kTmemBytes / 2); slot++)
+			pass_tmem_word(b, num_uploads, dev->rdram_size, slot);
 	for (uint32_t i = 0; i < num_prims; i++)
 		pass_setup_prim(b, i);
 	dev->launches++;
@@ -166,7 +162,7 @@ int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 			int lo, hi;
 			pass_span_line(b, fb, p, y, lo, hi);
 			if (lo <= hi)
-				pass_bin_row(fb, i, y >> 3, lo, hi, or_fn, b.fine_mask, b.coarse_mask);
+				pass_bin_row(fb, i, y / int(kTileH), lo, hi, or_fn, b.fine_mask, b.coarse_mask);
 		}
 	}
 	dev->launches++;
@@ -187,11 +183,11 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info)
 				any = any || b.coarse_mask[size_t(tile) * fb.coarse_stride + cw] != 0;
 			if (!any)
 				continue;
-			for (int ly = 0; ly < 8; ly++)
+			for (int ly = 0; ly < int(kTileH); ly++)
 			{
-				for (int lx = 0; lx < 8; lx++)
+				for (int lx = 0; lx < int(kTileW); lx++)
 				{
-					const int x = int(tx) * 8 + lx, y = int(ty) * 8 + ly;
+					const int x = int(tx) * int(kTileW) + lx, y = int(ty) * int(kTileH) + ly;
 					if (x >= int(fb.width) || y >= int(fb.height))
 						continue;
 					FbView view;
