@@ -111,6 +111,8 @@ uint64_t rdp_b200_launch_count(rdp_b200_processor *p);
 uint64_t rdp_b200_primitive_count(rdp_b200_processor *p);
 uint64_t rdp_b200_pass_count(rdp_b200_processor *p);
 void *rdp_b200_cuda_stream(rdp_b200_processor *p);
+/* Name of the tile-kernel instantiation the most recent render pass ran ("generic" = the uber-kernel fallback). */
+const char *rdp_b200_last_tile_variant(rdp_b200_processor *p);
 /* The backend device handle (rdpb_device*, include/rdp_b200_backend.h) for the measurement entry points. */
 void *rdp_b200_backend_device(rdp_b200_processor *p);
 

@@ -73,7 +73,11 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *counts);
  * decode `num_prims` primitives from their raw command words and allocate their span jobs. */
 int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims);
 int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo */);
-int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo */);
+/* `summary` (rdpb::PassSummary) describes what the pass's states have in common; the backend uses it to pick a
+ * specialised instantiation of the tile kernel (NULL: the generic one). */
+int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo */, const void *summary /* rdpb::PassSummary */);
+/* Name of the tile-kernel instantiation chosen for the most recent pass (diagnostics / tests). */
+const char *rdpb_last_tile_variant(rdpb_device *dev);
 int rdpb_pass_end(rdpb_device *dev);
 
 /* VI scan-out.  `frame` is rdpb::ViFrame (built by the host from the VI registers), `lines` rdpb::ViLine[288].

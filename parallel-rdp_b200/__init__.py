@@ -65,6 +65,7 @@ def _bind(lib):
         "rdp_b200_primitive_count": (U64, [P]),
         "rdp_b200_pass_count": (U64, [P]),
         "rdp_b200_cuda_stream": (P, [P]),
+        "rdp_b200_last_tile_variant": (C.c_char_p, [P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -199,6 +200,9 @@ class CommandProcessor:
 
     def pass_count(self) -> int:
         return self.lib.rdp_b200_pass_count(self._h)
+
+    def last_tile_variant(self) -> str:
+        return self.lib.rdp_b200_last_tile_variant(self._h).decode()
 
     def cuda_stream(self) -> int:
         return self.lib.rdp_b200_cuda_stream(self._h) or 0

@@ -24,6 +24,7 @@
 #include <deque>
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <utility>
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
 // horizontally adjacent tiles (they mostly see the same primitives, which keeps L1 warm).
 constexpr uint32_t kTileWarpsPerBlock = 4;
 
+template <class S>
 __global__ void __launch_bounds__(kTileWarpsPerBlock * 32) k_tiles(PassBuffers b, FbInfo fb)
 {
 	const uint32_t lane = threadIdx.x & 31u;
@@ -154,8 +156,8 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32) k_tiles(PassBuffers b
 	{
 		FbView view;
 		PixelState px;
-		pass_pixel_begin(b, fb, view, px, x, y);
-		shaded = pass_pixel_walk(b, fb, view, px, x, y, tile);
+		pass_pixel_begin<S>(b, fb, view, px, x, y);
+		shaded = pass_pixel_walk<S>(b, fb, view, px, x, y, tile);
 		pass_pixel_end(fb, view, px, x, y);
 	}
 	// One atomic per warp keeps the "shaded pixels" metric essentially free.
@@ -186,6 +188,57 @@ __global__ void __launch_bounds__(256) k_vi_scale(ViFrame f, ViBuffers b)
 		vi_scale_thread(f, b, x, y);
 }
 
+// ---- tile-kernel instantiations ------------------------------------------------------------------------------
+// Ordered from most to least specialised; a pass runs the first entry that covers all of its non-fill states
+// (rdp_spec.h).  The last entry is the fully dynamic uber-kernel.
+typedef void (*TileKernel)(PassBuffers, FbInfo);
+
+struct TileVariant
+{
+	const char *name;
+	uint32_t rf_may, rf_must, bf_may, bf_must, fmt_mask, tk_mask;
+	bool exact;
+	uint64_t comb_rgb;
+	uint32_t comb_alpha, blend_misc;
+	TileKernel kernel;
+};
+
+template <class S>
+static TileVariant make_variant(const char *name)
+{
+	return { name, S::rf_may, S::rf_must, S::bf_may, S::bf_must, S::fmt_mask, S::tk_mask, S::exact, S::comb_rgb, S::comb_alpha,
+		     S::blend_misc, &k_tiles<S> };
+}
+
+#include "rdp_variants.inc"
+
+static const TileVariant *pick_tile_variant(const PassSummary *sum, uint32_t fmt)
+{
+	const size_t n = sizeof(kTileVariants) / sizeof(kTileVariants[0]);
+	if (!sum || getenv("RDP_B200_FORCE_GENERIC"))
+		return &kTileVariants[n - 1];
+	for (size_t i = 0; i < n; i++)
+	{
+		const TileVariant &v = kTileVariants[i];
+		if (!(v.fmt_mask & (1u << fmt)))
+			continue;
+		if (sum->num_shaded_states != 0)
+		{
+			if ((sum->rf_or & ~v.rf_may) != 0 || (sum->rf_and & v.rf_must) != v.rf_must)
+				continue;
+			if ((sum->bf_or & ~v.bf_may) != 0 || (sum->bf_and & v.bf_must) != v.bf_must)
+				continue;
+			if ((sum->texel_kinds & ~v.tk_mask) != 0)
+				continue;
+			if (v.exact && (!sum->modes_uniform || sum->comb_rgb != v.comb_rgb || sum->comb_alpha != v.comb_alpha ||
+			                sum->blend_misc != v.blend_misc))
+				continue;
+		}
+		return &v;
+	}
+	return &kTileVariants[n - 1];
+}
+
 // One GPU-side operation, as issued live or replayed from the log.
 enum OpKind
 {
@@ -199,6 +252,7 @@ struct GpuOp
 {
 	int kind;
 	uint32_t count, count2, flag;
+	const TileVariant *variant;
 	FbInfo fb;
 	ViFrame vi;
 	// device-resident inputs (live buffers, or arena slices when recorded)
@@ -266,6 +320,8 @@ struct rdpb_device
 	const TmemUpload *cur_uploads = nullptr;
 
 	uint64_t launches = 0;
+	const TileVariant *last_variant = nullptr;
+	bool debug_summary = false;
 	std::string error;
 
 	PassBuffers buffers(const GpuOp &op) const
@@ -354,7 +410,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	{
 		const int s = prof_begin(dev, RDPB_KERNEL_TILES);
 		const uint32_t tiles = op.fb.tiles_x * op.fb.tiles_y;
-		k_tiles<<<(tiles + kTileWarpsPerBlock - 1) / kTileWarpsPerBlock, kTileWarpsPerBlock * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
+		op.variant->kernel<<<(tiles + kTileWarpsPerBlock - 1) / kTileWarpsPerBlock, kTileWarpsPerBlock * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
 		prof_end(dev, s);
 		dev->launches++;
 		break;
@@ -440,6 +496,7 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	dev->ordinal = cuda_ordinal;
 	dev->rdram_size = rdram_size;
 	dev->hidden_size = hidden_size;
+	dev->debug_summary = getenv("RDP_B200_DEBUG_PASSES") != nullptr;
 
 	bool ok = true;
 	auto need = [&](cudaError_t e, const char *what) { ok = ok && check(dev, e, what); };
@@ -711,12 +768,22 @@ int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 	return submit(dev, op);
 }
 
-int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info)
+const char *rdpb_last_tile_variant(rdpb_device *dev) { return dev->last_variant ? dev->last_variant->name : ""; }
+
+int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary)
 {
 	cudaSetDevice(dev->ordinal);
 	GpuOp op = {};
 	op.kind = GOP_TILES;
 	op.fb = *static_cast<const FbInfo *>(fb_info);
+	const PassSummary *sum = static_cast<const PassSummary *>(summary);
+	op.variant = pick_tile_variant(sum, op.fb.fmt);
+	dev->last_variant = op.variant;
+	if (dev->debug_summary && sum)
+		fprintf(stderr, "[rdp-b200] pass: prims=%u fmt=%u states=%u rf_or=%08x rf_and=%08x bf_or=%02x bf_and=%02x tk=%04x uniform=%u "
+		                "comb_rgb=%010llx comb_alpha=%06x blend_misc=%06x -> %s\n",
+		        op.fb.num_prims, op.fb.fmt, sum->num_shaded_states, sum->rf_or, sum->rf_and, sum->bf_or, sum->bf_and, sum->texel_kinds,
+		        sum->modes_uniform, (unsigned long long)sum->comb_rgb, sum->comb_alpha, sum->blend_misc, op.variant->name);
 	if (!op.fb.tiles_x || !op.fb.tiles_y)
 		return 0;
 	return submit(dev, op);

@@ -363,11 +363,13 @@ struct BlendInputs
 };
 
 // One blender cycle: blender.h:55-143
-RDP_HD void blend_cycle(const BlendInputs &in, const PassState &st, const uint8_t *modes, const DepthResult &d,
+template <class M>
+RDP_HD void blend_cycle(const BlendInputs &in, const PassState &st, uint32_t bf, const M &m, int cycle, const DepthResult &d,
                         bool final_cycle, const uint8_t *lut, int &or_, int &og, int &ob)
 {
-	const bool force_blend = (st.blend_flags & BF_FORCE_BLEND) != 0;
-	const bool color_on_cvg = (st.blend_flags & BF_COLOR_ON_CVG) != 0;
+	const int modes[4] = { m.blend(cycle, 0), m.blend(cycle, 1), m.blend(cycle, 2), m.blend(cycle, 3) };
+	const bool force_blend = (bf & BF_FORCE_BLEND) != 0;
+	const bool color_on_cvg = (bf & BF_COLOR_ON_CVG) != 0;
 
 	int r1, g1, b1;
 	switch (modes[2])
@@ -464,9 +466,11 @@ RDP_HD int blend_coverage(int coverage, int mem_coverage, bool blend_en, int mod
 }
 
 // memory_interfacing.h:488-571
-RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup &p, const PassState &st, const Shaded &sh)
+template <class M>
+RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup &p, const PassState &st,
+                              const M &m, const Shaded &sh)
 {
-	const uint32_t bf = st.blend_flags;
+	const uint32_t bf = m.bf;
 	const bool image_read = (bf & BF_IMAGE_READ) != 0;
 	int coverage = sh.coverage;
 
@@ -484,7 +488,7 @@ RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup 
 	in.ma = mem_cvg_bits;
 	const int mem_coverage = mem_cvg_bits >> 5;
 
-	const DepthResult d = depth_test(sh.z, p.dz, p.dz_compressed, px.depth, px.dz, coverage, mem_coverage, bf, st.z_mode);
+	const DepthResult d = depth_test(sh.z, p.dz, p.dz_compressed, px.depth, px.dz, coverage, mem_coverage, bf, m.z_mode());
 	const bool aa = (bf & BF_AA) != 0;
 	if (!d.pass || (aa && coverage == 0))
 		return;
@@ -495,12 +499,12 @@ RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup 
 	int r, g, b;
 	if (bf & BF_TWO_CYCLE)
 	{
-		blend_cycle(in, st, st.blend_modes[0], d, false, fb.blend_lut, r, g, b);
+		blend_cycle(in, st, bf, m, 0, d, false, fb.blend_lut, r, g, b);
 		in.pr = r; in.pg = g; in.pb = b;
-		blend_cycle(in, st, st.blend_modes[1], d, true, fb.blend_lut, r, g, b);
+		blend_cycle(in, st, bf, m, 1, d, true, fb.blend_lut, r, g, b);
 	}
 	else
-		blend_cycle(in, st, st.blend_modes[0], d, true, fb.blend_lut, r, g, b);
+		blend_cycle(in, st, bf, m, 0, d, true, fb.blend_lut, r, g, b);
 
 	if (bf & BF_DITHER)
 	{
@@ -509,7 +513,7 @@ RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup 
 		b = dither_channel(b, (sh.dither >> 6) & 7);
 	}
 
-	const int new_coverage = blend_coverage(coverage, mem_coverage, d.blend_en, st.cvg_mode);
+	const int new_coverage = blend_coverage(coverage, mem_coverage, d.blend_en, m.cvg_mode());
 	write_color(fb, px, r & 0xff, g & 0xff, b & 0xff, new_coverage << 5);
 
 	if (bf & BF_Z_UPDATE)
@@ -526,19 +530,35 @@ RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup 
 
 // Walk one pixel through one binned primitive (shade, then fill / copy / depth-blend).
 // Returns true when the pixel was shaded (a "shaded pixel" of the Mpix/s metric: shade_pixel returned true).
+// Fill-mode states are handled here for every specialisation; everything else goes through Spec S.
+template <class S>
 RDP_HD bool process_pixel_primitive(const ShadeContext &ctx, const FbView &fb, PixelState &px, int x, int y, uint32_t prim)
 {
-	Shaded sh;
-	if (!shade_pixel(ctx, x, y, prim, sh))
-		return false;
 	const PrimSetup &p = ctx.prims[prim];
+	if (y < p.line_lo || y > p.line_hi)
+		return false;
+	const Span &sp = ctx.spans[p.span_base + uint32_t(y - p.line_lo)];
+	if (!sp.valid)
+		return false;
 	const PassState &st = ctx.states[p.state_id];
-	if (sh.kind == 1)
+
+	if (st.raster_flags & RF_FILL)
+	{
+		if (x < sp.start_x || x > sp.end_x)
+			return false;
 		fill_pixel(fb, px, st.fill_color);
-	else if (sh.kind == 2)
+		return true;
+	}
+
+	StaticModes<S> m;
+	resolve_modes<S>(st, m);
+	Shaded sh;
+	if (!shade_pixel<S>(ctx, x, y, prim, p, sp, st, m, sh))
+		return false;
+	if (sh.kind == 2)
 		copy_pixel(fb, px, sh.raw);
 	else
-		depth_blend_pixel(fb, px, p, st, sh);
+		depth_blend_pixel(fb, px, p, st, m, sh);
 	return true;
 }
 

@@ -98,12 +98,13 @@ RDP_HD void pass_bin_row(const FbInfo &fb, uint32_t prim, int tile_y, int x_lo, 
 }
 
 // ---- stage 4 -------------------------------------------------------------------------------------
+template <class S>
 RDP_HD void pass_pixel_begin(const PassBuffers &b, const FbInfo &fb, FbView &view, PixelState &px, int x, int y)
 {
 	view.rdram = b.rdram;
 	view.hidden = b.hidden;
 	view.blend_lut = b.blend_lut;
-	view.fmt = fb.fmt;
+	view.fmt = resolve_fb_fmt<S>(fb.fmt);
 	view.rdram_size = fb.rdram_size;
 	view.alias = fb.color_addr == fb.depth_addr;
 
@@ -115,7 +116,7 @@ RDP_HD void pass_pixel_begin(const PassBuffers &b, const FbInfo &fb, FbView &vie
 	if (x < int(fb.width) && y < int(fb.height))
 	{
 		const uint32_t pix = fb.width * uint32_t(y) + uint32_t(x);
-		const uint32_t shift = fb.fmt == FB_RGBA8888 ? 2u : ((fb.fmt == FB_RGBA5551 || fb.fmt == FB_IA88) ? 1u : 0u);
+		const uint32_t shift = view.fmt == FB_RGBA8888 ? 2u : ((view.fmt == FB_RGBA5551 || view.fmt == FB_IA88) ? 1u : 0u);
 		px.color_index = (fb.color_addr >> shift) + pix;
 		load_color(view, px, px.color_index);
 		load_depth(view, px, (fb.depth_addr >> 1) + pix);
@@ -132,6 +133,7 @@ RDP_HD void pass_pixel_end(const FbInfo &fb, const FbView &view, PixelState &px,
 }
 
 // Returns the number of primitives that shaded this pixel.
+template <class S>
 RDP_HD uint32_t pass_pixel_walk(const PassBuffers &b, const FbInfo &fb, const FbView &view, PixelState &px, int x, int y,
                                 uint32_t tile)
 {
@@ -141,7 +143,7 @@ RDP_HD uint32_t pass_pixel_walk(const PassBuffers &b, const FbInfo &fb, const Fb
 	ctx.states = b.states;
 	ctx.spans = b.spans;
 	ctx.tmem = b.tmem_instances;
-	ctx.fb_fmt = fb.fmt;
+	ctx.fb_fmt = view.fmt;
 	ctx.base_prim_index = fb.base_prim_index;
 
 	const uint32_t *coarse = b.coarse_mask + size_t(tile) * fb.coarse_stride;
@@ -159,7 +161,7 @@ RDP_HD uint32_t pass_pixel_walk(const PassBuffers &b, const FbInfo &fb, const Fb
 			{
 				const int i = find_lsb(bits);
 				bits &= bits - 1u;
-				if (process_pixel_primitive(ctx, view, px, x, y, group * 32u + uint32_t(i)))
+				if (process_pixel_primitive<S>(ctx, view, px, x, y, group * 32u + uint32_t(i)))
 					shaded++;
 			}
 		}

@@ -264,28 +264,6 @@ RDP_HD Vec4 expand_ia16(uint32_t word)
 	return vec4(i, i, i, a);
 }
 
-RDP_HD int resolve_texel_kind(int fmt, int size, bool tlut)
-{
-	if (tlut)
-	{
-		// texture.h:548-600: the TLUT path only distinguishes texel size.
-		return size == 0 ? TK_CI4_TLUT : (size == 1 ? TK_CI8_TLUT : TK_CI16_TLUT);
-	}
-	switch (fmt)
-	{
-	case 0: // RGBA
-		return size == 0 ? TK_I4 : (size == 1 ? TK_I8 : (size == 2 ? TK_RGBA16 : TK_RGBA32));
-	case 1: // YUV
-		return TK_YUV16;
-	case 2: // CI
-		return size == 0 ? TK_CI4 : (size == 1 ? TK_I8 : TK_RAW16);
-	case 3: // IA
-		return size == 0 ? TK_IA4 : (size == 1 ? TK_IA8 : (size == 2 ? TK_IA16 : TK_RAW16));
-	default: // I (and the undefined formats 5..7 behave like I in the reference's switch fall-through: none sampled)
-		return size == 0 ? TK_I4 : (size == 1 ? TK_I8 : TK_RAW16);
-	}
-}
-
 // Fetch one texel.  lut_bank / addr_xor select which of the four replicated TLUT banks is read
 // (texture.h:150-171, :556-600).  chroma_x only matters for YUV.
 RDP_HD Vec4 fetch_texel(int kind, const TileDesc &tile, const uint8_t *tmem, int s, int t, uint32_t lut_bank,
@@ -865,10 +843,11 @@ RDP_HD int combine_channel(int a, int b, int c, int d)
 	return (((a - b) * c + 0x80) >> 8) + d;
 }
 
-RDP_HD Vec4 run_combiner_equation(const CombinerRegs &in, const PassState &st, const StaticModes &m, int cycle)
+template <class M>
+RDP_HD Vec4 run_combiner_equation(const CombinerRegs &in, const PassState &st, const M &m, int cycle)
 {
-	const int *rs = m.comb_rgb[cycle];
-	const int *as = m.comb_alpha[cycle];
+	const int rs[4] = { m.comb_rgb(cycle, 0), m.comb_rgb(cycle, 1), m.comb_rgb(cycle, 2), m.comb_rgb(cycle, 3) };
+	const int as[4] = { m.comb_alpha(cycle, 0), m.comb_alpha(cycle, 1), m.comb_alpha(cycle, 2), m.comb_alpha(cycle, 3) };
 	int ar, ag, ab, br, bg, bb, cr, cg, cb, dr, dg, db;
 	bool hit;
 
@@ -930,7 +909,8 @@ RDP_HD Vec4 run_combiner_equation(const CombinerRegs &in, const PassState &st, c
 }
 
 // First cycle of 2-cycle mode: result stays unclamped; yields the alpha-test reference.
-RDP_HD Vec4 combiner_first_cycle(const CombinerRegs &in, const PassState &st, const StaticModes &m, int alpha_dith,
+template <class M>
+RDP_HD Vec4 combiner_first_cycle(const CombinerRegs &in, const PassState &st, const M &m, int alpha_dith,
                                  int coverage, uint32_t rf, int &alpha_ref)
 {
 	Vec4 c = run_combiner_equation(in, st, m, 0);
@@ -950,7 +930,8 @@ RDP_HD Vec4 combiner_first_cycle(const CombinerRegs &in, const PassState &st, co
 }
 
 // Last (or only) cycle: clamps, and may fold coverage into alpha.
-RDP_HD Vec4 combiner_last_cycle(const CombinerRegs &in, const PassState &st, const StaticModes &m, int alpha_dith,
+template <class M>
+RDP_HD Vec4 combiner_last_cycle(const CombinerRegs &in, const PassState &st, const M &m, int alpha_dith,
                                 int &coverage, uint32_t rf)
 {
 	Vec4 c = run_combiner_equation(in, st, m, 1);
@@ -1013,18 +994,13 @@ RDP_HD void dither_coefficients(int x, int y, int mode_rgb, int mode_alpha, uint
 // ---------------------------------------------------------------------------------------------
 // shade_pixel: shading.h:38-359
 // ---------------------------------------------------------------------------------------------
-RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_index, Shaded &out)
+// The caller has already resolved the primitive, its span for line y (valid) and its state; fill-mode states never
+// get here (process_pixel_primitive handles them).  `m` holds the state's static modes, literal under a Spec.
+template <class S>
+RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_index, const PrimSetup &p, const Span &sp,
+                        const PassState &st, const StaticModes<S> &m, Shaded &out)
 {
-	const PrimSetup &p = ctx.prims[prim_index];
-	if (y < p.line_lo || y > p.line_hi)
-		return false;
-
-	const Span &sp = ctx.spans[p.span_base + uint32_t(y - p.line_lo)];
-	if (!sp.valid)
-		return false;
-
-	const PassState &st = ctx.states[p.state_id];
-	const uint32_t rf = st.raster_flags;
+	const uint32_t rf = m.rf;
 	const uint8_t *tmem = ctx.tmem + size_t(p.tmem_instance) * kTmemBytes;
 	const bool flip = (p.flags & SF_FLIP) != 0;
 	const bool perspective = (rf & RF_PERSPECTIVE) != 0;
@@ -1065,11 +1041,6 @@ RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 		if ((rf & RF_ALPHA_TEST) && fb_bytes == 2 && (texel & 1) == 0)
 			return false;
 		return true;
-	}
-	else if (rf & RF_FILL)
-	{
-		out.kind = 1;
-		return x >= sp.start_x && x <= sp.end_x;
 	}
 
 	int coverage = compute_coverage(sp, x);
@@ -1128,7 +1099,7 @@ RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 	bool uses_texel1 = (rf & RF_USES_TEXEL1) != 0;
 
 	if (rf & RF_USES_TEXEL0)
-		regs.texel0 = sample_texture(st.tiles[tile0], tmem, s, t, rf, bilerp0, false, st.convert, splat4(0));
+		regs.texel0 = sample_texture<S::tk_mask>(st.tiles[tile0], tmem, s, t, rf, bilerp0, false, st.convert, splat4(0));
 
 	if (rf & RF_USES_PIPELINED_TEXEL1)
 	{
@@ -1156,17 +1127,17 @@ RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 		if (convert_one && !bilerp1)
 			regs.texel1 = texture_convert(regs.texel0, st.convert);
 		else
-			regs.texel1 = sample_texture(st.tiles[tile1], tmem, s, t, rf, bilerp1, convert_one, st.convert, regs.texel0);
+			regs.texel1 = sample_texture<S::tk_mask>(st.tiles[tile1], tmem, s, t, rf, bilerp1, convert_one, st.convert, regs.texel0);
 	}
 
 	int rgb_dith, alpha_dith;
-	dither_coefficients(x, (rf & RF_INTERLACE) ? (y >> 1) : y, st.dither_rgb, st.dither_alpha, noise, rgb_dith, alpha_dith);
+	dither_coefficients(x, (rf & RF_INTERLACE) ? (y >> 1) : y, m.dither_rgb(), m.dither_alpha(), noise, rgb_dith, alpha_dith);
 
 	Vec4 combined;
 	int alpha_ref;
 	if (rf & RF_TWO_CYCLE)
 	{
-		regs.combined = combiner_first_cycle(regs, st, alpha_dith, coverage_count, rf, alpha_ref);
+		regs.combined = combiner_first_cycle(regs, st, m, alpha_dith, coverage_count, rf, alpha_ref);
 		// Pipelining: TEXEL1 is seen as TEXEL0 by the second cycle and vice versa.
 		const Vec4 tmp = regs.texel0;
 		regs.texel0 = regs.texel1;
@@ -1178,11 +1149,11 @@ RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 			// NB: the reseed also changes the noise seen by the alpha-test dither below (noise.h keeps one seed).
 			noise = n2;
 		}
-		combined = combiner_last_cycle(regs, st, alpha_dith, coverage_count, rf);
+		combined = combiner_last_cycle(regs, st, m, alpha_dith, coverage_count, rf);
 	}
 	else
 	{
-		combined = combiner_last_cycle(regs, st, alpha_dith, coverage_count, rf);
+		combined = combiner_last_cycle(regs, st, m, alpha_dith, coverage_count, rf);
 		alpha_ref = combined.w;
 	}
 

@@ -35,6 +35,29 @@ enum TexelKind
 	TK_COUNT
 };
 
+// (tile format, tile size, TLUT enable) -> texel kind; texture.h:498-600 only distinguishes these cases.
+RDP_HD int resolve_texel_kind(int fmt, int size, bool tlut)
+{
+	if (tlut)
+	{
+		// texture.h:548-600: the TLUT path only distinguishes texel size.
+		return size == 0 ? TK_CI4_TLUT : (size == 1 ? TK_CI8_TLUT : TK_CI16_TLUT);
+	}
+	switch (fmt)
+	{
+	case 0: // RGBA
+		return size == 0 ? TK_I4 : (size == 1 ? TK_I8 : (size == 2 ? TK_RGBA16 : TK_RGBA32));
+	case 1: // YUV
+		return TK_YUV16;
+	case 2: // CI
+		return size == 0 ? TK_CI4 : (size == 1 ? TK_I8 : TK_RAW16);
+	case 3: // IA
+		return size == 0 ? TK_IA4 : (size == 1 ? TK_IA8 : (size == 2 ? TK_IA16 : TK_RAW16));
+	default: // I (and the undefined formats 5..7 behave like I in the reference's switch fall-through: none sampled)
+		return size == 0 ? TK_I4 : (size == 1 ? TK_I8 : TK_RAW16);
+	}
+}
+
 // Static mode words of a state, packed (host: Renderer::finalize_state; device: Spec template arguments).
 //   comb_rgb  : selector [cycle][i] at bits (cycle*4+i)*5, 5 bits each
 //   comb_alpha: selector [cycle][i] at bits (cycle*4+i)*3, 3 bits each
@@ -83,45 +106,38 @@ struct Spec
 // Fully dynamic: the uber-kernel fallback (ref shaders/ubershader.comp).
 using SpecGeneric = Spec<~0u, 0u, ~0u, 0u, 0x1fu, ~0u>;
 
-// Per-state modes as the per-pixel code consumes them: plain ints that are literals under an exact Spec.
+// Per-state modes as the per-pixel code consumes them.  Under an exact Spec every accessor is a literal; otherwise
+// it reads the state snapshot on demand (nothing is materialised up front, which keeps the generic kernel's
+// register count where it was).
+template <class S>
 struct StaticModes
 {
+	const PassState *st;
 	uint32_t rf, bf;
-	int comb_rgb[2][4], comb_alpha[2][4], blend[2][4];
-	int dither_rgb, dither_alpha, cvg_mode, z_mode;
+	RDP_HD int comb_rgb(int cycle, int i) const
+	{
+		return S::exact ? int((S::comb_rgb >> ((cycle * 4 + i) * 5)) & 31u) : int(st->comb_rgb[cycle][i]);
+	}
+	RDP_HD int comb_alpha(int cycle, int i) const
+	{
+		return S::exact ? int((S::comb_alpha >> ((cycle * 4 + i) * 3)) & 7u) : int(st->comb_alpha[cycle][i]);
+	}
+	RDP_HD int blend(int cycle, int i) const
+	{
+		return S::exact ? int((S::blend_misc >> ((cycle * 4 + i) * 2)) & 3u) : int(st->blend_modes[cycle][i]);
+	}
+	RDP_HD int dither_rgb() const { return S::exact ? int((S::blend_misc >> 16) & 3u) : int(st->dither_rgb); }
+	RDP_HD int dither_alpha() const { return S::exact ? int((S::blend_misc >> 18) & 3u) : int(st->dither_alpha); }
+	RDP_HD int cvg_mode() const { return S::exact ? int((S::blend_misc >> 20) & 3u) : int(st->cvg_mode); }
+	RDP_HD int z_mode() const { return S::exact ? int((S::blend_misc >> 22) & 3u) : int(st->z_mode); }
 };
 
 template <class S>
-RDP_HD void resolve_modes(const PassState &st, StaticModes &m)
+RDP_HD void resolve_modes(const PassState &st, StaticModes<S> &m)
 {
+	m.st = &st;
 	m.rf = (st.raster_flags & S::rf_may) | S::rf_must;
 	m.bf = (st.blend_flags & S::bf_may) | S::bf_must;
-	if (S::exact)
-	{
-		for (int i = 0; i < 8; i++)
-		{
-			m.comb_rgb[i >> 2][i & 3] = int((S::comb_rgb >> (i * 5)) & 31u);
-			m.comb_alpha[i >> 2][i & 3] = int((S::comb_alpha >> (i * 3)) & 7u);
-			m.blend[i >> 2][i & 3] = int((S::blend_misc >> (i * 2)) & 3u);
-		}
-		m.dither_rgb = int((S::blend_misc >> 16) & 3u);
-		m.dither_alpha = int((S::blend_misc >> 18) & 3u);
-		m.cvg_mode = int((S::blend_misc >> 20) & 3u);
-		m.z_mode = int((S::blend_misc >> 22) & 3u);
-	}
-	else
-	{
-		for (int i = 0; i < 8; i++)
-		{
-			m.comb_rgb[i >> 2][i & 3] = st.comb_rgb[i >> 2][i & 3];
-			m.comb_alpha[i >> 2][i & 3] = st.comb_alpha[i >> 2][i & 3];
-			m.blend[i >> 2][i & 3] = st.blend_modes[i >> 2][i & 3];
-		}
-		m.dither_rgb = st.dither_rgb;
-		m.dither_alpha = st.dither_alpha;
-		m.cvg_mode = st.cvg_mode;
-		m.z_mode = st.z_mode;
-	}
 }
 
 constexpr uint32_t ct_log2(uint32_t v) { return v <= 1u ? 0u : 1u + ct_log2(v >> 1); }

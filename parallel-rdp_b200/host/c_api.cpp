@@ -122,5 +122,6 @@ uint64_t rdp_b200_launch_count(rdp_b200_processor *p) { return p->impl.get_backe
 uint64_t rdp_b200_primitive_count(rdp_b200_processor *p) { return p->impl.get_primitive_counter(); }
 uint64_t rdp_b200_pass_count(rdp_b200_processor *p) { return p->impl.get_pass_counter(); }
 void *rdp_b200_backend_device(rdp_b200_processor *p) { return p->impl.get_backend_device(); }
+const char *rdp_b200_last_tile_variant(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_last_tile_variant(p->impl.get_backend_device()) : ""; }
 void *rdp_b200_cuda_stream(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_stream(p->impl.get_backend_device()) : nullptr; }
 }

@@ -185,7 +185,16 @@ void Renderer::ensure_pass()
 	pass_open = true;
 	num_words = num_prims = num_states = num_uploads = num_spans = num_jobs = 0;
 	pass_reads_tmem = false;
+	reset_summary();
 	state_dirty = true;
+}
+
+void Renderer::reset_summary()
+{
+	summary = {};
+	summary.rf_and = ~0u;
+	summary.bf_and = ~0u;
+	summary.modes_uniform = 1;
 }
 
 void Renderer::snapshot_state()
@@ -194,6 +203,30 @@ void Renderer::snapshot_state()
 	dst = regs;
 	finalize_state(dst);
 	state_dirty = false;
+
+	// Fill-mode states are handled by every tile-kernel instantiation; only the others constrain the choice.
+	if (dst.raster_flags & RF_FILL)
+		return;
+	const uint64_t comb_rgb = pack_comb_rgb(dst.comb_rgb);
+	const uint32_t comb_alpha = pack_comb_alpha(dst.comb_alpha);
+	const uint32_t blend_misc = pack_blend_misc(dst.blend_modes, dst.dither_rgb, dst.dither_alpha, dst.cvg_mode, dst.z_mode);
+	if (summary.num_shaded_states == 0)
+	{
+		summary.comb_rgb = comb_rgb;
+		summary.comb_alpha = comb_alpha;
+		summary.blend_misc = blend_misc;
+	}
+	else if (summary.comb_rgb != comb_rgb || summary.comb_alpha != comb_alpha || summary.blend_misc != blend_misc)
+		summary.modes_uniform = 0;
+	summary.num_shaded_states++;
+	summary.rf_or |= dst.raster_flags;
+	summary.rf_and &= dst.raster_flags;
+	summary.bf_or |= dst.blend_flags;
+	summary.bf_and &= dst.blend_flags;
+
+	const bool tlut = (dst.raster_flags & RF_TLUT) != 0;
+	for (int i = 0; i < 8; i++)
+		state_tile_kind_bits[i] = 1u << resolve_texel_kind(dst.tiles[i].fmt, dst.tiles[i].size, tlut);
 }
 
 void Renderer::validate_draw_state() const
@@ -272,7 +305,28 @@ void Renderer::draw_primitive(const uint32_t *words, unsigned count)
 	}
 
 	if (!(st.raster_flags & RF_FILL))
+	{
 		pass_reads_tmem = true;
+		// Texel kinds this primitive can sample: its own tile (+1 for the second texel), or any tile under LOD.
+		const uint32_t rf = st.raster_flags;
+		if (rf & (RF_USES_TEXEL0 | RF_USES_TEXEL1 | RF_USES_PIPELINED_TEXEL1))
+		{
+			if (rf & RF_TEX_LOD)
+			{
+				for (int i = 0; i < 8; i++)
+					summary.texel_kinds |= state_tile_kind_bits[i];
+			}
+			else
+			{
+				const uint32_t op = (words[0] >> 24) & 63u;
+				const uint32_t t = (op == OP_TEX_RECT || op == OP_TEX_RECT_FLIP) ? ((words[1] >> 24) & 7u) : ((words[0] >> 16) & 7u);
+				if (rf & (RF_USES_TEXEL0 | RF_USES_PIPELINED_TEXEL1))
+					summary.texel_kinds |= state_tile_kind_bits[t];
+				if (rf & RF_USES_TEXEL1)
+					summary.texel_kinds |= state_tile_kind_bits[(t + 1) & 7u];
+			}
+		}
+	}
 	fb.color_write_pending = true;
 	if (st.blend_flags & BF_Z_UPDATE)
 		fb.depth_write_pending = true;
@@ -343,7 +397,7 @@ void Renderer::flush_queues()
 
 		info.num_jobs = num_jobs;
 		rdpb_launch_span_bin(device, &info);
-		rdpb_launch_tiles(device, &info);
+		rdpb_launch_tiles(device, &info, &summary);
 
 		const uint32_t pixels = info.width * info.height;
 		const uint32_t bpp = fb.fmt == FBFormat::RGBA8888 ? 4 : ((fb.fmt == FBFormat::RGBA5551 || fb.fmt == FBFormat::IA88) ? 2 : 1);

@@ -7,6 +7,7 @@
 #pragma once
 #include "rdp_b200_backend.h"
 #include "rdp_types.h"
+#include "rdp_spec.h"
 #include <stddef.h>
 #include <stdint.h>
 
@@ -123,6 +124,10 @@ private:
 	bool pass_open = false;
 	uint32_t num_words = 0, num_prims = 0, num_states = 0, num_uploads = 0, num_spans = 0, num_jobs = 0;
 	bool pass_reads_tmem = false;
+	// What the pass's non-fill states have in common; lets the backend pick a specialised tile kernel.
+	rdpb::PassSummary summary = {};
+	uint32_t state_tile_kind_bits[8] = {}; // texel kind bit of each tile descriptor under the current snapshot
+	void reset_summary();
 	uint32_t base_primitive_index = 0;
 	uint64_t pass_counter = 0;
 	bool tmem_snapshot_valid = false;

@@ -169,9 +169,19 @@ int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 	return 0;
 }
 
-int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info)
+const char *rdpb_last_tile_variant(rdpb_device *) { return "generic"; }
+
+int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary)
 {
 	const FbInfo fb = *static_cast<const FbInfo *>(fb_info);
+	if (summary && getenv("RDP_B200_DEBUG_PASSES"))
+	{
+		const PassSummary *sum = static_cast<const PassSummary *>(summary);
+		fprintf(stderr, "[hostsim] pass: prims=%u fmt=%u states=%u rf_or=%08x rf_and=%08x bf_or=%02x bf_and=%02x tk=%04x uniform=%u "
+		                "comb_rgb=%010llx comb_alpha=%06x blend_misc=%06x\n",
+		        fb.num_prims, fb.fmt, sum->num_shaded_states, sum->rf_or, sum->rf_and, sum->bf_or, sum->bf_and, sum->texel_kinds,
+		        sum->modes_uniform, (unsigned long long)sum->comb_rgb, sum->comb_alpha, sum->blend_misc);
+	}
 	PassBuffers b = dev->buffers();
 	for (uint32_t ty = 0; ty < fb.tiles_y; ty++)
 	{
@@ -192,8 +202,8 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info)
 						continue;
 					FbView view;
 					PixelState px;
-					pass_pixel_begin(b, fb, view, px, x, y);
-					dev->counters[1] += pass_pixel_walk(b, fb, view, px, x, y, tile);
+					pass_pixel_begin<SpecGeneric>(b, fb, view, px, x, y);
+					dev->counters[1] += pass_pixel_walk<SpecGeneric>(b, fb, view, px, x, y, tile);
 					pass_pixel_end(fb, view, px, x, y);
 				}
 			}
