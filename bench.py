@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -243,8 +243,16 @@ def run_ours(args):
     lib.rdpb_counters_read(dev, counters, 1)
     launches0 = proc.launch_count()
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
+    # nvidia-smi needs a moment before its first sample: keep the same replay load running until it reports, so the
+    # clock record brackets the timed region instead of starting after it.
+    t_wait = time.perf_counter()
+    while not sampler.lines and time.perf_counter() - t_wait < 3.0:
+        replay_steps(0, 8)
+        lib.rdpb_sync(dev)
+    lib.rdpb_counters_read(dev, counters, 1)
+    launches0 = proc.launch_count()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     replay_steps(0, args.steps)
@@ -252,7 +260,6 @@ def run_ours(args):
     e1.synchronize()
     barrier()
     value_ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
     launches = proc.launch_count() - launches0
     lib.rdpb_counters_read(dev, counters, 1)
     tiles_processed, shaded_pairs = int(counters[0]), int(counters[1])
@@ -298,6 +305,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     barrier()
+    clocks = sampler.stop()  # sampled from before the device-timed region to the end of the e2e region
 
     result = None
     if rank == 0:

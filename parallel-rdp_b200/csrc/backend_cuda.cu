@@ -21,6 +21,7 @@
 #include "rdp_vi.cuh"
 
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <deque>
 #include <mutex>
 #include <stdio.h>
@@ -53,6 +54,9 @@ constexpr uint32_t kTmemBlocks = kTmemBytes / 2 / kFrontThreads;
 __global__ void __launch_bounds__(kFrontThreads) k_front(PassBuffers b, uint32_t tmem_blocks, uint32_t num_uploads,
                                                          uint32_t rdram_size, uint32_t num_prims)
 {
+	// Stream order puts this launch after the previous pass's tile kernel: reset its tile counter here.
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		b.job_counter[1] = 0;
 	if (blockIdx.x < tmem_blocks)
 	{
 		pass_tmem_word(b, num_uploads, rdram_size, int(blockIdx.x * kFrontThreads + threadIdx.x));
@@ -127,48 +131,215 @@ __global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
 	}
 }
 
-// One warp per 8x4 tile, one thread per pixel; warps never synchronise with each other.  A block is four
-// horizontally adjacent tiles (they mostly see the same primitives, which keeps L1 warm).
+// One warp per 8x4 tile, one thread per pixel; warps never synchronise with each other and pull tiles from a
+// global counter until none are left (persistent warps: the grid is sized to the machine, not to the frame, so
+// heavy tiles do not leave a ragged tail).
+//
+// Per tile:
+//   gather      lanes read the tile's fine-mask words 32 at a time (coalesced), zero them for the next pass, and
+//               scatter the set bits into a per-warp list of primitive indices in shared memory (ballot-free
+//               prefix sum over popcounts keeps submission order).
+//   mask phase  lane j looks at list entry j: header (one 16-byte load), the four span headers of the tile's rows
+//               (8 bytes each) -> a 32-bit pixel mask of where the primitive can touch this tile, plus L1
+//               prefetches of everything the shade phase will read.  32 primitives' dependent loads overlap.
+//   shade phase walks the live primitives in order; header fields arrive by shuffle, so the only loads left on
+//               the critical path hit lines the mask phase already requested.
 constexpr uint32_t kTileWarpsPerBlock = 4;
+constexpr uint32_t kTileListCapacity = 128;
+
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 
 template <class S>
-__global__ void __launch_bounds__(kTileWarpsPerBlock * 32) k_tiles(PassBuffers b, FbInfo fb)
+struct TileWalker
 {
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t tile = blockIdx.x * kTileWarpsPerBlock + (threadIdx.x >> 5);
-	if (blockIdx.x == 0 && threadIdx.x == 0)
-		*b.job_counter = 0; // the span jobs of this pass are consumed; the next pass allocates from zero
-	if (tile >= fb.tiles_x * fb.tiles_y)
-		return;
+	const PassBuffers &b;
+	const FbInfo &fb;
+	const ShadeContext &ctx;
+	const FbView &view;
+	PixelState &px;
+	uint32_t lane;
+	int x0, y0, x, y;
+	uint32_t inside_mask;
+	uint32_t shaded;
 
-	const uint32_t *coarse = b.coarse_mask + size_t(tile) * fb.coarse_stride;
-	uint32_t any = 0;
-	for (uint32_t cw = 0; cw < fb.coarse_stride; cw++)
-		any |= coarse[cw];
-	if (!any)
-		return;
-
-	const uint32_t tx = tile % fb.tiles_x, ty = tile / fb.tiles_x;
-	const int x = int(tx * kTileW + (lane & 7u));
-	const int y = int(ty * kTileH + (lane >> 3));
-	uint32_t shaded = 0;
-	if (x < int(fb.width) && y < int(fb.height))
+	// Mask + shade phases over list[0..n).
+	__device__ __forceinline__ void run(const uint16_t *list, uint32_t n)
 	{
+		for (uint32_t c = 0; c < n; c += 32u)
+		{
+			// ---- mask phase: lane j <-> list[c + j] ----
+			uint4 hdr = make_uint4(0u, 0u, 0u, 0u);
+			uint32_t pixmask = 0, my_prim = 0;
+			if (c + lane < n)
+			{
+				my_prim = list[c + lane];
+				const PrimSetup *pp = b.prims + my_prim;
+				hdr = *reinterpret_cast<const uint4 *>(&pp->span_base);
+				const int line_lo = int(int16_t(hdr.z & 0xffffu)), line_hi = int(int16_t(hdr.z >> 16));
+#pragma unroll
+				for (int r = 0; r < int(kTileH); r++)
+				{
+					const int yy = y0 + r;
+					if (yy < line_lo || yy > line_hi)
+						continue;
+					const Span *sp = b.spans + (hdr.x + uint32_t(yy - line_lo));
+					const uint2 sh = *reinterpret_cast<const uint2 *>(&sp->start_x);
+					if ((sh.y >> 16) == 0u) // !valid
+						continue;
+					const int lo = max(int(int16_t(sh.x & 0xffffu)) - x0, 0);
+					const int hi = min(int(int16_t(sh.x >> 16)) - x0, int(kTileW) - 1);
+					if (lo > hi)
+						continue;
+					pixmask |= (((2u << hi) - 1u) & ~((1u << lo) - 1u)) << (r * int(kTileW));
+					prefetch_l1(sp);
+				}
+				pixmask &= inside_mask;
+				if (pixmask)
+				{
+					prefetch_l1(pp);
+					prefetch_l1(reinterpret_cast<const uint8_t *>(pp) + 128);
+				}
+			}
+
+			// ---- shade phase: live primitives in order ----
+			uint32_t live = __ballot_sync(0xffffffffu, pixmask != 0u);
+			while (live)
+			{
+				const int j = __ffs(int(live)) - 1;
+				live &= live - 1u;
+				const uint32_t pm = __shfl_sync(0xffffffffu, pixmask, j);
+				const uint32_t prim = __shfl_sync(0xffffffffu, my_prim, j);
+				const uint32_t span_base = __shfl_sync(0xffffffffu, hdr.x, j);
+				const uint32_t ids = __shfl_sync(0xffffffffu, hdr.y, j);
+				const uint32_t lines = __shfl_sync(0xffffffffu, hdr.z, j);
+				if ((pm >> lane) & 1u)
+				{
+					const int line_lo = int(int16_t(lines & 0xffffu));
+					const PrimSetup &p = b.prims[prim];
+					const Span &sp = b.spans[span_base + uint32_t(y - line_lo)];
+					const PassState &st = b.states[ids & 0xffffu];
+					if (process_pixel_span<S>(ctx, view, px, x, y, prim, p, sp, st))
+						shaded++;
+				}
+			}
+		}
+	}
+};
+
+template <class S>
+__global__ void __launch_bounds__(kTileWarpsPerBlock * 32, S::min_blocks_per_sm) k_tiles(PassBuffers b, FbInfo fb)
+{
+	__shared__ uint16_t s_list[kTileWarpsPerBlock][kTileListCapacity];
+	uint16_t *list = s_list[threadIdx.x >> 5];
+
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t num_tiles = fb.tiles_x * fb.tiles_y;
+
+	ShadeContext ctx;
+	ctx.prims = b.prims;
+	ctx.states = b.states;
+	ctx.spans = b.spans;
+	ctx.tmem = b.tmem_instances;
+	ctx.fb_fmt = resolve_fb_fmt<S>(fb.fmt);
+	ctx.base_prim_index = fb.base_prim_index;
+
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		b.job_counter[0] = 0; // this pass's span jobs are consumed; the next pass allocates from zero
+
+	uint32_t tiles_done = 0, shaded_total = 0;
+	for (;;)
+	{
+		uint32_t tile = 0;
+		if (lane == 0)
+			tile = atomicAdd(&b.job_counter[1], 1u);
+		tile = __shfl_sync(0xffffffffu, tile, 0);
+		if (tile >= num_tiles)
+			break;
+
+		uint32_t *coarse = b.coarse_mask + size_t(tile) * fb.coarse_stride;
+		uint32_t *fine = b.fine_mask + size_t(tile) * fb.mask_stride;
+		uint32_t any = 0;
+		for (uint32_t cw = 0; cw < fb.coarse_stride; cw++)
+			any |= coarse[cw];
+		if (!any)
+			continue;
+		tiles_done++;
+
+		const uint32_t tx = tile % fb.tiles_x, ty = tile / fb.tiles_x;
 		FbView view;
 		PixelState px;
-		pass_pixel_begin<S>(b, fb, view, px, x, y);
-		shaded = pass_pixel_walk<S>(b, fb, view, px, x, y, tile);
-		pass_pixel_end(fb, view, px, x, y);
+		TileWalker<S> walk = { b, fb, ctx, view, px, lane, int(tx * kTileW), int(ty * kTileH), 0, 0, 0u, 0u };
+		walk.x = walk.x0 + int(lane & 7u);
+		walk.y = walk.y0 + int(lane >> 3);
+		walk.inside_mask = __ballot_sync(0xffffffffu, walk.x < int(fb.width) && walk.y < int(fb.height));
+		pass_pixel_begin<S>(b, fb, view, px, walk.x, walk.y);
+
+		// Gather / process until the tile's masks are exhausted.  `w` holds this lane's not-yet-listed bits of the
+		// current round (coarse word cw summarises fine words cw*32 .. cw*32+31: one lane-parallel round).
+		uint32_t cw = 0, w = 0, idx = 0;
+		for (;;)
+		{
+			uint32_t count = 0;
+			while (count < kTileListCapacity)
+			{
+				if (__ballot_sync(0xffffffffu, w != 0u) == 0u)
+				{
+					while (cw < fb.coarse_stride && coarse[cw] == 0u)
+						cw++;
+					if (cw >= fb.coarse_stride)
+						break;
+					idx = cw * 32u + lane;
+					w = idx < fb.mask_stride ? fine[idx] : 0u;
+					if (w)
+						fine[idx] = 0u; // consumed: the next pass starts from clean masks
+					__syncwarp();
+					if (lane == 0)
+						coarse[cw] = 0u;
+					cw++;
+				}
+				const uint32_t n = uint32_t(__popc(w));
+				uint32_t incl = n;
+#pragma unroll
+				for (int off = 1; off < 32; off <<= 1)
+				{
+					const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+					if (lane >= uint32_t(off))
+						incl += v;
+				}
+				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+				const uint32_t space = kTileListCapacity - count;
+				// Bits are listed in submission order; whatever does not fit stays in `w` for the next list.
+				uint32_t at = incl - n;
+				while (w && at < space)
+				{
+					list[count + at] = uint16_t(idx * 32u + uint32_t(__ffs(int(w)) - 1));
+					w &= w - 1u;
+					at++;
+				}
+				count += min(total, space);
+			}
+			if (count == 0u)
+				break;
+			__syncwarp();
+			walk.run(list, count);
+			__syncwarp();
+		}
+		shaded_total += walk.shaded;
+
+		pass_pixel_end(fb, view, px, walk.x, walk.y);
 	}
-	// One atomic per warp keeps the "shaded pixels" metric essentially free.
-	const uint32_t warp_total = __reduce_add_sync(0xffffffffu, shaded);
-	__syncwarp();
+
+	// One atomic per warp keeps the metrics essentially free.
+	const uint32_t warp_total = __reduce_add_sync(0xffffffffu, shaded_total);
 	if (lane == 0)
 	{
-		pass_tile_clear_masks(b, fb, tile);
 		if (warp_total)
 			atomicAdd(&b.counters[1], (unsigned long long)warp_total);
-		atomicAdd(&b.counters[0], 1ull);
+		if (tiles_done)
+			atomicAdd(&b.counters[0], (unsigned long long)tiles_done);
 	}
 }
 
@@ -211,6 +382,8 @@ static TileVariant make_variant(const char *name)
 }
 
 #include "rdp_variants.inc"
+
+static_assert(sizeof(kTileVariants) / sizeof(kTileVariants[0]) <= 32, "grow rdpb_device::variant_blocks_per_sm");
 
 static const TileVariant *pick_tile_variant(const PassSummary *sum, uint32_t fmt)
 {
@@ -321,6 +494,9 @@ struct rdpb_device
 
 	uint64_t launches = 0;
 	const TileVariant *last_variant = nullptr;
+	uint32_t num_sms = 148;
+	uint32_t variant_blocks_per_sm[32] = {}; // resident blocks per SM of each tile-kernel instantiation (lazy)
+	uint32_t tile_blocks_per_sm_override = 0;
 	bool debug_summary = false;
 	std::string error;
 
@@ -410,7 +586,18 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	{
 		const int s = prof_begin(dev, RDPB_KERNEL_TILES);
 		const uint32_t tiles = op.fb.tiles_x * op.fb.tiles_y;
-		op.variant->kernel<<<(tiles + kTileWarpsPerBlock - 1) / kTileWarpsPerBlock, kTileWarpsPerBlock * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
+		// Persistent grid: exactly as many blocks as can be resident (occupancy of this instantiation x SMs).
+		const size_t vi = size_t(op.variant - kTileVariants);
+		if (!dev->variant_blocks_per_sm[vi])
+		{
+			int n = 0;
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, op.variant->kernel, int(kTileWarpsPerBlock * 32), 0) != cudaSuccess || n <= 0)
+				n = 4;
+			dev->variant_blocks_per_sm[vi] = uint32_t(n);
+		}
+		const uint32_t per_sm = dev->tile_blocks_per_sm_override ? dev->tile_blocks_per_sm_override : dev->variant_blocks_per_sm[vi];
+		const uint32_t blocks = std::min((tiles + kTileWarpsPerBlock - 1) / kTileWarpsPerBlock, dev->num_sms * per_sm);
+		op.variant->kernel<<<blocks, kTileWarpsPerBlock * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
 		prof_end(dev, s);
 		dev->launches++;
 		break;
@@ -502,6 +689,13 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	auto need = [&](cudaError_t e, const char *what) { ok = ok && check(dev, e, what); };
 
 	need(cudaSetDevice(cuda_ordinal), "cudaSetDevice");
+	{
+		int sms = 0;
+		if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cuda_ordinal) == cudaSuccess && sms > 0)
+			dev->num_sms = uint32_t(sms);
+		if (const char *env = getenv("RDP_B200_TILE_BLOCKS_PER_SM"))
+			dev->tile_blocks_per_sm_override = uint32_t(std::max(1, atoi(env)));
+	}
 	need(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking), "cudaStreamCreate");
 	need(cudaMalloc(&dev->rdram, rdram_size), "cudaMalloc rdram");
 	need(cudaMalloc(&dev->hidden, hidden_size), "cudaMalloc hidden");

@@ -531,17 +531,11 @@ RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup 
 // Walk one pixel through one binned primitive (shade, then fill / copy / depth-blend).
 // Returns true when the pixel was shaded (a "shaded pixel" of the Mpix/s metric: shade_pixel returned true).
 // Fill-mode states are handled here for every specialisation; everything else goes through Spec S.
+// The part after the primitive / span / state look-ups (the CUDA tile kernel resolves those warp-cooperatively).
 template <class S>
-RDP_HD bool process_pixel_primitive(const ShadeContext &ctx, const FbView &fb, PixelState &px, int x, int y, uint32_t prim)
+RDP_HD bool process_pixel_span(const ShadeContext &ctx, const FbView &fb, PixelState &px, int x, int y, uint32_t prim,
+                               const PrimSetup &p, const Span &sp, const PassState &st)
 {
-	const PrimSetup &p = ctx.prims[prim];
-	if (y < p.line_lo || y > p.line_hi)
-		return false;
-	const Span &sp = ctx.spans[p.span_base + uint32_t(y - p.line_lo)];
-	if (!sp.valid)
-		return false;
-	const PassState &st = ctx.states[p.state_id];
-
 	if (st.raster_flags & RF_FILL)
 	{
 		if (x < sp.start_x || x > sp.end_x)
@@ -560,6 +554,18 @@ RDP_HD bool process_pixel_primitive(const ShadeContext &ctx, const FbView &fb, P
 	else
 		depth_blend_pixel(fb, px, p, st, m, sh);
 	return true;
+}
+
+template <class S>
+RDP_HD bool process_pixel_primitive(const ShadeContext &ctx, const FbView &fb, PixelState &px, int x, int y, uint32_t prim)
+{
+	const PrimSetup &p = ctx.prims[prim];
+	if (y < p.line_lo || y > p.line_hi)
+		return false;
+	const Span &sp = ctx.spans[p.span_base + uint32_t(y - p.line_lo)];
+	if (!sp.valid)
+		return false;
+	return process_pixel_span<S>(ctx, fb, px, x, y, prim, p, sp, ctx.states[p.state_id]);
 }
 
 // Blender divider table (reference data: parallel-rdp/luts.hpp blender_lut, itself generated by the oracle's

@@ -26,7 +26,7 @@ struct PassBuffers
 	uint32_t *fine_mask;   // [tile][mask_stride]
 	uint32_t *coarse_mask; // [tile][coarse_stride]
 	uint32_t *jobs;        // span jobs (span_job_pack), written by the set-up kernel (CUDA backend only)
-	uint32_t *job_counter; // [0] number of jobs allocated so far in this pass
+	uint32_t *job_counter; // [0] span jobs allocated so far in this pass, [1] next tile for the tile kernel's warps
 	uint8_t *tmem;           // live TMEM, 4 KiB
 	uint8_t *tmem_instances; // snapshot k = TMEM after k uploads of this pass
 	uint8_t *rdram;

@@ -115,34 +115,38 @@ RDP_HD int compute_coverage(const Span &s, int x)
 // ---------------------------------------------------------------------------------------------
 // Perspective divide: perspective.h:27-112
 // ---------------------------------------------------------------------------------------------
-#if defined(__CUDA_ARCH__)
-#define RDP_CONST_TABLE __device__ static const
-#else
-#define RDP_CONST_TABLE static const
+// 64 x (reciprocal base, slope) pairs of the RDP's normalised-W reciprocal ROM, packed base | slope << 16.
+// Indexed per lane, so on the device it lives in global memory (L1-resident) rather than in the constant bank
+// (divergent constant reads serialise) or on the stack (rebuilt per call).
+#define RDP_PERSP_ROM_INIT                                                                                              \
+	{                                                                                                                   \
+		RDP_PR(0x4000, -252), RDP_PR(0x3f04, -244), RDP_PR(0x3e10, -238), RDP_PR(0x3d22, -230), RDP_PR(0x3c3c, -223),   \
+		RDP_PR(0x3b5d, -218), RDP_PR(0x3a83, -210), RDP_PR(0x39b1, -205), RDP_PR(0x38e4, -200), RDP_PR(0x381c, -194),   \
+		RDP_PR(0x375a, -189), RDP_PR(0x369d, -184), RDP_PR(0x35e5, -179), RDP_PR(0x3532, -175), RDP_PR(0x3483, -170),   \
+		RDP_PR(0x33d9, -166), RDP_PR(0x3333, -162), RDP_PR(0x3291, -157), RDP_PR(0x31f4, -155), RDP_PR(0x3159, -150),   \
+		RDP_PR(0x30c3, -147), RDP_PR(0x3030, -143), RDP_PR(0x2fa1, -140), RDP_PR(0x2f15, -137), RDP_PR(0x2e8c, -134),   \
+		RDP_PR(0x2e06, -131), RDP_PR(0x2d83, -128), RDP_PR(0x2d03, -125), RDP_PR(0x2c86, -123), RDP_PR(0x2c0b, -120),   \
+		RDP_PR(0x2b93, -117), RDP_PR(0x2b1e, -115), RDP_PR(0x2aab, -113), RDP_PR(0x2a3a, -110), RDP_PR(0x29cc, -108),   \
+		RDP_PR(0x2960, -106), RDP_PR(0x28f6, -104), RDP_PR(0x288e, -102), RDP_PR(0x2828, -100), RDP_PR(0x27c4, -98),    \
+		RDP_PR(0x2762, -96), RDP_PR(0x2702, -94), RDP_PR(0x26a4, -92), RDP_PR(0x2648, -91), RDP_PR(0x25ed, -89),        \
+		RDP_PR(0x2594, -87), RDP_PR(0x253d, -86), RDP_PR(0x24e7, -85), RDP_PR(0x2492, -83), RDP_PR(0x243f, -81),        \
+		RDP_PR(0x23ee, -80), RDP_PR(0x239e, -79), RDP_PR(0x234f, -77), RDP_PR(0x2302, -76), RDP_PR(0x22b6, -74),        \
+		RDP_PR(0x226c, -74), RDP_PR(0x2222, -72), RDP_PR(0x21da, -71), RDP_PR(0x2193, -70), RDP_PR(0x214d, -69),        \
+		RDP_PR(0x2108, -67), RDP_PR(0x20c5, -67), RDP_PR(0x2082, -65), RDP_PR(0x2041, -65),                             \
+	}
+#define RDP_PR(base, slope) (uint32_t(base) | (uint32_t(uint16_t(int16_t((slope) * 4))) << 16))
+#if defined(__CUDACC__)
+static __device__ const uint32_t g_persp_rom_device[64] = RDP_PERSP_ROM_INIT;
 #endif
+static const uint32_t g_persp_rom_host[64] = RDP_PERSP_ROM_INIT;
 
-// 64 x (reciprocal base, slope) pairs of the RDP's normalised-W reciprocal ROM.
-RDP_HD int persp_table_base(int i)
+RDP_HD uint32_t persp_rom(int i)
 {
-	const int16_t t[64] = {
-		0x4000, 0x3f04, 0x3e10, 0x3d22, 0x3c3c, 0x3b5d, 0x3a83, 0x39b1, 0x38e4, 0x381c, 0x375a, 0x369d, 0x35e5,
-		0x3532, 0x3483, 0x33d9, 0x3333, 0x3291, 0x31f4, 0x3159, 0x30c3, 0x3030, 0x2fa1, 0x2f15, 0x2e8c, 0x2e06,
-		0x2d83, 0x2d03, 0x2c86, 0x2c0b, 0x2b93, 0x2b1e, 0x2aab, 0x2a3a, 0x29cc, 0x2960, 0x28f6, 0x288e, 0x2828,
-		0x27c4, 0x2762, 0x2702, 0x26a4, 0x2648, 0x25ed, 0x2594, 0x253d, 0x24e7, 0x2492, 0x243f, 0x23ee, 0x239e,
-		0x234f, 0x2302, 0x22b6, 0x226c, 0x2222, 0x21da, 0x2193, 0x214d, 0x2108, 0x20c5, 0x2082, 0x2041,
-	};
-	return t[i];
-}
-
-RDP_HD int persp_table_slope(int i)
-{
-	const int16_t t[64] = {
-		-252, -244, -238, -230, -223, -218, -210, -205, -200, -194, -189, -184, -179, -175, -170, -166,
-		-162, -157, -155, -150, -147, -143, -140, -137, -134, -131, -128, -125, -123, -120, -117, -115,
-		-113, -110, -108, -106, -104, -102, -100, -98,  -96,  -94,  -92,  -91,  -89,  -87,  -86,  -85,
-		-83,  -81,  -80,  -79,  -77,  -76,  -74,  -74,  -72,  -71,  -70,  -69,  -67,  -67,  -65,  -65,
-	};
-	return t[i] * 4;
+#if defined(__CUDA_ARCH__)
+	return g_persp_rom_device[i];
+#else
+	return g_persp_rom_host[i];
+#endif
 }
 
 RDP_HD void perspective_divide(int s, int t, int w, int &os, int &ot, bool &overflow)
@@ -154,7 +158,8 @@ RDP_HD void perspective_divide(int s, int t, int w, int &os, int &ot, bool &over
 	const int normout = (w << shift) & 0x3fff;
 	const int wnorm = normout & 0xff;
 	const int idx = normout >> 8;
-	const int rcp = ((persp_table_slope(idx) * wnorm) >> 10) + persp_table_base(idx);
+	const uint32_t rom = persp_rom(idx);
+	const int rcp = ((int(int16_t(rom >> 16)) * wnorm) >> 10) + int(rom & 0xffffu);
 
 	int prod[2] = { s * rcp, t * rcp };
 	const int temp_mask = ((1 << 30) - 1) & -((1 << 29) >> shift);
@@ -963,9 +968,11 @@ RDP_HD Vec4 combiner_last_cycle(const CombinerRegs &in, const PassState &st, con
 // ---------------------------------------------------------------------------------------------
 RDP_HD int dither_matrix(int which, int idx)
 {
-	const uint8_t magic[16] = { 0, 6, 1, 7, 4, 2, 5, 3, 3, 5, 2, 4, 7, 1, 6, 0 };
-	const uint8_t bayer[16] = { 0, 4, 1, 5, 4, 0, 5, 1, 3, 7, 2, 6, 7, 3, 6, 2 };
-	return which ? bayer[idx] : magic[idx];
+	// magic = { 0, 6, 1, 7, 4, 2, 5, 3, 3, 5, 2, 4, 7, 1, 6, 0 }, bayer = { 0, 4, 1, 5, 4, 0, 5, 1, 3, 7, 2, 6, 7, 3, 6, 2 },
+	// one nibble per entry so the look-up is a shift instead of a table in local memory.
+	const uint64_t magic = 0x0617425335247160ull;
+	const uint64_t bayer = 0x2637627315045140ull;
+	return int(((which ? bayer : magic) >> (idx * 4)) & 7u);
 }
 
 RDP_HD void dither_coefficients(int x, int y, int mode_rgb, int mode_alpha, uint32_t noise, int &rgb_dither,

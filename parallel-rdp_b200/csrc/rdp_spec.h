@@ -101,6 +101,9 @@ struct Spec
 	static constexpr uint64_t comb_rgb = COMB_RGB;
 	static constexpr uint32_t comb_alpha = COMB_ALPHA;
 	static constexpr uint32_t blend_misc = BLEND_MISC;
+	// Resident 128-thread blocks per SM the tile kernel is compiled for: 8 (<= 64 registers) when the state is exact,
+	// 5 (<= 96 registers) for the feature classes and the uber-kernel.
+	static constexpr int min_blocks_per_sm = EXACT ? 8 : 5;
 };
 
 // Fully dynamic: the uber-kernel fallback (ref shaders/ubershader.comp).

@@ -7,6 +7,7 @@
 // Behavioural reference for the fields: parallel-rdp/rdp_data_structures.hpp:95-254,
 // parallel-rdp/rdp_common.hpp:37-322 (enums), parallel-rdp/rdp_device.cpp:268-860 (decode).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -215,12 +216,14 @@ struct PrimSetup
 	// rgba / stzw attribute planes: value, d/dx, d/de, d/dy
 	int32_t rgba[4], drgba_dx[4], drgba_de[4], drgba_dy[4];
 	int32_t stzw[4], dstzw_dx[4], dstzw_de[4], dstzw_dy[4];
+	// Header: one aligned 16-byte word at byte 160 (read lane-parallel by the tile kernel's mask phase).
 	uint32_t span_base;
 	uint16_t state_id, tmem_instance;
 	int16_t line_lo, line_hi;
 	uint16_t dz;
 	uint8_t dz_compressed, pad;
 };
+static_assert(offsetof(PrimSetup, span_base) == 160, "PrimSetup header must sit at byte 160");
 
 // Per (primitive, scanline) edge-walk result, 64 bytes.
 struct Span
@@ -229,12 +232,14 @@ struct Span
 	int32_t stzw[4];
 	uint16_t xl[4]; // left edge per sub-scanline, x.3 fixed point, scissor-clamped
 	uint16_t xr[4];
-	int32_t base_x; // integer X the attributes were latched at
+	// The next 8 bytes are what binning and the tile kernel's mask phase read: keep them in one aligned 8-byte word.
 	int16_t start_x, end_x;
 	int16_t lodlength;
 	uint16_t valid;
+	int32_t base_x; // integer X the attributes were latched at
 	uint32_t pad;
 };
+static_assert(offsetof(Span, start_x) == 48, "Span header word must sit at byte 48");
 
 // TMEM upload descriptor (LoadTile / LoadBlock / LoadTLUT), decomposed on the host.
 // Semantics: UploadInfo, rdp_data_structures.hpp:182-202.
