@@ -343,12 +343,41 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, S::min_blocks_per_sm)
 	}
 }
 
+// VI filter: a 32x8 block computes the AA / dither-reconstruction result ("fetch") of its pixels plus one halo
+// column on each side into shared memory, then the divot median reads its three inputs from there -- each fetch
+// result (up to nine RDRAM reads) is computed once instead of three times.
 __global__ void __launch_bounds__(256) k_vi_filter(ViFrame f, ViBuffers b)
 {
-	const int x = int(blockIdx.x * blockDim.x + threadIdx.x);
-	const int y = int(blockIdx.y * blockDim.y + threadIdx.y);
+	__shared__ uint32_t s_fetch[8][34];
+	const int tx = int(threadIdx.x), ty = int(threadIdx.y);
+	const int x = int(blockIdx.x) * 32 + tx;
+	const int y = int(blockIdx.y) * 8 + ty;
+	const bool bug = blockIdx.z != 0;
+
+	ViColor c = vi_fetch_pixel(f, b, x, y, bug);
+	if (f.status & VI_STATUS_DIVOT)
+	{
+		// Fetch results fit 8 bits per channel (the dither filter cannot leave [0, 255]), so packing is lossless.
+		s_fetch[ty][tx + 1] = vi_pack(c);
+		const int tid = ty * 32 + tx;
+		if (tid < 16)
+		{
+			const int row = tid >> 1, right = tid & 1;
+			const int hx = int(blockIdx.x) * 32 + (right ? 32 : -1);
+			s_fetch[row][right ? 33 : 0] = vi_pack(vi_fetch_pixel(f, b, hx, int(blockIdx.y) * 8 + row, bug));
+		}
+		__syncthreads();
+		const ViColor l = vi_unpack(s_fetch[ty][tx]);
+		const ViColor r = vi_unpack(s_fetch[ty][tx + 2]);
+		if ((l.a & c.a & r.a) != 7)
+		{
+			c.r = vi_median3(l.r, c.r, r.r);
+			c.g = vi_median3(l.g, c.g, r.g);
+			c.b = vi_median3(l.b, c.b, r.b);
+		}
+	}
 	if (x < f.filt_width && y < f.filt_height)
-		vi_filter_thread(f, b, x, y, int(blockIdx.z));
+		b.filtered[size_t(blockIdx.z) * f.layer_stride + size_t(y) * f.stage_stride + size_t(x)] = vi_pack(c);
 }
 
 __global__ void __launch_bounds__(256) k_vi_scale(ViFrame f, ViBuffers b)
