@@ -152,6 +152,42 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
 	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
+// Vectorised (128-bit, read-only path) loads of what the shade phase reads from a span and a primitive.  The
+// structs are copied field by field so they stay in registers.
+__device__ __forceinline__ void load_span(const Span *g, Span &sp)
+{
+	const uint4 *q = reinterpret_cast<const uint4 *>(g);
+	const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+	sp.rgba[0] = int(a.x); sp.rgba[1] = int(a.y); sp.rgba[2] = int(a.z); sp.rgba[3] = int(a.w);
+	sp.stzw[0] = int(b.x); sp.stzw[1] = int(b.y); sp.stzw[2] = int(b.z); sp.stzw[3] = int(b.w);
+	sp.xl[0] = uint16_t(c.x); sp.xl[1] = uint16_t(c.x >> 16); sp.xl[2] = uint16_t(c.y); sp.xl[3] = uint16_t(c.y >> 16);
+	sp.xr[0] = uint16_t(c.z); sp.xr[1] = uint16_t(c.z >> 16); sp.xr[2] = uint16_t(c.w); sp.xr[3] = uint16_t(c.w >> 16);
+	sp.start_x = int16_t(d.x); sp.end_x = int16_t(d.x >> 16);
+	sp.lodlength = int16_t(d.y); sp.valid = uint16_t(d.y >> 16);
+	sp.base_x = int(d.z);
+}
+
+__device__ __forceinline__ void load_prim_for_shading(const PrimSetup *g, uint32_t span_base, uint32_t ids, uint32_t lines,
+                                                      uint32_t dzw, PrimSetup &p)
+{
+	const uint4 *q = reinterpret_cast<const uint4 *>(g);
+	const uint32_t w28 = __ldg(reinterpret_cast<const uint32_t *>(g) + 7);
+	const uint4 cdx = __ldg(q + 3), cdy = __ldg(q + 5), tdx = __ldg(q + 7), tdy = __ldg(q + 9);
+	p.flags = uint8_t(w28 >> 16);
+	p.tile = uint8_t(w28 >> 24);
+	p.drgba_dx[0] = int(cdx.x); p.drgba_dx[1] = int(cdx.y); p.drgba_dx[2] = int(cdx.z); p.drgba_dx[3] = int(cdx.w);
+	p.drgba_dy[0] = int(cdy.x); p.drgba_dy[1] = int(cdy.y); p.drgba_dy[2] = int(cdy.z); p.drgba_dy[3] = int(cdy.w);
+	p.dstzw_dx[0] = int(tdx.x); p.dstzw_dx[1] = int(tdx.y); p.dstzw_dx[2] = int(tdx.z); p.dstzw_dx[3] = int(tdx.w);
+	p.dstzw_dy[0] = int(tdy.x); p.dstzw_dy[1] = int(tdy.y); p.dstzw_dy[2] = int(tdy.z); p.dstzw_dy[3] = int(tdy.w);
+	p.span_base = span_base;
+	p.state_id = uint16_t(ids);
+	p.tmem_instance = uint16_t(ids >> 16);
+	p.line_lo = int16_t(lines);
+	p.line_hi = int16_t(lines >> 16);
+	p.dz = uint16_t(dzw);
+	p.dz_compressed = uint8_t(dzw >> 16);
+}
+
 template <class S>
 struct TileWalker
 {
@@ -215,11 +251,14 @@ struct TileWalker
 				const uint32_t span_base = __shfl_sync(0xffffffffu, hdr.x, j);
 				const uint32_t ids = __shfl_sync(0xffffffffu, hdr.y, j);
 				const uint32_t lines = __shfl_sync(0xffffffffu, hdr.z, j);
+				const uint32_t dzw = __shfl_sync(0xffffffffu, hdr.w, j);
 				if ((pm >> lane) & 1u)
 				{
 					const int line_lo = int(int16_t(lines & 0xffffu));
-					const PrimSetup &p = b.prims[prim];
-					const Span &sp = b.spans[span_base + uint32_t(y - line_lo)];
+					Span sp;
+					load_span(b.spans + (span_base + uint32_t(y - line_lo)), sp);
+					PrimSetup p;
+					load_prim_for_shading(b.prims + prim, span_base, ids, lines, dzw, p);
 					const PassState &st = b.states[ids & 0xffffu];
 					if (process_pixel_span<S>(ctx, view, px, x, y, prim, p, sp, st))
 						shaded++;

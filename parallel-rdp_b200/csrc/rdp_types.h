@@ -164,7 +164,7 @@ enum TileFlags : uint32_t
 };
 
 // One of the 8 RDP tile descriptors (SetTile + SetTileSize), 32 bytes.
-struct TileDesc
+struct alignas(16) TileDesc
 {
 	uint32_t slo, shi, tlo, thi; // 10.2 fixed point
 	uint32_t offset, stride;     // TMEM bytes
@@ -174,7 +174,7 @@ struct TileDesc
 
 // Everything non-geometric a primitive depends on, snapshotted by the host whenever any state
 // command arrived since the previous primitive.  Primitives name a snapshot by index.
-struct PassState
+struct alignas(16) PassState
 {
 	uint32_t raster_flags;
 	uint32_t blend_flags;
@@ -207,7 +207,7 @@ struct PrimRecord
 };
 
 // Decoded primitive, produced on the device by the set-up kernel.
-struct PrimSetup
+struct alignas(16) PrimSetup
 {
 	int32_t xh, xm, xl;
 	int32_t dxhdy, dxmdy, dxldy;
@@ -226,7 +226,7 @@ struct PrimSetup
 static_assert(offsetof(PrimSetup, span_base) == 160, "PrimSetup header must sit at byte 160");
 
 // Per (primitive, scanline) edge-walk result, 64 bytes.
-struct Span
+struct alignas(16) Span
 {
 	int32_t rgba[4];
 	int32_t stzw[4];
