@@ -70,6 +70,10 @@ void rdp_b200_enqueue_command(rdp_b200_processor *p, unsigned num_words, const u
 void rdp_b200_enqueue_command_direct(rdp_b200_processor *p, unsigned num_words, const uint32_t *words);
 /* Extension: many back-to-back commands in one call (dump replay / bulk feed). */
 void rdp_b200_enqueue_command_stream(rdp_b200_processor *p, size_t num_words, const uint32_t *words);
+/* Extension: zero-copy variant.  `words` is borrowed: it must stay valid and unmodified until a later idle(),
+ * wait_for_timeline() or scan-out fence covering these commands has returned.  Pinned memory makes the GPU upload
+ * asynchronous. */
+void rdp_b200_enqueue_command_stream_borrowed(rdp_b200_processor *p, size_t num_words, const uint32_t *words);
 
 /* flush / signal_timeline / wait_for_timeline / idle / begin_frame_context, rdp_device.cpp:169-174,1038-1080 */
 void rdp_b200_flush(rdp_b200_processor *p);
@@ -103,6 +107,11 @@ const void *rdp_b200_scanout(rdp_b200_processor *p, const rdp_b200_scanout_optio
 /* scanout_sync, rdp_device.cpp:1160-1182: copies up to `capacity_pixels` RGBA8 pixels into `rgba`. */
 void rdp_b200_scanout_sync(rdp_b200_processor *p, const rdp_b200_scanout_options *opts, uint32_t *rgba,
                            size_t capacity_pixels, unsigned *width, unsigned *height);
+/* scanout_async_buffer, rdp_device.cpp:1130-1158 ({Buffer, Fence} pair): scans out and starts an asynchronous copy
+ * into `rgba` (pinned memory recommended); returns a fence for rdp_b200_scanout_wait (0: blank / too small). */
+uint64_t rdp_b200_scanout_async(rdp_b200_processor *p, const rdp_b200_scanout_options *opts, uint32_t *rgba,
+                                size_t capacity_pixels, unsigned *width, unsigned *height);
+void rdp_b200_scanout_wait(rdp_b200_processor *p, uint64_t fence);
 void rdp_b200_default_scanout_options(rdp_b200_scanout_options *opts);
 
 /* Introspection (not in the reference API): backend name, kernels launched, primitives / passes submitted. */

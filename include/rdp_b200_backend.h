@@ -68,7 +68,10 @@ void *rdpb_hidden_device_ptr(rdpb_device *dev);
 
 /* Pass recording and submission. */
 int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out);
+/* Uploads records / states / texture-load descriptors of the pass from the staging area; command words follow as
+ * one rdpb_pass_upload_words() call per contiguous run (`src` is staging memory or caller-owned "borrowed" memory). */
 int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *counts);
+int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_words, uint32_t dst_word_offset);
 /* Front end of a pass in one launch: replay `num_uploads` texture loads into TMEM snapshots (when update_tmem),
  * decode `num_prims` primitives from their raw command words and allocate their span jobs. */
 int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims);

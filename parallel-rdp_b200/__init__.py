@@ -39,6 +39,7 @@ def _bind(lib):
         "rdp_b200_enqueue_command": (None, [P, C.c_uint, P]),
         "rdp_b200_enqueue_command_direct": (None, [P, C.c_uint, P]),
         "rdp_b200_enqueue_command_stream": (None, [P, SZ, P]),
+        "rdp_b200_enqueue_command_stream_borrowed": (None, [P, SZ, P]),
         "rdp_b200_flush": (None, [P]),
         "rdp_b200_signal_timeline": (U64, [P]),
         "rdp_b200_wait_for_timeline": (None, [P, U64]),
@@ -60,6 +61,8 @@ def _bind(lib):
         "rdp_b200_scanout": (P, [P, P, P, P]),
         "rdp_b200_scanout_sync": (None, [P, P, P, SZ, P, P]),
         "rdp_b200_default_scanout_options": (None, [P]),
+        "rdp_b200_scanout_async": (U64, [P, P, P, SZ, P, P]),
+        "rdp_b200_scanout_wait": (None, [P, U64]),
         "rdp_b200_backend_name": (C.c_char_p, []),
         "rdp_b200_launch_count": (U64, [P]),
         "rdp_b200_primitive_count": (U64, [P]),
@@ -126,6 +129,12 @@ class CommandProcessor:
         w = np.ascontiguousarray(words, dtype=np.uint32)
         self.lib.rdp_b200_enqueue_command_stream(self._h, w.size, w.ctypes.data)
 
+    def enqueue_command_stream_borrowed(self, words: np.ndarray):
+        """Zero-copy: `words` (uint32, contiguous, ideally pinned) must stay alive and unmodified until a later idle(),
+        wait_for_timeline() or scan-out fence wait returns."""
+        assert words.dtype == np.uint32 and words.flags["C_CONTIGUOUS"]
+        self.lib.rdp_b200_enqueue_command_stream_borrowed(self._h, words.size, words.ctypes.data)
+
     def enqueue_command_stream_ptr(self, ptr: int, num_words: int):
         self.lib.rdp_b200_enqueue_command_stream(self._h, num_words, ptr)
 
@@ -181,6 +190,16 @@ class CommandProcessor:
                                        C.byref(w), C.byref(h))
         n = w.value * h.value
         return out[:n].reshape(h.value, w.value) if n else out[:0].reshape(0, 0), w.value, h.value
+
+    def scanout_async(self, opts: ScanoutOptions | None, out: np.ndarray):
+        """Starts scan-out + asynchronous copy into `out` (uint32, ideally pinned).  Returns (fence, w, h)."""
+        w, h = C.c_uint(0), C.c_uint(0)
+        fence = self.lib.rdp_b200_scanout_async(self._h, C.byref(opts) if opts is not None else None, out.ctypes.data, out.size,
+                                                C.byref(w), C.byref(h))
+        return fence, w.value, h.value
+
+    def scanout_wait(self, fence: int):
+        self.lib.rdp_b200_scanout_wait(self._h, fence)
 
     def scanout(self, opts: ScanoutOptions | None = None):
         """Device-pointer scan-out (no host copy).  Returns (device_ptr, w, h)."""

@@ -988,8 +988,6 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 		}
 	}
 
-	if (c->num_words)
-		CK(cudaMemcpyAsync(words, base + StagingLayout::words_off, size_t(c->num_words) * 4, cudaMemcpyHostToDevice, dev->stream));
 	if (c->num_prims)
 		CK(cudaMemcpyAsync(records, base + StagingLayout::records_off, size_t(c->num_prims) * sizeof(PrimRecord), cudaMemcpyHostToDevice, dev->stream));
 	if (c->num_states)
@@ -1003,6 +1001,22 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 	dev->cur_records = records;
 	dev->cur_states = states;
 	dev->cur_uploads = uploads;
+	return 0;
+}
+
+int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_words, uint32_t dst_word_offset)
+{
+	cudaSetDevice(dev->ordinal);
+	if (!num_words)
+		return 0;
+	if (size_t(dst_word_offset) + num_words > kMaxPassWords)
+	{
+		dev->error = "pass word buffer overflow";
+		return -1;
+	}
+	CK(cudaMemcpyAsync(const_cast<uint32_t *>(dev->cur_words) + dst_word_offset, src, size_t(num_words) * 4, cudaMemcpyHostToDevice, dev->stream));
+	// Staged runs live in the current staging slot: its reuse must wait for this copy too.
+	CK(cudaEventRecord(dev->staging_done[dev->staging_index], dev->stream));
 	return 0;
 }
 
@@ -1119,18 +1133,20 @@ int rdpb_wait(rdpb_device *dev, uint64_t value)
 	cudaSetDevice(dev->ordinal);
 	cudaEvent_t ev = nullptr;
 	{
+		// Points are recorded in stream order, so everything queued before `value` completes no later than it.
+		// Values come from independent counters (timeline, scan-out fences): match by identity, not by magnitude.
 		std::lock_guard<std::mutex> holder{dev->timeline_lock};
-		// Retire everything up to and including `value`; the last one retired is the one to wait on.
-		while (!dev->timeline.empty() && dev->timeline.front().first <= value)
-		{
-			if (ev)
-				dev->free_events.push_back(ev);
-			ev = dev->timeline.front().second;
-			dev->timeline.pop_front();
-		}
+		size_t found = dev->timeline.size();
+		for (size_t i = 0; i < dev->timeline.size(); i++)
+			if (dev->timeline[i].first == value)
+				found = i;
+		if (found == dev->timeline.size())
+			return 0; // already retired
+		ev = dev->timeline[found].second;
+		for (size_t i = 0; i < found; i++)
+			dev->free_events.push_back(dev->timeline[i].second);
+		dev->timeline.erase(dev->timeline.begin(), dev->timeline.begin() + found + 1);
 	}
-	if (!ev)
-		return 0;
 	CK(cudaEventSynchronize(ev));
 	std::lock_guard<std::mutex> holder{dev->timeline_lock};
 	dev->free_events.push_back(ev);

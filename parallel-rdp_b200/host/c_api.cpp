@@ -52,6 +52,7 @@ int rdp_b200_device_is_supported(const rdp_b200_processor *p) { return p && p->i
 void rdp_b200_enqueue_command(rdp_b200_processor *p, unsigned n, const uint32_t *w) { p->impl.enqueue_command(n, w); }
 void rdp_b200_enqueue_command_direct(rdp_b200_processor *p, unsigned n, const uint32_t *w) { p->impl.enqueue_command_direct(n, w); }
 void rdp_b200_enqueue_command_stream(rdp_b200_processor *p, size_t n, const uint32_t *w) { p->impl.enqueue_command_stream(n, w); }
+void rdp_b200_enqueue_command_stream_borrowed(rdp_b200_processor *p, size_t n, const uint32_t *w) { p->impl.enqueue_command_stream_borrowed(n, w); }
 
 void rdp_b200_flush(rdp_b200_processor *p) { p->impl.flush(); }
 uint64_t rdp_b200_signal_timeline(rdp_b200_processor *p) { return p->impl.signal_timeline(); }
@@ -116,6 +117,13 @@ void rdp_b200_scanout_sync(rdp_b200_processor *p, const rdp_b200_scanout_options
 	if (n)
 		memcpy(rgba, buf.pixels.data(), n * 4);
 }
+
+uint64_t rdp_b200_scanout_async(rdp_b200_processor *p, const rdp_b200_scanout_options *opts, uint32_t *rgba, size_t capacity_pixels,
+                                unsigned *width, unsigned *height)
+{
+	return p->impl.scanout_async(rgba, capacity_pixels, *width, *height, convert_options(opts));
+}
+void rdp_b200_scanout_wait(rdp_b200_processor *p, uint64_t fence) { p->impl.scanout_wait(fence); }
 
 const char *rdp_b200_backend_name(void) { return rdpb_backend_name(); }
 uint64_t rdp_b200_launch_count(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_launch_count(p->impl.get_backend_device()) : 0; }

@@ -1,7 +1,9 @@
 // command_ring.cpp -- see command_ring.hpp.
 #include "command_ring.hpp"
 #include "rdp_device.hpp"
+#include "rdp_setup.cuh"
 #include <chrono>
+#include <string.h>
 
 namespace RDP
 {
@@ -10,11 +12,10 @@ void CommandRing::init(CommandProcessor *processor_, unsigned count_words)
 	teardown_thread();
 	processor = processor_;
 	ring.assign(count_words, 0);
-	mask = count_words - 1;
+	size = count_words;
 	write_count = 0;
 	read_count = 0;
-	completed_count = 0;
-	dead = false;
+	producer_pos = 0;
 	thr = std::thread(&CommandRing::thread_loop, this);
 }
 
@@ -22,7 +23,8 @@ void CommandRing::teardown_thread()
 {
 	if (thr.joinable())
 	{
-		enqueue_command(0, nullptr); // zero-length record = sentinel
+		reserve(0, kHeaderExit);
+		publish(0);
 		thr.join();
 	}
 }
@@ -32,39 +34,100 @@ CommandRing::~CommandRing()
 	teardown_thread();
 }
 
-void CommandRing::enqueue_command(unsigned num_words, const uint32_t *words)
+// Returns a contiguous payload area of `payload_words` words preceded by `header` (already written).
+uint32_t *CommandRing::reserve(uint32_t payload_words, uint32_t header)
 {
-	const uint64_t need = uint64_t(num_words) + 1;
-	uint64_t w = write_count.load(std::memory_order_relaxed);
+	const uint64_t need = uint64_t(payload_words) + 1;
+	uint64_t offset = producer_pos % size;
+	uint64_t total = need;
+	const bool pad = offset + need > size;
+	if (pad)
+		total += size - offset; // the tail is skipped
 
-	// Wait for space (rare: the ring is far larger than a frame's worth of state commands).
-	while (w + need > read_count.load(std::memory_order_acquire) + ring.size())
+	// Wait for space (rare: the ring holds several frames' worth of commands).
+	while (producer_pos + total > read_count.load(std::memory_order_acquire) + size)
 	{
 		std::unique_lock<std::mutex> holder{lock};
 		producer_asleep.store(true, std::memory_order_seq_cst);
 		cond_producer.wait_for(holder, std::chrono::microseconds(100), [&]() {
-			return w + need <= read_count.load(std::memory_order_acquire) + ring.size();
+			return producer_pos + total <= read_count.load(std::memory_order_acquire) + size;
 		});
 		producer_asleep.store(false, std::memory_order_relaxed);
 	}
 
-	ring[w++ & mask] = num_words;
-	for (unsigned i = 0; i < num_words; i++)
-		ring[w++ & mask] = words[i];
-	write_count.store(w, std::memory_order_seq_cst);
+	if (pad)
+	{
+		ring[offset] = kHeaderPad;
+		producer_pos += size - offset;
+		offset = 0;
+	}
+	ring[offset] = header;
+	return ring.data() + offset + 1;
+}
 
-	if (consumer_asleep.load(std::memory_order_seq_cst))
+void CommandRing::publish(uint32_t payload_words)
+{
+	producer_pos += uint64_t(payload_words) + 1;
+	write_count.store(producer_pos, std::memory_order_release);
+	std::atomic_thread_fence(std::memory_order_seq_cst);
+	if (consumer_asleep.load(std::memory_order_relaxed))
 	{
 		std::lock_guard<std::mutex> holder{lock};
 		cond_consumer.notify_one();
 	}
 }
 
+void CommandRing::enqueue_command(unsigned num_words, const uint32_t *words)
+{
+	if (!num_words)
+		return;
+	uint32_t *dst = reserve(num_words, num_words);
+	memcpy(dst, words, size_t(num_words) * sizeof(uint32_t));
+	publish(num_words);
+}
+
+void CommandRing::enqueue_stream(size_t num_words, const uint32_t *words)
+{
+	size_t pos = 0;
+	while (pos < num_words)
+	{
+		// Cut at a command boundary at or below kMaxRecordWords.
+		size_t end = pos;
+		while (end < num_words)
+		{
+			const size_t len = rdpb::command_length_words((words[end] >> 24) & 63u);
+			if (end + len > num_words || end + len - pos > kMaxRecordWords)
+				break;
+			end += len;
+		}
+		if (end == pos)
+			break; // truncated trailing command: dropped, as a short enqueue_command would be
+		const uint32_t n = uint32_t(end - pos);
+		uint32_t *dst = reserve(n, n | kHeaderStream);
+		memcpy(dst, words + pos, size_t(n) * sizeof(uint32_t));
+		publish(n);
+		pos = end;
+	}
+}
+
+void CommandRing::enqueue_stream_borrowed(size_t num_words, const uint32_t *words)
+{
+	if (!num_words)
+		return;
+	uint32_t *dst = reserve(4, 4u | kHeaderBorrowed);
+	const uint64_t ptr = uint64_t(reinterpret_cast<uintptr_t>(words)), n = uint64_t(num_words);
+	dst[0] = uint32_t(ptr);
+	dst[1] = uint32_t(ptr >> 32);
+	dst[2] = uint32_t(n);
+	dst[3] = uint32_t(n >> 32);
+	publish(4);
+}
+
 void CommandRing::drain()
 {
-	const uint64_t target = write_count.load(std::memory_order_relaxed);
+	const uint64_t target = producer_pos;
 	unsigned spins = 0;
-	while (completed_count.load(std::memory_order_acquire) < target)
+	while (read_count.load(std::memory_order_acquire) < target)
 	{
 		if (++spins < 2000)
 			std::this_thread::yield();
@@ -75,10 +138,7 @@ void CommandRing::drain()
 
 void CommandRing::thread_loop()
 {
-	std::vector<uint32_t> cmd;
-	cmd.reserve(64);
 	uint64_t r = 0;
-
 	for (;;)
 	{
 		// Wait for a record; after 500 us without traffic tell the renderer the producer went idle.
@@ -93,6 +153,7 @@ void CommandRing::thread_loop()
 			}
 			std::unique_lock<std::mutex> holder{lock};
 			consumer_asleep.store(true, std::memory_order_seq_cst);
+			std::atomic_thread_fence(std::memory_order_seq_cst);
 			bool got = cond_consumer.wait_for(holder, std::chrono::microseconds(500), [&]() {
 				return write_count.load(std::memory_order_acquire) != r;
 			});
@@ -111,23 +172,49 @@ void CommandRing::thread_loop()
 			continue;
 		}
 
-		const uint32_t num_words = ring[r++ & mask];
-		cmd.resize(num_words);
-		for (uint32_t i = 0; i < num_words; i++)
-			cmd[i] = ring[r++ & mask];
+		uint64_t offset = r % size;
+		uint32_t header = ring[offset];
+		if (header == kHeaderPad)
+		{
+			r += size - offset;
+			offset = 0;
+			header = ring[0];
+		}
+		if (header == kHeaderExit)
+		{
+			read_count.store(r + 1, std::memory_order_release);
+			break;
+		}
+
+		const uint32_t n = header & ~uint32_t(kHeaderStream | kHeaderBorrowed);
+		const uint32_t *payload = ring.data() + offset + 1;
+		if (header & kHeaderBorrowed)
+		{
+			const uint32_t *words = reinterpret_cast<const uint32_t *>(uintptr_t(uint64_t(payload[0]) | (uint64_t(payload[1]) << 32)));
+			const uint64_t total = uint64_t(payload[2]) | (uint64_t(payload[3]) << 32);
+			processor->execute_borrowed_stream(size_t(total), words);
+		}
+		else if (header & kHeaderStream)
+		{
+			uint32_t pos = 0;
+			while (pos < n)
+			{
+				const uint32_t len = rdpb::command_length_words((payload[pos] >> 24) & 63u);
+				processor->enqueue_command_direct(len, payload + pos);
+				pos += len;
+			}
+		}
+		else
+			processor->enqueue_command_direct(n, payload);
+
+		// The record was executed in place: only now may the producer reuse its words.
+		r += uint64_t(n) + 1;
 		read_count.store(r, std::memory_order_release);
 		if (producer_asleep.load(std::memory_order_seq_cst))
 		{
 			std::lock_guard<std::mutex> holder{lock};
 			cond_producer.notify_one();
 		}
-
-		if (cmd.empty())
-			break;
-
-		processor->enqueue_command_direct(num_words, cmd.data());
-		completed_count.store(r, std::memory_order_release);
 	}
-	completed_count.store(r, std::memory_order_release);
 }
 }

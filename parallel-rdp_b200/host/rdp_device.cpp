@@ -63,7 +63,7 @@ CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, 
 		single_threaded_processing = false;
 
 	if (is_supported && !single_threaded_processing)
-		ring.init(this, 64 * 1024);
+		ring.init(this, 1024 * 1024); // 4 MiB: several frames of command words, so the producer never waits on parsing
 }
 
 CommandProcessor::~CommandProcessor()
@@ -330,6 +330,13 @@ void CommandProcessor::enqueue_command(unsigned num_words, const uint32_t *words
 
 void CommandProcessor::enqueue_command_stream(size_t num_words, const uint32_t *words)
 {
+	if (!is_supported)
+		return;
+	if (!single_threaded_processing)
+	{
+		ring.enqueue_stream(num_words, words);
+		return;
+	}
 	size_t pos = 0;
 	while (pos < num_words)
 	{
@@ -339,6 +346,31 @@ void CommandProcessor::enqueue_command_stream(size_t num_words, const uint32_t *
 		enqueue_command_inner(len, words + pos);
 		pos += len;
 	}
+}
+
+void CommandProcessor::execute_borrowed_stream(size_t num_words, const uint32_t *words)
+{
+	renderer.begin_borrowed_source(words, num_words);
+	size_t pos = 0;
+	while (pos < num_words)
+	{
+		const uint32_t len = command_length_words((words[pos] >> 24) & 63u);
+		if (pos + len > num_words)
+			break;
+		enqueue_command_direct(len, words + pos);
+		pos += len;
+	}
+	renderer.end_borrowed_source();
+}
+
+void CommandProcessor::enqueue_command_stream_borrowed(size_t num_words, const uint32_t *words)
+{
+	if (!is_supported)
+		return;
+	if (single_threaded_processing)
+		execute_borrowed_stream(num_words, words);
+	else
+		ring.enqueue_stream_borrowed(num_words, words);
 }
 
 void CommandProcessor::set_quirks(const Quirks &q)
@@ -531,6 +563,25 @@ void CommandProcessor::scanout_async_buffer(VIScanoutBuffer &buffer, const Scano
 	buffer.height = img.height;
 	buffer.pixels.resize(size_t(img.width) * img.height);
 	rdpb_vi_read_output(device, buffer.pixels.data(), img.width, img.height, 1);
+}
+
+uint64_t CommandProcessor::scanout_async(void *rgba, size_t capacity_pixels, unsigned &width, unsigned &height, const ScanoutOptions &opts)
+{
+	ScanoutImage img = scanout(opts);
+	width = img ? img.width : 0;
+	height = img ? img.height : 0;
+	if (!img || size_t(width) * height > capacity_pixels)
+		return 0;
+	rdpb_vi_read_output(device, rgba, width, height, 0);
+	const uint64_t fence = (1ull << 63) | ++scanout_fence_counter; // own namespace, never collides with the timeline
+	rdpb_signal(device, fence);
+	return fence;
+}
+
+void CommandProcessor::scanout_wait(uint64_t fence)
+{
+	if (fence && device)
+		rdpb_wait(device, fence);
 }
 
 void CommandProcessor::scanout_sync(std::vector<RGBA> &colors, unsigned &width, unsigned &height, const ScanoutOptions &opts)

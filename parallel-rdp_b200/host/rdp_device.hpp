@@ -86,6 +86,12 @@ public:
 	void enqueue_command_direct(unsigned num_words, const uint32_t *words);
 	// Extension: a packed stream of back-to-back commands (dump replay, benchmarking).
 	void enqueue_command_stream(size_t num_words, const uint32_t *words);
+	// Extension: same, but the words are *borrowed* -- nothing is copied on the host; primitives are DMA'd to the
+	// GPU straight from `words` (pinned memory makes that asynchronous).  The buffer must stay valid and unmodified
+	// until a later idle(), wait_for_timeline() or scan-out fence covering these commands has returned.
+	void enqueue_command_stream_borrowed(size_t num_words, const uint32_t *words);
+	// Called by the command thread for a borrowed record.
+	void execute_borrowed_stream(size_t num_words, const uint32_t *words);
 
 	void set_quirks(const Quirks &quirks);
 
@@ -103,6 +109,11 @@ public:
 	ScanoutImage scanout(const ScanoutOptions &opts = {});
 	void scanout_sync(std::vector<RGBA> &colors, unsigned &width, unsigned &height, const ScanoutOptions &opts = {});
 	void scanout_async_buffer(VIScanoutBuffer &buffer, const ScanoutOptions &opts = {});
+	// Scan out and start an asynchronous copy of the RGBA8 image into caller memory (pinned memory makes it a true
+	// DMA); returns a fence for scanout_wait().  This is scanout_async_buffer's {buffer, fence} pair (reference
+	// rdp_device.cpp:1130-1158) with a caller-owned buffer.
+	uint64_t scanout_async(void *rgba, size_t capacity_pixels, unsigned &width, unsigned &height, const ScanoutOptions &opts = {});
+	void scanout_wait(uint64_t fence);
 
 	void begin_vi_register_per_scanline(VideoInterface::PerScanlineRegisterFlags flags);
 	void set_vi_register_for_scanline(VideoInterface::PerScanlineRegisterBits reg, uint32_t value);
@@ -123,6 +134,7 @@ private:
 	size_t rdram_size = 0;
 	size_t hidden_size = 0;
 	CommandProcessorFlags flags = 0;
+	uint64_t scanout_fence_counter = 0;
 	bool is_supported = false;
 	bool single_threaded_processing = true;
 

@@ -184,6 +184,8 @@ void Renderer::ensure_pass()
 	rdpb_pass_begin(device, &pass);
 	pass_open = true;
 	num_words = num_prims = num_states = num_uploads = num_spans = num_jobs = 0;
+	staged_words = 0;
+	segments.clear();
 	pass_reads_tmem = false;
 	reset_summary();
 	state_dirty = true;
@@ -264,6 +266,43 @@ void Renderer::set_depth_framebuffer(uint32_t addr)
 	fb.depth_addr = addr;
 }
 
+// Decide where a primitive's words live in the device word buffer; returns that offset.
+uint32_t Renderer::place_words(const uint32_t *words, unsigned count)
+{
+	enum : uint32_t { kMaxGapWords = 1024 };
+	const bool borrowed = words >= borrowed_base && words + count <= borrowed_end;
+	if (borrowed)
+	{
+		if (!segments.empty())
+		{
+			WordSegment &seg = segments.back();
+			const uint32_t *seg_end = seg.src + seg.count;
+			if (seg.borrowed && seg.src >= borrowed_base && words >= seg_end && size_t(words - seg_end) <= kMaxGapWords)
+			{
+				const uint32_t offset = seg.dst + uint32_t(words - seg.src);
+				seg.count = uint32_t(words - seg.src) + count;
+				num_words = seg.dst + seg.count;
+				return offset;
+			}
+		}
+		segments.push_back({ words, count, num_words, true });
+		const uint32_t offset = num_words;
+		num_words += count;
+		return offset;
+	}
+
+	uint32_t *dst = pass.words + staged_words;
+	memcpy(dst, words, count * sizeof(uint32_t));
+	if (!segments.empty() && !segments.back().borrowed && segments.back().src + segments.back().count == dst)
+		segments.back().count += count;
+	else
+		segments.push_back({ dst, count, num_words, false });
+	staged_words += count;
+	const uint32_t offset = num_words;
+	num_words += count;
+	return offset;
+}
+
 void Renderer::draw_primitive(const uint32_t *words, unsigned count)
 {
 	if (validation)
@@ -286,15 +325,13 @@ void Renderer::draw_primitive(const uint32_t *words, unsigned count)
 	primitive_line_range(words, st.raster_flags, st.sc_ylo, st.sc_yhi, line_lo, line_hi);
 
 	PrimRecord &rec = static_cast<PrimRecord *>(pass.records)[num_prims];
-	rec.word_offset = num_words;
+	rec.word_offset = place_words(words, count);
 	rec.span_base = num_spans;
 	rec.state_id = uint16_t(num_states - 1);
 	rec.tmem_instance = uint16_t(num_uploads);
 	rec.line_lo = int16_t(line_lo);
 	rec.line_hi = int16_t(line_hi);
 
-	memcpy(pass.words + num_words, words, count * sizeof(uint32_t));
-	num_words += count;
 	num_prims++;
 
 	if (line_hi >= line_lo)
@@ -331,7 +368,7 @@ void Renderer::draw_primitive(const uint32_t *words, unsigned count)
 	if (st.blend_flags & BF_Z_UPDATE)
 		fb.depth_write_pending = true;
 
-	const bool full = num_prims == kMaxPrimsPerPass || num_words + 44 > kMaxPassWords ||
+	const bool full = num_prims == kMaxPrimsPerPass || num_words + 44 + 1024 > kMaxPassWords ||
 	                  num_spans + kMaxFbHeight + 2 > kMaxSpansPerPass;
 	if (full)
 		flush_queues();
@@ -369,6 +406,8 @@ void Renderer::flush_queues()
 	counts.num_uploads = num_uploads;
 	counts.num_spans = num_spans;
 	rdpb_pass_upload(device, &counts);
+	for (const WordSegment &seg : segments)
+		rdpb_pass_upload_words(device, seg.src, seg.count, seg.dst);
 
 	const bool need_render = fb.width != 0 && fb.deduced_height != 0 && num_spans != 0;
 
@@ -412,6 +451,8 @@ void Renderer::flush_queues()
 	base_primitive_index += num_prims;
 	pass_open = false;
 	num_words = num_prims = num_states = num_uploads = num_spans = num_jobs = 0;
+	staged_words = 0;
+	segments.clear();
 	pass_reads_tmem = false;
 	fb.deduced_height = 0;
 	fb.color_write_pending = false;

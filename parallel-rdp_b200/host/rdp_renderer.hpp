@@ -10,6 +10,7 @@
 #include "rdp_spec.h"
 #include <stddef.h>
 #include <stdint.h>
+#include <vector>
 
 namespace RDP
 {
@@ -91,6 +92,9 @@ public:
 	void set_depth_framebuffer(uint32_t addr);
 
 	void draw_primitive(const uint32_t *words, unsigned num_words);
+	// While a borrowed source is active, primitives whose words lie inside it are uploaded from there (no host copy).
+	void begin_borrowed_source(const uint32_t *words, size_t num_words) { borrowed_base = words; borrowed_end = words + num_words; }
+	void end_borrowed_source() { borrowed_base = borrowed_end = nullptr; }
 	void load_tile(uint32_t tile, const LoadTileInfo &info);
 
 	void flush_queues();
@@ -124,6 +128,19 @@ private:
 	bool pass_open = false;
 	uint32_t num_words = 0, num_prims = 0, num_states = 0, num_uploads = 0, num_spans = 0, num_jobs = 0;
 	bool pass_reads_tmem = false;
+	// Where the pass's command words come from: runs of host words and their offsets in the device word buffer.
+	// Staged runs point into pass.words; borrowed runs point into the caller's stream (gaps between primitives --
+	// state commands -- ride along, which is cheaper than cutting the run).
+	struct WordSegment
+	{
+		const uint32_t *src;
+		uint32_t count, dst;
+		bool borrowed;
+	};
+	std::vector<WordSegment> segments;
+	uint32_t staged_words = 0;
+	const uint32_t *borrowed_base = nullptr, *borrowed_end = nullptr;
+	uint32_t place_words(const uint32_t *words, unsigned count);
 	// What the pass's non-fill states have in common; lets the backend pick a specialised tile kernel.
 	rdpb::PassSummary summary = {};
 	uint32_t state_tile_kind_bits[8] = {}; // texel kind bit of each tile descriptor under the current snapshot

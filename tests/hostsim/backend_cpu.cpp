@@ -21,7 +21,7 @@ struct rdpb_device
 {
 	uint32_t rdram_size = 0, hidden_size = 0;
 	std::vector<uint8_t> rdram, hidden, tmem, tmem_instances, blend_lut, gamma_lut;
-	std::vector<uint32_t> words;
+	std::vector<uint32_t> words, staging_words;
 	std::vector<PrimRecord> records;
 	std::vector<PassState> states;
 	std::vector<TmemUpload> uploads;
@@ -58,6 +58,9 @@ struct rdpb_device
 	}
 };
 
+// RDP_HOSTSIM_NULL=1 turns every launch into a no-op: used to time the host front-end alone (tools/host_timing.py).
+static const bool g_null_compute = getenv("RDP_HOSTSIM_NULL") != nullptr;
+
 extern "C" {
 
 const char *rdpb_backend_name(void) { return "hostsim-cpu (test only)"; }
@@ -76,6 +79,7 @@ rdpb_device *rdpb_device_create(int, uint32_t rdram_size, uint32_t hidden_size)
 	d->gamma_lut.resize(256 + 256 * 64);
 	build_gamma_lut(d->gamma_lut.data());
 	d->words.resize(kMaxPassWords);
+	d->staging_words.resize(kMaxPassWords);
 	d->records.resize(kMaxPrimsPerPass);
 	d->states.resize(kMaxStatesPerPass);
 	d->uploads.resize(kMaxUploadsPerPass);
@@ -122,7 +126,7 @@ void *rdpb_hidden_device_ptr(rdpb_device *dev) { return dev->hidden.data(); }
 
 int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
 {
-	out->words = dev->words.data();
+	out->words = dev->staging_words.data();
 	out->records = dev->records.data();
 	out->states = dev->states.data();
 	out->uploads = dev->uploads.data();
@@ -135,8 +139,16 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *counts)
 	return 0;
 }
 
+int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_words, uint32_t dst_word_offset)
+{
+	memcpy(dev->words.data() + dst_word_offset, src, size_t(num_words) * 4);
+	return 0;
+}
+
 int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims)
 {
+	if (g_null_compute)
+		return 0;
 	PassBuffers b = dev->buffers();
 	if (update_tmem)
 		for (int slot = 0; slot < int(kTmemBytes / 2); slot++)
@@ -149,6 +161,8 @@ int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, u
 
 int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 {
+	if (g_null_compute)
+		return 0;
 	const FbInfo fb = *static_cast<const FbInfo *>(fb_info);
 	PassBuffers b = dev->buffers();
 	auto or_fn = [](uint32_t *p, uint32_t v) { *p |= v; };
@@ -173,6 +187,8 @@ const char *rdpb_last_tile_variant(rdpb_device *) { return "generic"; }
 
 int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary)
 {
+	if (g_null_compute)
+		return 0;
 	const FbInfo fb = *static_cast<const FbInfo *>(fb_info);
 	if (summary && getenv("RDP_B200_DEBUG_PASSES"))
 	{
@@ -219,6 +235,8 @@ int rdpb_pass_end(rdpb_device *) { return 0; }
 
 int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *lines)
 {
+	if (g_null_compute)
+		return 0;
 	const ViFrame f = *static_cast<const ViFrame *>(frame);
 	const size_t max_out = size_t(640) * 576;
 	if (dev->vi_out.size() != max_out)

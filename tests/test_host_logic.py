@@ -1,0 +1,151 @@
+"""Host-side logic that needs no GPU: the command ring (single commands, bulk stream records, wrap-around),
+asynchronous scan-out fences, and pass summaries.  Runs on the test-only host simulator."""
+import numpy as np
+import pytest
+
+from harness import rdp_builder as rb
+from harness import workloads as wl
+from oracle import angrylion
+from sidebyside import HOSTSIM_LIB, build_hostsim, rdp
+
+VI_REG = rdp.VI_REG
+
+
+def _proc(single_threaded=False, monkeypatch=None):
+    build_hostsim()
+    if monkeypatch is not None:
+        if single_threaded:
+            monkeypatch.setenv("PARALLEL_RDP_SINGLE_THREADED_COMMAND", "1")
+        else:
+            monkeypatch.delenv("PARALLEL_RDP_SINGLE_THREADED_COMMAND", raising=False)
+    rdram = np.zeros(wl.RDRAM_SIZE, dtype=np.uint8)
+    tex, tlut = wl.c3_assets()
+    rdram[wl.TEX_ADDR:wl.TEX_ADDR + tex.size] = tex
+    rdram[wl.TEX_ADDR + 0x1000:wl.TEX_ADDR + 0x1000 + tlut.size] = tlut
+    p = rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, library=HOSTSIM_LIB)
+    p.begin_read_hidden_rdram()[:] = 0
+    p.end_write_hidden_rdram()
+    p.end_write_rdram()
+    return p
+
+
+def _render(feed, monkeypatch, single_threaded=False, frames=3):
+    p = _proc(single_threaded, monkeypatch)
+    try:
+        rng = np.random.RandomState(7)
+        for _ in range(frames):
+            feed(p, wl.c3_frame(rng, 2))
+        p.idle()
+        return p.begin_read_rdram().copy(), (p.begin_read_hidden_rdram() & 3).copy(), p.primitive_count()
+    finally:
+        p.close()
+
+
+def _feed_stream(p, words):
+    p.enqueue_command_stream(words)
+
+
+_KEEP_ALIVE = []
+
+
+def _feed_borrowed(p, words):
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    _KEEP_ALIVE.append(w)  # borrowed: must outlive the processing
+    p.enqueue_command_stream_borrowed(w)
+
+
+def _feed_mixed(p, words):
+    # Alternate copied single commands and borrowed runs inside one pass: staged and borrowed word segments interleave.
+    cmds = rb.split_commands(words)
+    i = 0
+    while i < len(cmds):
+        run = np.ascontiguousarray(np.concatenate(cmds[i:i + 3]), dtype=np.uint32)
+        _KEEP_ALIVE.append(run)
+        p.enqueue_command_stream_borrowed(run)
+        i += 3
+        if i < len(cmds):
+            p.enqueue_command(cmds[i])
+            i += 1
+
+
+def _feed_per_command(p, words):
+    for c in rb.split_commands(words):
+        p.enqueue_command(c)
+
+
+def test_ring_bulk_stream_equals_per_command_and_direct(monkeypatch):
+    a = _render(_feed_stream, monkeypatch)
+    b = _render(_feed_per_command, monkeypatch)
+    c = _render(_feed_stream, monkeypatch, single_threaded=True)
+    d = _render(_feed_borrowed, monkeypatch)
+    e = _render(_feed_mixed, monkeypatch)
+    f = _render(_feed_borrowed, monkeypatch, single_threaded=True)
+    for other in (b, c, d, e, f):
+        assert a[2] == other[2]
+        assert np.array_equal(a[0], other[0]) and np.array_equal(a[1], other[1])
+
+
+def test_ring_wraps_and_splits_large_streams(monkeypatch):
+    """More command words than the ring holds (1 Mi words), in streams larger than one record (32 Ki words):
+    exercises record splitting at command boundaries, the PAD/wrap path and producer back-pressure."""
+    p = _proc(False, monkeypatch)
+    try:
+        b = rb.Builder()
+        b.set_color_image(rb.FMT_RGBA, rb.SIZE_16, wl.COLOR_ADDR, 64)
+        b.set_scissor(0, 0, 64, 64)
+        b.om.__init__()
+        b.om.cycle_type = rb.CYCLE_FILL
+        b.touch_other_modes()
+        b.set_fill_color(0x12341234)
+        head = b.words()
+        # 100k fill rectangles + interleaved NOPs of odd total length so records never align with the ring size.
+        rect = rb.Builder()
+        rect.fill_rectangle(0, 0, 8, 8)
+        one = rect.words()
+        nop = np.zeros(2, dtype=np.uint32)
+        body = np.concatenate([one, nop, one] * 35000)
+        total = 0
+        for _ in range(8):
+            p.enqueue_command_stream(np.concatenate([head, body]))
+            total += 70000
+        p.idle()
+        assert p.primitive_count() == total
+    finally:
+        p.close()
+
+
+def _scanout_frames(mode, monkeypatch):
+    p = _proc(False, monkeypatch)
+    try:
+        rng = np.random.RandomState(11)
+        opts = p.default_scanout_options()
+        opts.blend_previous_frame = 1
+        opts.upscale_deinterlacing = 0
+        frames, fences = [], []
+        bufs = [np.zeros(640 * 576, dtype=np.uint32) for _ in range(3)]
+        for i in range(3):
+            p.enqueue_command_stream(wl.c3_frame(rng, 2))
+            for k, v in wl.c3_vi_registers(i & 1).items():
+                p.set_vi_register(VI_REG[k], v)
+            if mode == "sync":
+                pix, w, h = p.scanout_sync(opts)
+                frames.append(pix.copy())
+            else:
+                fence, w, h = p.scanout_async(opts, bufs[i])
+                assert fence != 0 and (w, h) == (640, 480)
+                fences.append((fence, w, h))
+        for i, (fence, w, h) in enumerate(fences):
+            p.scanout_wait(fence)
+            frames.append(bufs[i][: w * h].reshape(h, w).copy())
+        return frames
+    finally:
+        p.close()
+
+
+def test_scanout_async_matches_sync(monkeypatch):
+    """Three frames in flight with deferred fence waits give the same images as the blocking call."""
+    a = _scanout_frames("sync", monkeypatch)
+    b = _scanout_frames("async", monkeypatch)
+    assert len(a) == len(b) == 3
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and x.any() and np.array_equal(x, y)
