@@ -298,34 +298,35 @@ def run_ours(args):
     # reads that frame's scan-out image back into pinned host memory (scanout_async = the reference's
     # scanout_async_buffer {buffer, fence} pair).  Up to E2E_DEPTH frames are in flight; every fence is waited on
     # inside the timed region, so all K images have landed on the host when the clock stops.
-    E2E_DEPTH = 3
+    E2E_DEPTH = args.e2e_depth
     outs_t = [torch.empty(640 * 576, dtype=torch.int32).pin_memory() for _ in range(E2E_DEPTH)]
     outs = [t.numpy().view(np.uint32) for t in outs_t]
 
     def e2e_run(count):
         fences = []
         for i in range(count):
-            if i >= E2E_DEPTH:
-                proc.scanout_wait(fences[i - E2E_DEPTH])  # buffer i % E2E_DEPTH is free again
+            if i >= E2E_DEPTH and proc.scanout_wait(fences[i - E2E_DEPTH]) != (640, 480):  # frees buffer i % E2E_DEPTH
+                raise SystemExit("bench.py: scan-out failed in the e2e leg")
             proc.enqueue_command_stream_borrowed(frames[i % n_frames])
             for k, v in wl.c2_vi_registers(i & 1).items():
                 proc.set_vi_register(VI_REG[k], v)
-            fence, w, h = proc.scanout_async(opts, outs[i % E2E_DEPTH])
-            if not fence or (w, h) != (640, 480):
-                raise SystemExit("bench.py: scan-out failed in the e2e leg")
-            fences.append(fence)
+            fences.append(proc.scanout_async(opts, outs[i % E2E_DEPTH]))
         for f in fences[-E2E_DEPTH:]:
-            proc.scanout_wait(f)
+            if proc.scanout_wait(f) != (640, 480):
+                raise SystemExit("bench.py: scan-out failed in the e2e leg")
 
     proc.idle()
     e2e_run(max(args.warmup, 3))
     proc.idle()
     barrier()
+    host_t0 = proc.host_timing()
     t0 = time.perf_counter()
     e2e_run(args.steps)
     proc.idle()
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    host_t1 = proc.host_timing()
+    host_us = {k: round(1e6 * (host_t1[k] - host_t0[k]) / args.steps, 2) for k in host_t1}
     barrier()
     clocks = sampler.stop()  # sampled from before the device-timed region to the end of the e2e region
 
@@ -347,6 +348,7 @@ def run_ours(args):
             "shaded_pixels_per_frame": int(shaded_pairs / max(args.steps, 1)),
             "e2e": {"value": round(total_frames / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": frame_bytes + 288 * 32,
                     "d2h_bytes_per_step": 640 * 480 * 4, "ms_per_step": round(e2e_ms / args.steps, 5),
+                    "command_thread_us_per_step": host_us,
                     "path": "rdp_b200_enqueue_command_stream_borrowed + rdp_b200_set_vi_register + rdp_b200_scanout_async/_wait "
                             "(pinned host buffers, %d frames in flight)" % E2E_DEPTH},
             "gpu_launches": int(launches),
@@ -449,6 +451,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="frames in flight in the e2e leg")
     ap.add_argument("--small", action="store_true", help="fewer distinct frames (quick functional run; violates the L2 rule)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -107,8 +107,10 @@ const void *rdp_b200_scanout(rdp_b200_processor *p, const rdp_b200_scanout_optio
 /* scanout_sync, rdp_device.cpp:1160-1182: copies up to `capacity_pixels` RGBA8 pixels into `rgba`. */
 void rdp_b200_scanout_sync(rdp_b200_processor *p, const rdp_b200_scanout_options *opts, uint32_t *rgba,
                            size_t capacity_pixels, unsigned *width, unsigned *height);
-/* scanout_async_buffer, rdp_device.cpp:1130-1158 ({Buffer, Fence} pair): scans out and starts an asynchronous copy
- * into `rgba` (pinned memory recommended); returns a fence for rdp_b200_scanout_wait (0: blank / too small). */
+/* scanout_async_buffer, rdp_device.cpp:1130-1158 ({Buffer, Fence} pair).  Snapshots the VI registers and queues a
+ * scan-out + asynchronous copy into `rgba` (pinned memory recommended) behind the commands enqueued so far; returns at
+ * once with a fence for rdp_b200_scanout_wait.  *width / *height (0 x 0: blank or buffer too small) and the pixels
+ * are valid once the wait has returned; `rgba`, `width` and `height` must stay alive until then. */
 uint64_t rdp_b200_scanout_async(rdp_b200_processor *p, const rdp_b200_scanout_options *opts, uint32_t *rgba,
                                 size_t capacity_pixels, unsigned *width, unsigned *height);
 void rdp_b200_scanout_wait(rdp_b200_processor *p, uint64_t fence);
@@ -122,6 +124,9 @@ uint64_t rdp_b200_pass_count(rdp_b200_processor *p);
 void *rdp_b200_cuda_stream(rdp_b200_processor *p);
 /* Name of the tile-kernel instantiation the most recent render pass ran ("generic" = the uber-kernel fallback). */
 const char *rdp_b200_last_tile_variant(rdp_b200_processor *p);
+/* Seconds the command thread spent: [0] executing ring records, [1] of that submitting passes, [2] of that in queued
+ * scan-outs; [0] - [1] - [2] is command parsing / pass recording. */
+void rdp_b200_host_timing(rdp_b200_processor *p, double out3[3]);
 /* The backend device handle (rdpb_device*, include/rdp_b200_backend.h) for the measurement entry points. */
 void *rdp_b200_backend_device(rdp_b200_processor *p);
 

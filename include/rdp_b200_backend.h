@@ -89,6 +89,8 @@ int rdpb_pass_end(rdpb_device *dev);
 int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame /* rdpb::ViFrame */, const void *lines /* rdpb::ViLine[288] */);
 void *rdpb_vi_output_device_ptr(rdpb_device *dev);
 int rdpb_vi_read_output(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, int sync);
+/* Asynchronous read-back on a side stream + a timeline point after it: rdpb_wait(fence_value) => pixels are in dst. */
+int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, uint64_t fence_value);
 
 /* Synchronisation. */
 int rdpb_signal(rdpb_device *dev, uint64_t value);   /* records a point in stream order */

@@ -69,6 +69,7 @@ def _bind(lib):
         "rdp_b200_pass_count": (U64, [P]),
         "rdp_b200_cuda_stream": (P, [P]),
         "rdp_b200_last_tile_variant": (C.c_char_p, [P]),
+        "rdp_b200_host_timing": (None, [P, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -192,14 +193,17 @@ class CommandProcessor:
         return out[:n].reshape(h.value, w.value) if n else out[:0].reshape(0, 0), w.value, h.value
 
     def scanout_async(self, opts: ScanoutOptions | None, out: np.ndarray):
-        """Starts scan-out + asynchronous copy into `out` (uint32, ideally pinned).  Returns (fence, w, h)."""
+        """Queues scan-out + asynchronous copy into `out` (uint32, ideally pinned) behind the commands enqueued so far.
+        Returns a ticket for scanout_wait(), which returns (w, h)."""
         w, h = C.c_uint(0), C.c_uint(0)
         fence = self.lib.rdp_b200_scanout_async(self._h, C.byref(opts) if opts is not None else None, out.ctypes.data, out.size,
                                                 C.byref(w), C.byref(h))
-        return fence, w.value, h.value
+        return (fence, w, h, out, opts)  # the ticket keeps everything the library writes to alive
 
-    def scanout_wait(self, fence: int):
+    def scanout_wait(self, ticket):
+        fence, w, h = ticket[0], ticket[1], ticket[2]
         self.lib.rdp_b200_scanout_wait(self._h, fence)
+        return w.value, h.value
 
     def scanout(self, opts: ScanoutOptions | None = None):
         """Device-pointer scan-out (no host copy).  Returns (device_ptr, w, h)."""
@@ -219,6 +223,11 @@ class CommandProcessor:
 
     def pass_count(self) -> int:
         return self.lib.rdp_b200_pass_count(self._h)
+
+    def host_timing(self):
+        out = (C.c_double * 3)()
+        self.lib.rdp_b200_host_timing(self._h, out)
+        return {"ring_busy_s": out[0], "submit_s": out[1], "scanout_s": out[2], "parse_s": out[0] - out[1] - out[2]}
 
     def last_tile_variant(self) -> str:
         return self.lib.rdp_b200_last_tile_variant(self._h).decode()

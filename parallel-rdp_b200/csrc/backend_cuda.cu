@@ -518,14 +518,23 @@ struct rdpb_device
 	unsigned long long *d_counters = nullptr;
 
 	uint8_t *staging[kStagingSlots] = {};
-	cudaEvent_t staging_done[kStagingSlots] = {};
+	cudaEvent_t staging_done[kStagingSlots] = {};   // recorded on stream_up: the slot's uploads have landed
 	bool staging_in_flight[kStagingSlots] = {};
+	cudaEvent_t kernels_done[kStagingSlots] = {};   // recorded on stream: the pass that read the slot's device inputs is done
+	bool kernels_in_flight[kStagingSlots] = {};
+	bool pass_upload_pending = false;               // the compute stream has not yet waited for this pass's uploads
+
+	// Copy engines run beside the SMs: pass inputs go up on stream_up while the previous pass computes, scan-out
+	// images come down on stream_down while the next frame renders.
+	cudaStream_t stream_up = nullptr, stream_down = nullptr;
+	bool side_streams_owned = true;
+	cudaEvent_t vi_done = nullptr;
+	cudaEvent_t readback_done[2] = {};
+	bool readback_in_flight[2] = {};
 	unsigned staging_index = 0;
 
-	uint32_t *d_words = nullptr;
-	PrimRecord *d_records = nullptr;
-	PassState *d_states = nullptr;
-	TmemUpload *d_uploads = nullptr;
+	uint32_t *d_words[kStagingSlots] = {};  // device-side input slots, one per staging slot
+	uint8_t *d_inputs[kStagingSlots] = {};  // records | states | texture-load descriptors
 	PrimSetup *d_prims = nullptr;
 	Span *d_spans = nullptr;
 	uint32_t *d_fine = nullptr, *d_coarse = nullptr;
@@ -673,6 +682,13 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	case GOP_VI:
 	{
 		dev->vi_out_index ^= 1u;
+		if (dev->readback_in_flight[dev->vi_out_index])
+		{
+			// The image about to be overwritten may still be on its way to the host.
+			if (!check(dev, cudaStreamWaitEvent(dev->stream, dev->readback_done[dev->vi_out_index], 0), "cudaStreamWaitEvent"))
+				return -1;
+			dev->readback_in_flight[dev->vi_out_index] = false;
+		}
 		ViBuffers b;
 		b.rdram = dev->rdram;
 		b.hidden = dev->hidden;
@@ -710,6 +726,13 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 
 static int submit(rdpb_device *dev, GpuOp &op)
 {
+	if (dev->pass_upload_pending)
+	{
+		// First kernel of the pass: everything uploaded so far for it (stream_up) must have landed.
+		if (!check(dev, cudaStreamWaitEvent(dev->stream, dev->staging_done[dev->staging_index], 0), "cudaStreamWaitEvent"))
+			return -1;
+		dev->pass_upload_pending = false;
+	}
 	op.words = dev->cur_words;
 	op.records = dev->cur_records;
 	op.states = dev->cur_states;
@@ -765,6 +788,20 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 			dev->tile_blocks_per_sm_override = uint32_t(std::max(1, atoi(env)));
 	}
 	need(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	if (getenv("RDP_B200_SINGLE_STREAM"))
+	{
+		// Diagnostic: no copy/compute overlap (everything in one stream's order).
+		dev->stream_up = dev->stream_down = dev->stream;
+		dev->side_streams_owned = false;
+	}
+	else
+	{
+		need(cudaStreamCreateWithFlags(&dev->stream_up, cudaStreamNonBlocking), "cudaStreamCreate up");
+		need(cudaStreamCreateWithFlags(&dev->stream_down, cudaStreamNonBlocking), "cudaStreamCreate down");
+	}
+	need(cudaEventCreateWithFlags(&dev->vi_done, cudaEventDisableTiming), "cudaEventCreate");
+	for (auto &e : dev->readback_done)
+		need(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
 	need(cudaMalloc(&dev->rdram, rdram_size), "cudaMalloc rdram");
 	need(cudaMalloc(&dev->hidden, hidden_size), "cudaMalloc hidden");
 	need(cudaHostAlloc(&dev->tmem_host, kTmemBytes, cudaHostAllocMapped), "cudaHostAlloc tmem");
@@ -774,10 +811,14 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	need(cudaMalloc(&dev->blend_lut, 0x8000), "cudaMalloc blend lut");
 	need(cudaMalloc(&dev->gamma_lut, 256 + 256 * 64), "cudaMalloc gamma lut");
 	need(cudaMalloc(&dev->d_counters, 8 * sizeof(unsigned long long)), "cudaMalloc counters");
-	need(cudaMalloc(&dev->d_words, size_t(kMaxPassWords) * 4), "cudaMalloc words");
-	need(cudaMalloc(&dev->d_records, size_t(kMaxPrimsPerPass) * sizeof(PrimRecord)), "cudaMalloc records");
-	need(cudaMalloc(&dev->d_states, size_t(kMaxStatesPerPass) * sizeof(PassState)), "cudaMalloc states");
-	need(cudaMalloc(&dev->d_uploads, size_t(kMaxUploadsPerPass) * sizeof(TmemUpload)), "cudaMalloc uploads");
+	for (unsigned i = 0; i < kStagingSlots; i++)
+	{
+		need(cudaMalloc(&dev->d_words[i], size_t(kMaxPassWords) * 4), "cudaMalloc words");
+		// One block: records, then states, then texture-load descriptors (packed per pass by rdpb_pass_upload).
+		need(cudaMalloc(&dev->d_inputs[i], size_t(kMaxPrimsPerPass) * sizeof(PrimRecord) + size_t(kMaxStatesPerPass) * sizeof(PassState) +
+		                                       size_t(kMaxUploadsPerPass) * sizeof(TmemUpload) + 1024),
+		     "cudaMalloc pass inputs");
+	}
 	need(cudaMalloc(&dev->d_prims, size_t(kMaxPrimsPerPass) * sizeof(PrimSetup)), "cudaMalloc prims");
 	need(cudaMalloc(&dev->d_spans, size_t(kMaxSpansPerPass) * sizeof(Span)), "cudaMalloc spans");
 	const size_t fine_bytes = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 32) * 4;
@@ -798,6 +839,7 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	{
 		need(cudaHostAlloc(&dev->staging[i], StagingLayout::total, cudaHostAllocDefault), "cudaHostAlloc staging");
 		need(cudaEventCreateWithFlags(&dev->staging_done[i], cudaEventDisableTiming), "cudaEventCreate");
+		need(cudaEventCreateWithFlags(&dev->kernels_done[i], cudaEventDisableTiming), "cudaEventCreate");
 	}
 
 	if (ok)
@@ -822,10 +864,10 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		need(cudaStreamSynchronize(dev->stream), "initial sync");
 	}
 
-	dev->cur_words = dev->d_words;
-	dev->cur_records = dev->d_records;
-	dev->cur_states = dev->d_states;
-	dev->cur_uploads = dev->d_uploads;
+	dev->cur_words = dev->d_words[0];
+	dev->cur_records = reinterpret_cast<PrimRecord *>(dev->d_inputs[0]);
+	dev->cur_states = nullptr;
+	dev->cur_uploads = nullptr;
 
 	if (!ok)
 	{
@@ -841,8 +883,7 @@ void rdpb_device_destroy(rdpb_device *dev)
 	if (!dev)
 		return;
 	cudaSetDevice(dev->ordinal);
-	if (dev->stream)
-		cudaStreamSynchronize(dev->stream);
+	cudaDeviceSynchronize();
 	cudaFree(dev->rdram);
 	cudaFree(dev->hidden);
 	cudaFreeHost(dev->tmem_host);
@@ -850,10 +891,11 @@ void rdpb_device_destroy(rdpb_device *dev)
 	cudaFree(dev->blend_lut);
 	cudaFree(dev->gamma_lut);
 	cudaFree(dev->d_counters);
-	cudaFree(dev->d_words);
-	cudaFree(dev->d_records);
-	cudaFree(dev->d_states);
-	cudaFree(dev->d_uploads);
+	for (unsigned i = 0; i < kStagingSlots; i++)
+	{
+		cudaFree(dev->d_words[i]);
+		cudaFree(dev->d_inputs[i]);
+	}
 	cudaFree(dev->d_prims);
 	cudaFree(dev->d_spans);
 	cudaFree(dev->d_fine);
@@ -874,6 +916,8 @@ void rdpb_device_destroy(rdpb_device *dev)
 		cudaFreeHost(dev->staging[i]);
 		if (dev->staging_done[i])
 			cudaEventDestroy(dev->staging_done[i]);
+		if (dev->kernels_done[i])
+			cudaEventDestroy(dev->kernels_done[i]);
 	}
 	for (auto &t : dev->timeline)
 		cudaEventDestroy(t.second);
@@ -884,6 +928,15 @@ void rdpb_device_destroy(rdpb_device *dev)
 		cudaEventDestroy(p.a);
 		cudaEventDestroy(p.b);
 	}
+	if (dev->vi_done)
+		cudaEventDestroy(dev->vi_done);
+	for (auto &e : dev->readback_done)
+		if (e)
+			cudaEventDestroy(e);
+	if (dev->stream_up && dev->side_streams_owned)
+		cudaStreamDestroy(dev->stream_up);
+	if (dev->stream_down && dev->side_streams_owned)
+		cudaStreamDestroy(dev->stream_down);
 	if (dev->stream)
 		cudaStreamDestroy(dev->stream);
 	delete dev;
@@ -970,32 +1023,48 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 	const unsigned i = dev->staging_index;
 	const uint8_t *base = dev->staging[i];
 
-	uint32_t *words = dev->d_words;
-	PrimRecord *records = dev->d_records;
-	PassState *states = dev->d_states;
-	TmemUpload *uploads = dev->d_uploads;
+	// Records, states and texture-load descriptors travel as one block: the (small) state and descriptor arrays are
+	// packed right behind the records in the staging slot so a pass costs one H2D copy, not three.
+	const size_t records_bytes = size_t(c->num_prims) * sizeof(PrimRecord);
+	const size_t states_at = (records_bytes + 255) & ~size_t(255);
+	const size_t states_bytes = size_t(c->num_states) * sizeof(PassState);
+	const size_t uploads_at = (states_at + states_bytes + 255) & ~size_t(255);
+	const size_t uploads_bytes = size_t(c->num_uploads) * sizeof(TmemUpload);
+	const size_t block_bytes = uploads_at + uploads_bytes;
+	uint8_t *block_host = dev->staging[i] + StagingLayout::records_off;
+	if (states_bytes)
+		memmove(block_host + states_at, base + StagingLayout::states_off, states_bytes);
+	if (uploads_bytes)
+		memmove(block_host + uploads_at, base + StagingLayout::uploads_off, uploads_bytes);
+
+	uint32_t *words = dev->d_words[i];
+	uint8_t *block = dev->d_inputs[i];
+	// The previous pass that used this device slot may still be reading it.
+	if (dev->kernels_in_flight[i])
+	{
+		CK(cudaStreamWaitEvent(dev->stream_up, dev->kernels_done[i], 0));
+		dev->kernels_in_flight[i] = false;
+	}
 	if (dev->recording)
 	{
 		// Keep this pass's inputs resident in the arena so the pass can be replayed without host traffic.
 		words = static_cast<uint32_t *>(arena_alloc(dev, size_t(c->num_words) * 4 + 4));
-		records = static_cast<PrimRecord *>(arena_alloc(dev, size_t(c->num_prims) * sizeof(PrimRecord) + 16));
-		states = static_cast<PassState *>(arena_alloc(dev, size_t(c->num_states) * sizeof(PassState) + 16));
-		uploads = static_cast<TmemUpload *>(arena_alloc(dev, size_t(c->num_uploads) * sizeof(TmemUpload) + 16));
-		if (!words || !records || !states || !uploads)
+		block = static_cast<uint8_t *>(arena_alloc(dev, block_bytes + 16));
+		if (!words || !block)
 		{
 			dev->error = "record arena exhausted";
 			return -1;
 		}
 	}
+	PrimRecord *records = reinterpret_cast<PrimRecord *>(block);
+	PassState *states = reinterpret_cast<PassState *>(block + states_at);
+	TmemUpload *uploads = reinterpret_cast<TmemUpload *>(block + uploads_at);
 
-	if (c->num_prims)
-		CK(cudaMemcpyAsync(records, base + StagingLayout::records_off, size_t(c->num_prims) * sizeof(PrimRecord), cudaMemcpyHostToDevice, dev->stream));
-	if (c->num_states)
-		CK(cudaMemcpyAsync(states, base + StagingLayout::states_off, size_t(c->num_states) * sizeof(PassState), cudaMemcpyHostToDevice, dev->stream));
-	if (c->num_uploads)
-		CK(cudaMemcpyAsync(uploads, base + StagingLayout::uploads_off, size_t(c->num_uploads) * sizeof(TmemUpload), cudaMemcpyHostToDevice, dev->stream));
-	CK(cudaEventRecord(dev->staging_done[i], dev->stream));
+	if (block_bytes)
+		CK(cudaMemcpyAsync(block, block_host, block_bytes, cudaMemcpyHostToDevice, dev->stream_up));
+	CK(cudaEventRecord(dev->staging_done[i], dev->stream_up));
 	dev->staging_in_flight[i] = true;
+	dev->pass_upload_pending = true;
 
 	dev->cur_words = words;
 	dev->cur_records = records;
@@ -1014,9 +1083,10 @@ int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_w
 		dev->error = "pass word buffer overflow";
 		return -1;
 	}
-	CK(cudaMemcpyAsync(const_cast<uint32_t *>(dev->cur_words) + dst_word_offset, src, size_t(num_words) * 4, cudaMemcpyHostToDevice, dev->stream));
+	CK(cudaMemcpyAsync(const_cast<uint32_t *>(dev->cur_words) + dst_word_offset, src, size_t(num_words) * 4, cudaMemcpyHostToDevice, dev->stream_up));
 	// Staged runs live in the current staging slot: its reuse must wait for this copy too.
-	CK(cudaEventRecord(dev->staging_done[dev->staging_index], dev->stream));
+	CK(cudaEventRecord(dev->staging_done[dev->staging_index], dev->stream_up));
+	dev->pass_upload_pending = true;
 	return 0;
 }
 
@@ -1065,7 +1135,14 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 	return submit(dev, op);
 }
 
-int rdpb_pass_end(rdpb_device *) { return 0; }
+int rdpb_pass_end(rdpb_device *dev)
+{
+	cudaSetDevice(dev->ordinal);
+	const unsigned i = dev->staging_index;
+	CK(cudaEventRecord(dev->kernels_done[i], dev->stream));
+	dev->kernels_in_flight[i] = true;
+	return 0;
+}
 
 int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *lines)
 {
@@ -1111,7 +1188,29 @@ int rdpb_vi_read_output(rdpb_device *dev, void *dst, uint32_t width, uint32_t he
 	return copy_common(dev, dst, dev->vi_out[dev->vi_out_index], size_t(width) * height * 4, cudaMemcpyDeviceToHost, sync);
 }
 
+static int signal_on(rdpb_device *dev, uint64_t value, cudaStream_t stream);
+
+// Asynchronous read-back of the current scan-out image on the download stream, followed by a timeline point there:
+// waiting for `fence_value` means the pixels are in `dst`.  The compute stream is never blocked by the copy.
+int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, uint64_t fence_value)
+{
+	cudaSetDevice(dev->ordinal);
+	const unsigned idx = dev->vi_out_index;
+	CK(cudaEventRecord(dev->vi_done, dev->stream));
+	CK(cudaStreamWaitEvent(dev->stream_down, dev->vi_done, 0));
+	if (width && height)
+		CK(cudaMemcpyAsync(dst, dev->vi_out[idx], size_t(width) * height * 4, cudaMemcpyDeviceToHost, dev->stream_down));
+	CK(cudaEventRecord(dev->readback_done[idx], dev->stream_down));
+	dev->readback_in_flight[idx] = true;
+	return signal_on(dev, fence_value, dev->stream_down);
+}
+
 int rdpb_signal(rdpb_device *dev, uint64_t value)
+{
+	return signal_on(dev, value, dev->stream);
+}
+
+static int signal_on(rdpb_device *dev, uint64_t value, cudaStream_t stream)
 {
 	cudaSetDevice(dev->ordinal);
 	std::lock_guard<std::mutex> holder{dev->timeline_lock};
@@ -1123,7 +1222,7 @@ int rdpb_signal(rdpb_device *dev, uint64_t value)
 	}
 	else
 		CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
-	CK(cudaEventRecord(ev, dev->stream));
+	CK(cudaEventRecord(ev, stream));
 	dev->timeline.emplace_back(value, ev);
 	return 0;
 }
@@ -1156,7 +1255,9 @@ int rdpb_wait(rdpb_device *dev, uint64_t value)
 int rdpb_sync(rdpb_device *dev)
 {
 	cudaSetDevice(dev->ordinal);
+	CK(cudaStreamSynchronize(dev->stream_up));
 	CK(cudaStreamSynchronize(dev->stream));
+	CK(cudaStreamSynchronize(dev->stream_down));
 	return 0;
 }
 
@@ -1244,11 +1345,7 @@ int rdpb_record_end(rdpb_device *dev)
 	dev->recording = false;
 	if (dev->marks.empty() || dev->marks.back() != dev->log.size())
 		dev->marks.push_back(uint32_t(dev->log.size()));
-	dev->cur_words = dev->d_words;
-	dev->cur_records = dev->d_records;
-	dev->cur_states = dev->d_states;
-	dev->cur_uploads = dev->d_uploads;
-	CK(cudaStreamSynchronize(dev->stream));
+	CK(cudaDeviceSynchronize());
 	return 0;
 }
 

@@ -49,6 +49,7 @@ enum Op : uint32_t
 	OP_META_FLUSH = 0x02,
 	OP_META_IDLE = 0x03,
 	OP_META_SET_QUIRKS = 0x04,
+	OP_META_SCANOUT = 0x05, // words[1..2] = pointer to a heap-allocated scan-out request (command thread executes it)
 	OP_TRI_FILL = 0x08,
 	OP_TRI_FILL_Z = 0x09,
 	OP_TRI_TEX = 0x0a,

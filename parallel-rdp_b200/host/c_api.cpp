@@ -121,7 +121,7 @@ void rdp_b200_scanout_sync(rdp_b200_processor *p, const rdp_b200_scanout_options
 uint64_t rdp_b200_scanout_async(rdp_b200_processor *p, const rdp_b200_scanout_options *opts, uint32_t *rgba, size_t capacity_pixels,
                                 unsigned *width, unsigned *height)
 {
-	return p->impl.scanout_async(rgba, capacity_pixels, *width, *height, convert_options(opts));
+	return p->impl.scanout_async(rgba, capacity_pixels, width, height, convert_options(opts));
 }
 void rdp_b200_scanout_wait(rdp_b200_processor *p, uint64_t fence) { p->impl.scanout_wait(fence); }
 
@@ -129,6 +129,7 @@ const char *rdp_b200_backend_name(void) { return rdpb_backend_name(); }
 uint64_t rdp_b200_launch_count(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_launch_count(p->impl.get_backend_device()) : 0; }
 uint64_t rdp_b200_primitive_count(rdp_b200_processor *p) { return p->impl.get_primitive_counter(); }
 uint64_t rdp_b200_pass_count(rdp_b200_processor *p) { return p->impl.get_pass_counter(); }
+void rdp_b200_host_timing(rdp_b200_processor *p, double out3[3]) { p->impl.get_host_timing(out3); }
 void *rdp_b200_backend_device(rdp_b200_processor *p) { return p->impl.get_backend_device(); }
 const char *rdp_b200_last_tile_variant(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_last_tile_variant(p->impl.get_backend_device()) : ""; }
 void *rdp_b200_cuda_stream(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_stream(p->impl.get_backend_device()) : nullptr; }

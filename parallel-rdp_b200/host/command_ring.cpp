@@ -186,6 +186,7 @@ void CommandRing::thread_loop()
 			break;
 		}
 
+		const auto busy_t0 = std::chrono::steady_clock::now();
 		const uint32_t n = header & ~uint32_t(kHeaderStream | kHeaderBorrowed);
 		const uint32_t *payload = ring.data() + offset + 1;
 		if (header & kHeaderBorrowed)
@@ -207,6 +208,7 @@ void CommandRing::thread_loop()
 		else
 			processor->enqueue_command_direct(n, payload);
 
+		processor->add_ring_busy_ns(uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - busy_t0).count()));
 		// The record was executed in place: only now may the producer reuse its words.
 		r += uint64_t(n) + 1;
 		read_count.store(r, std::memory_order_release);

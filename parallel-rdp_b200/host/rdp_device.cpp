@@ -7,6 +7,7 @@
 // Triangles and rectangles are *not* decoded here: their raw words go to the renderer and are decoded on the GPU.
 #include "rdp_device.hpp"
 #include "rdp_setup.cuh"
+#include <chrono>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -279,6 +280,9 @@ void CommandProcessor::enqueue_command_direct(unsigned num_words, const uint32_t
 	case OP_META_SET_QUIRKS:
 		quirks.u.words[0] = words[1];
 		break;
+	case OP_META_SCANOUT:
+		execute_scanout_request(reinterpret_cast<ScanoutRequest *>(uintptr_t(uint64_t(words[1]) | (uint64_t(words[2]) << 32))));
+		break;
 
 	case OP_TRI_FILL: case OP_TRI_FILL_Z: case OP_TRI_TEX: case OP_TRI_TEX_Z:
 	case OP_TRI_SHADE: case OP_TRI_SHADE_Z: case OP_TRI_SHADE_TEX: case OP_TRI_SHADE_TEX_Z:
@@ -351,9 +355,14 @@ void CommandProcessor::enqueue_command_stream(size_t num_words, const uint32_t *
 void CommandProcessor::execute_borrowed_stream(size_t num_words, const uint32_t *words)
 {
 	renderer.begin_borrowed_source(words, num_words);
+	// Only the first cache line of each command is read here (opcode, Y bounds, tile); commands are up to 176 bytes
+	// apart, which defeats the hardware streamer, so fetch a few commands ahead explicitly.
 	size_t pos = 0;
 	while (pos < num_words)
 	{
+		__builtin_prefetch(words + pos + 512);
+		__builtin_prefetch(words + pos + 512 + 16);
+		__builtin_prefetch(words + pos + 512 + 32);
 		const uint32_t len = command_length_words((words[pos] >> 24) & 63u);
 		if (pos + len > num_words)
 			break;
@@ -565,23 +574,85 @@ void CommandProcessor::scanout_async_buffer(VIScanoutBuffer &buffer, const Scano
 	rdpb_vi_read_output(device, buffer.pixels.data(), img.width, img.height, 1);
 }
 
-uint64_t CommandProcessor::scanout_async(void *rgba, size_t capacity_pixels, unsigned &width, unsigned &height, const ScanoutOptions &opts)
+struct CommandProcessor::ScanoutRequest
 {
-	ScanoutImage img = scanout(opts);
-	width = img ? img.width : 0;
-	height = img ? img.height : 0;
-	if (!img || size_t(width) * height > capacity_pixels)
+	VideoInterface::RegisterFile registers;
+	ScanoutOptions opts;
+	void *rgba;
+	size_t capacity_pixels;
+	unsigned *width, *height;
+	uint64_t fence;
+};
+
+uint64_t CommandProcessor::scanout_async(void *rgba, size_t capacity_pixels, unsigned *width, unsigned *height, const ScanoutOptions &opts)
+{
+	if (!is_supported)
 		return 0;
-	rdpb_vi_read_output(device, rgba, width, height, 0);
-	const uint64_t fence = (1ull << 63) | ++scanout_fence_counter; // own namespace, never collides with the timeline
-	rdpb_signal(device, fence);
+	auto *req = new ScanoutRequest;
+	vi.capture_registers(req->registers); // set_vi_register acts immediately on this thread: freeze what this frame saw
+	req->opts = opts;
+	req->rgba = rgba;
+	req->capacity_pixels = capacity_pixels;
+	req->width = width;
+	req->height = height;
+	req->fence = (1ull << 63) | ++scanout_fence_counter; // own namespace, never collides with the timeline
+
+	const uint64_t ptr = uint64_t(reinterpret_cast<uintptr_t>(req));
+	const uint32_t words[3] = { uint32_t(OP_META_SCANOUT) << 24, uint32_t(ptr), uint32_t(ptr >> 32) };
+	const uint64_t fence = req->fence;
+	enqueue_command_inner(3, words);
 	return fence;
+}
+
+void CommandProcessor::get_host_timing(double out[3]) const
+{
+	out[0] = 1e-9 * double(ring_busy_ns.load(std::memory_order_relaxed));
+	out[1] = 1e-9 * double(renderer.get_flush_ns());
+	out[2] = 1e-9 * double(scanout_ns.load(std::memory_order_relaxed));
+}
+
+void CommandProcessor::execute_scanout_request(ScanoutRequest *req)
+{
+	const auto t0 = std::chrono::steady_clock::now();
+	struct Timer
+	{
+		std::atomic<uint64_t> &acc;
+		std::chrono::steady_clock::time_point t0;
+		~Timer() { acc.fetch_add(uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count()), std::memory_order_relaxed); }
+	} timer{scanout_ns, t0};
+	std::lock_guard<std::mutex> holder{idle_lock};
+	renderer.flush_queues();
+	sync_host_rdram_to_device();
+	const ScanoutImage img = vi.scanout(req->opts, req->registers);
+	unsigned w = img ? img.width : 0, h = img ? img.height : 0;
+	if (!img || size_t(w) * h > req->capacity_pixels)
+		w = h = 0;
+	if (req->width)
+		*req->width = w;
+	if (req->height)
+		*req->height = h;
+	rdpb_vi_read_output_fenced(device, req->rgba, w, h, req->fence);
+	recorded_scanout_fence.store(req->fence & ~(1ull << 63), std::memory_order_release);
+	delete req;
 }
 
 void CommandProcessor::scanout_wait(uint64_t fence)
 {
-	if (fence && device)
-		rdpb_wait(device, fence);
+	if (!fence || !device)
+		return;
+	// The command thread records the fence in stream order; wait for it to get there, then for the GPU.
+	const uint64_t index = fence & ~(1ull << 63);
+	unsigned spins = 0;
+	while (recorded_scanout_fence.load(std::memory_order_acquire) < index)
+	{
+		if (single_threaded_processing)
+			break;
+		if (++spins < 2000)
+			std::this_thread::yield();
+		else
+			std::this_thread::sleep_for(std::chrono::microseconds(20));
+	}
+	rdpb_wait(device, fence);
 }
 
 void CommandProcessor::scanout_sync(std::vector<RGBA> &colors, unsigned &width, unsigned &height, const ScanoutOptions &opts)

@@ -112,7 +112,10 @@ public:
 	// Scan out and start an asynchronous copy of the RGBA8 image into caller memory (pinned memory makes it a true
 	// DMA); returns a fence for scanout_wait().  This is scanout_async_buffer's {buffer, fence} pair (reference
 	// rdp_device.cpp:1130-1158) with a caller-owned buffer.
-	uint64_t scanout_async(void *rgba, size_t capacity_pixels, unsigned &width, unsigned &height, const ScanoutOptions &opts = {});
+	// The call only snapshots the VI registers and queues the scan-out behind the commands enqueued so far: the
+	// command thread flushes, scans out, starts the copy and records the fence, so the caller is free to feed the
+	// next frame immediately.  *width / *height are written before the fence signals.
+	uint64_t scanout_async(void *rgba, size_t capacity_pixels, unsigned *width, unsigned *height, const ScanoutOptions &opts = {});
 	void scanout_wait(uint64_t fence);
 
 	void begin_vi_register_per_scanline(VideoInterface::PerScanlineRegisterFlags flags);
@@ -124,6 +127,10 @@ public:
 	rdpb_device *get_backend_device() { return device; }
 	uint64_t get_primitive_counter() const { return renderer.get_primitive_counter(); }
 	uint64_t get_pass_counter() const { return renderer.get_pass_counter(); }
+	// Seconds the command thread spent [0] executing ring records in total, [1] inside pass submission
+	// (Renderer::flush_queues), [2] inside queued scan-outs.  [0] - [1] - [2] is command parsing / pass recording.
+	void get_host_timing(double out[3]) const;
+	void add_ring_busy_ns(uint64_t ns) { ring_busy_ns.fetch_add(ns, std::memory_order_relaxed); }
 
 private:
 	rdpb_device *device = nullptr;
@@ -135,6 +142,10 @@ private:
 	size_t hidden_size = 0;
 	CommandProcessorFlags flags = 0;
 	uint64_t scanout_fence_counter = 0;
+	std::atomic<uint64_t> ring_busy_ns{0}, scanout_ns{0};
+	std::atomic<uint64_t> recorded_scanout_fence{0};
+	struct ScanoutRequest;
+	void execute_scanout_request(ScanoutRequest *req);
 	bool is_supported = false;
 	bool single_threaded_processing = true;
 

@@ -399,6 +399,7 @@ void Renderer::flush_queues()
 	if (num_prims == 0 && num_uploads == 0)
 		return;
 
+	const auto flush_t0 = std::chrono::steady_clock::now();
 	rdpb_pass_counts counts = {};
 	counts.num_words = num_words;
 	counts.num_prims = num_prims;
@@ -447,6 +448,7 @@ void Renderer::flush_queues()
 
 	rdpb_pass_end(device);
 	pass_counter++;
+	flush_ns += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - flush_t0).count());
 
 	base_primitive_index += num_prims;
 	pass_open = false;

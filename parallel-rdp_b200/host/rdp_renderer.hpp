@@ -9,6 +9,7 @@
 #include "rdp_types.h"
 #include "rdp_spec.h"
 #include <stddef.h>
+#include <chrono>
 #include <stdint.h>
 #include <vector>
 
@@ -105,6 +106,7 @@ public:
 
 	uint64_t get_primitive_counter() const { return base_primitive_index; }
 	uint64_t get_pass_counter() const { return pass_counter; }
+	uint64_t get_flush_ns() const { return flush_ns; }
 
 private:
 	rdpb_device *device = nullptr;
@@ -147,6 +149,7 @@ private:
 	void reset_summary();
 	uint32_t base_primitive_index = 0;
 	uint64_t pass_counter = 0;
+	uint64_t flush_ns = 0; // time spent submitting passes (written by the thread that drives the renderer)
 	bool tmem_snapshot_valid = false;
 
 	uint32_t gpu_dirty_lo = ~0u, gpu_dirty_hi = 0;

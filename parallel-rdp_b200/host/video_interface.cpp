@@ -23,7 +23,7 @@ void VideoInterface::init(rdpb_device *device_, size_t rdram_size_)
 
 void VideoInterface::set_vi_register(VIRegister reg, uint32_t value)
 {
-	vi_registers[unsigned(reg)] = value;
+	regfile.vi_registers[unsigned(reg)] = value;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -31,74 +31,74 @@ void VideoInterface::set_vi_register(VIRegister reg, uint32_t value)
 // ---------------------------------------------------------------------------------------------
 void VideoInterface::begin_vi_register_per_scanline(PerScanlineRegisterFlags flags)
 {
-	per_line_state.flags = flags;
-	per_line_state.h_start.latched_state = vi_registers[unsigned(VIRegister::HStart)];
-	per_line_state.x_scale.latched_state = vi_registers[unsigned(VIRegister::XScale)];
-	per_line_state.h_start.line_state[0] = per_line_state.h_start.latched_state;
-	per_line_state.x_scale.line_state[0] = per_line_state.x_scale.latched_state;
-	per_line_state.line = 0;
-	per_line_state.ended = false;
+	regfile.per_line_state.flags = flags;
+	regfile.per_line_state.h_start.latched_state = regfile.vi_registers[unsigned(VIRegister::HStart)];
+	regfile.per_line_state.x_scale.latched_state = regfile.vi_registers[unsigned(VIRegister::XScale)];
+	regfile.per_line_state.h_start.line_state[0] = regfile.per_line_state.h_start.latched_state;
+	regfile.per_line_state.x_scale.line_state[0] = regfile.per_line_state.x_scale.latched_state;
+	regfile.per_line_state.line = 0;
+	regfile.per_line_state.ended = false;
 }
 
 void VideoInterface::set_vi_register_for_scanline(PerScanlineRegisterBits reg, uint32_t value)
 {
-	if ((per_line_state.flags & reg) == 0)
+	if ((regfile.per_line_state.flags & reg) == 0)
 	{
 		fprintf(stderr, "[rdp-b200] VI register %u was not flagged in begin_vi_register_per_scanline, ignoring.\n", unsigned(reg));
 		return;
 	}
 	if (reg == PER_SCANLINE_HSTART_BIT)
-		per_line_state.h_start.latched_state = value;
+		regfile.per_line_state.h_start.latched_state = value;
 	else if (reg == PER_SCANLINE_XSCALE_BIT)
-		per_line_state.x_scale.latched_state = value;
+		regfile.per_line_state.x_scale.latched_state = value;
 }
 
 void VideoInterface::latch_vi_register_for_scanline(unsigned vi_line)
 {
 	vi_line = std::min(vi_line, VI_V_END_MAX - 1);
-	if (vi_line <= per_line_state.line)
+	if (vi_line <= regfile.per_line_state.line)
 	{
-		fprintf(stderr, "[rdp-b200] vi_line %u is not monotonically increasing (current %u), ignoring.\n", vi_line, per_line_state.line);
+		fprintf(stderr, "[rdp-b200] vi_line %u is not monotonically increasing (current %u), ignoring.\n", vi_line, regfile.per_line_state.line);
 		return;
 	}
 	// Lines up to the latch point keep the previous values.
-	const unsigned from = per_line_state.line;
+	const unsigned from = regfile.per_line_state.line;
 	for (unsigned l = from + 1; l < vi_line; l++)
 	{
-		per_line_state.h_start.line_state[l] = per_line_state.h_start.line_state[from];
-		per_line_state.x_scale.line_state[l] = per_line_state.x_scale.line_state[from];
+		regfile.per_line_state.h_start.line_state[l] = regfile.per_line_state.h_start.line_state[from];
+		regfile.per_line_state.x_scale.line_state[l] = regfile.per_line_state.x_scale.line_state[from];
 	}
-	per_line_state.h_start.line_state[vi_line] = per_line_state.h_start.latched_state;
-	per_line_state.x_scale.line_state[vi_line] = per_line_state.x_scale.latched_state;
-	per_line_state.line = vi_line;
+	regfile.per_line_state.h_start.line_state[vi_line] = regfile.per_line_state.h_start.latched_state;
+	regfile.per_line_state.x_scale.line_state[vi_line] = regfile.per_line_state.x_scale.latched_state;
+	regfile.per_line_state.line = vi_line;
 }
 
 void VideoInterface::end_vi_register_per_scanline()
 {
-	if (per_line_state.flags == 0 || per_line_state.ended)
+	if (regfile.per_line_state.flags == 0 || regfile.per_line_state.ended)
 		return;
-	const unsigned from = per_line_state.line;
+	const unsigned from = regfile.per_line_state.line;
 	for (unsigned l = from + 1; l < VI_V_END_MAX; l++)
 	{
-		per_line_state.h_start.line_state[l] = per_line_state.h_start.line_state[from];
-		per_line_state.x_scale.line_state[l] = per_line_state.x_scale.line_state[from];
+		regfile.per_line_state.h_start.line_state[l] = regfile.per_line_state.h_start.line_state[from];
+		regfile.per_line_state.x_scale.line_state[l] = regfile.per_line_state.x_scale.line_state[from];
 	}
-	per_line_state.ended = true;
+	regfile.per_line_state.ended = true;
 }
 
 void VideoInterface::clear_per_scanline_state()
 {
-	per_line_state.flags = 0;
-	per_line_state.ended = false;
+	regfile.per_line_state.flags = 0;
+	regfile.per_line_state.ended = false;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Register decode: VI registers -> bounding boxes + per-output-line sampling parameters
 // ---------------------------------------------------------------------------------------------
-ViRegs VideoInterface::decode_vi_registers(ViLine *lines) const
+ViRegs VideoInterface::decode_vi_registers(const RegisterFile &file, ViLine *lines) const
 {
 	ViRegs reg = {};
-	const auto R = [&](VIRegister r) { return vi_registers[unsigned(r)]; };
+	const auto R = [&](VIRegister r) { return file.vi_registers[unsigned(r)]; };
 
 	reg.status = R(VIRegister::Control);
 	reg.vi_width = int(R(VIRegister::Width) & 0xfff);
@@ -178,7 +178,7 @@ ViRegs VideoInterface::decode_vi_registers(ViLine *lines) const
 		}
 	};
 
-	if (degenerate_y || !per_line_state.ended)
+	if (degenerate_y || !file.per_line_state.ended)
 	{
 		ViLine info = {};
 		analyze(int((R(VIRegister::XScale) >> 16) & 0xfff), int(R(VIRegister::XScale) & 0xfff),
@@ -192,8 +192,8 @@ ViRegs VideoInterface::decode_vi_registers(ViLine *lines) const
 		for (int l = reg.v_start; l < reg.v_start + reg.v_res; l++)
 		{
 			const int effective = 2 * l + v_offset + int(reg.v_current_line == 0);
-			const uint32_t xs = per_line_state.x_scale.line_state[effective];
-			const uint32_t hs = per_line_state.h_start.line_state[effective];
+			const uint32_t xs = file.per_line_state.x_scale.line_state[effective];
+			const uint32_t hs = file.per_line_state.h_start.line_state[effective];
 			analyze(int((xs >> 16) & 0xfff), int(xs & 0xfff), int((hs >> 16) & 0x3ff), int(hs & 0x3ff), lines ? &lines[l] : nullptr);
 		}
 	}
@@ -224,12 +224,32 @@ static bool shifted_rect(int32_t *dst, int x, int y, int w, int h, int dx, int d
 	return true;
 }
 
+void VideoInterface::capture_registers(RegisterFile &out)
+{
+	if (regfile.per_line_state.flags != 0)
+		out = regfile;
+	else
+	{
+		// No raster effects programmed: the 14 registers are the whole story.
+		memcpy(out.vi_registers, regfile.vi_registers, sizeof(out.vi_registers));
+		out.per_line_state.flags = 0;
+		out.per_line_state.ended = false;
+	}
+	clear_per_scanline_state();
+}
+
 ScanoutImage VideoInterface::scanout(const ScanoutOptions &options)
+{
+	RegisterFile file;
+	capture_registers(file);
+	return scanout(options, file);
+}
+
+ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const RegisterFile &file)
 {
 	ScanoutImage result;
 	ViLine lines[VI_MAX_OUTPUT_SCANLINES];
-	ViRegs regs = decode_vi_registers(lines);
-	clear_per_scanline_state();
+	ViRegs regs = decode_vi_registers(file, lines);
 
 	if (regs.vi_offset == 0)
 	{

@@ -127,8 +127,31 @@ public:
 	};
 	using PerScanlineRegisterFlags = uint32_t;
 
+	// Everything the emulator writes: the register file is snapshotted per scan-out so a scan-out can execute
+	// later (on the command thread) while the emulator already programs the next frame's registers.
+	struct PerScanlineRegisterState
+	{
+		uint32_t latched_state;
+		uint32_t line_state[VI_V_END_MAX];
+	};
+	struct RegisterFile
+	{
+		uint32_t vi_registers[unsigned(VIRegister::Count)] = {};
+		struct
+		{
+			PerScanlineRegisterState h_start;
+			PerScanlineRegisterState x_scale;
+			PerScanlineRegisterFlags flags = 0;
+			unsigned line = 0;
+			bool ended = false;
+		} per_line_state;
+	};
+
 	void init(rdpb_device *device, size_t rdram_size);
 	void set_vi_register(VIRegister reg, uint32_t value);
+	// Copies the register file for one scan-out and resets the per-scanline latches (as scanout() always did).
+	void capture_registers(RegisterFile &out);
+	ScanoutImage scanout(const ScanoutOptions &options, const RegisterFile &file);
 	ScanoutImage scanout(const ScanoutOptions &options);
 
 	void begin_vi_register_per_scanline(PerScanlineRegisterFlags flags);
@@ -139,21 +162,7 @@ public:
 private:
 	rdpb_device *device = nullptr;
 	size_t rdram_size = 0;
-	uint32_t vi_registers[unsigned(VIRegister::Count)] = {};
-
-	struct PerScanlineRegisterState
-	{
-		uint32_t latched_state;
-		uint32_t line_state[VI_V_END_MAX];
-	};
-	struct
-	{
-		PerScanlineRegisterState h_start;
-		PerScanlineRegisterState x_scale;
-		PerScanlineRegisterFlags flags = 0;
-		unsigned line = 0;
-		bool ended = false;
-	} per_line_state;
+	RegisterFile regfile;
 
 	uint32_t frame_count = 0;
 	uint32_t last_valid_frame_count = 0;
@@ -161,7 +170,7 @@ private:
 	bool have_prev_scanout = false;
 	unsigned prev_width = 0, prev_height = 0;
 
-	rdpb::ViRegs decode_vi_registers(rdpb::ViLine *lines) const;
+	rdpb::ViRegs decode_vi_registers(const RegisterFile &file, rdpb::ViLine *lines) const;
 	void clear_per_scanline_state();
 };
 }

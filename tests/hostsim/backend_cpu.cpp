@@ -275,6 +275,10 @@ int rdpb_vi_read_output(rdpb_device *dev, void *dst, uint32_t width, uint32_t he
 	return 0;
 }
 
+int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, uint64_t)
+{
+	return rdpb_vi_read_output(dev, dst, width, height, 1);
+}
 int rdpb_signal(rdpb_device *, uint64_t) { return 0; }
 int rdpb_wait(rdpb_device *, uint64_t) { return 0; }
 int rdpb_sync(rdpb_device *) { return 0; }

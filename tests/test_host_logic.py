@@ -131,11 +131,10 @@ def _scanout_frames(mode, monkeypatch):
                 pix, w, h = p.scanout_sync(opts)
                 frames.append(pix.copy())
             else:
-                fence, w, h = p.scanout_async(opts, bufs[i])
-                assert fence != 0 and (w, h) == (640, 480)
-                fences.append((fence, w, h))
-        for i, (fence, w, h) in enumerate(fences):
-            p.scanout_wait(fence)
+                fences.append(p.scanout_async(opts, bufs[i]))
+        for i, ticket in enumerate(fences):
+            w, h = p.scanout_wait(ticket)
+            assert (w, h) == (640, 480)
             frames.append(bufs[i][: w * h].reshape(h, w).copy())
         return frames
     finally:
