@@ -126,6 +126,9 @@ int rdpb_record_mark(rdpb_device *dev);
 int rdpb_record_end(rdpb_device *dev);
 uint32_t rdpb_record_steps(rdpb_device *dev);
 int rdpb_replay_step(rdpb_device *dev, uint32_t step);
+/* Several independent streams on one GPU (BASELINE: "1/2/4/8 streams"): re-issue steps first .. first+count-1 of every
+ * device, round-robin per step, so the streams' kernels overlap on the SMs.  Step numbers wrap per device. */
+int rdpb_replay_interleaved(rdpb_device *const *devs, uint32_t num_devs, uint32_t first_step, uint32_t count);
 
 #ifdef __cplusplus
 }

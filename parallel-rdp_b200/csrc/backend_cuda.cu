@@ -1364,4 +1364,16 @@ int rdpb_replay_step(rdpb_device *dev, uint32_t step)
 			return -1;
 	return 0;
 }
+
+int rdpb_replay_interleaved(rdpb_device *const *devs, uint32_t num_devs, uint32_t first_step, uint32_t count)
+{
+	for (uint32_t s = first_step; s < first_step + count; s++)
+		for (uint32_t d = 0; d < num_devs; d++)
+		{
+			const uint32_t steps = rdpb_record_steps(devs[d]);
+			if (!steps || rdpb_replay_step(devs[d], s % steps) != 0)
+				return -1;
+		}
+	return 0;
+}
 }

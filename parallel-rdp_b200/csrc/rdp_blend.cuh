@@ -355,6 +355,22 @@ RDP_HD DepthResult depth_test(int z, int dz, int dz_compressed, int mem_depth, i
 	return r;
 }
 
+// The depth test exactly as depth_blend_pixel will run it, evaluated before texturing (see EarlyDepth).
+RDP_HD bool depth_early_reject(int z, const PrimSetup &p, const EarlyDepth &e, int coverage_count, uint32_t bf, int z_mode)
+{
+	int coverage = coverage_count;
+	const DepthResult d = depth_test(z, p.dz, p.dz_compressed, e.mem_depth, e.mem_dz, coverage, e.mem_coverage, bf, z_mode);
+	return !d.pass;
+}
+
+// Coverage the blender and the depth test see as "memory coverage": memory_interfacing.h:501-520
+RDP_HD int memory_coverage_bits(const FbView &fb, const PixelState &px, uint32_t bf)
+{
+	if (fb.fmt == FB_I4 || fb.fmt == FB_I8)
+		return 0xe0;
+	return (bf & BF_IMAGE_READ) ? (px.a & 0xe0) : 0xe0;
+}
+
 struct BlendInputs
 {
 	int pr, pg, pb, pa;     // pixel colour (combiner output, or first blender cycle's output)
@@ -471,16 +487,15 @@ RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup 
                               const M &m, const Shaded &sh)
 {
 	const uint32_t bf = m.bf;
-	const bool image_read = (bf & BF_IMAGE_READ) != 0;
 	int coverage = sh.coverage;
 
 	// Decode what the blender sees as "memory colour".
 	BlendInputs in;
-	int mem_cvg_bits = image_read ? (px.a & 0xe0) : 0xe0;
+	const int mem_cvg_bits = memory_coverage_bits(fb, px, bf);
 	switch (fb.fmt)
 	{
-	case FB_I4: in.mr = in.mg = in.mb = 0; mem_cvg_bits = 0xe0; break;
-	case FB_I8: in.mr = in.mg = in.mb = px.r; mem_cvg_bits = 0xe0; break;
+	case FB_I4: in.mr = in.mg = in.mb = 0; break;
+	case FB_I8: in.mr = in.mg = in.mb = px.r; break;
 	case FB_RGBA5551: in.mr = px.r & 0xf8; in.mg = px.g & 0xf8; in.mb = px.b & 0xf8; break;
 	case FB_IA88: in.mr = in.mg = in.mb = px.r; break;
 	default: in.mr = px.r; in.mg = px.g; in.mb = px.b; break;
@@ -547,8 +562,13 @@ RDP_HD bool process_pixel_span(const ShadeContext &ctx, const FbView &fb, PixelS
 	StaticModes<S> m;
 	resolve_modes<S>(st, m);
 	Shaded sh;
-	if (!shade_pixel<S>(ctx, x, y, prim, p, sp, st, m, sh))
-		return false;
+	EarlyDepth early;
+	early.mem_depth = px.depth;
+	early.mem_dz = px.dz;
+	early.mem_coverage = memory_coverage_bits(fb, px, m.bf) >> 5;
+	const int shaded = shade_pixel<S>(ctx, x, y, prim, p, sp, st, m, early, sh);
+	if (shaded != 1)
+		return shaded == 2; // a depth-rejected fragment still counts as shaded for the Mpix/s metric (the reference shades it)
 	if (sh.kind == 2)
 		copy_pixel(fb, px, sh.raw);
 	else

@@ -40,6 +40,15 @@ struct Shaded
 	int kind;        // 0 = normal, 1 = fill, 2 = copy
 };
 
+// What the pixel currently holds in the depth buffer, handed to shade_pixel so that a fragment the depth test is
+// going to reject skips texturing and the combiner (the result is identical: a rejected fragment writes nothing;
+// depth_test.h:41-144 only needs Z, delta-Z and the coverage count, none of which depend on colour unless coverage
+// is modulated by alpha, in which case the early test is not attempted).
+struct EarlyDepth
+{
+	int mem_depth, mem_dz, mem_coverage;
+};
+
 // Read-only view of everything a pass's pixels consume.
 struct ShadeContext
 {
@@ -1004,8 +1013,12 @@ RDP_HD void dither_coefficients(int x, int y, int mode_rgb, int mode_alpha, uint
 // The caller has already resolved the primitive, its span for line y (valid) and its state; fill-mode states never
 // get here (process_pixel_primitive handles them).  `m` holds the state's static modes, literal under a Spec.
 template <class S>
-RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_index, const PrimSetup &p, const Span &sp,
-                        const PassState &st, const StaticModes<S> &m, Shaded &out)
+RDP_HD bool depth_early_reject(int z, const PrimSetup &p, const EarlyDepth &e, int coverage_count, uint32_t bf, int z_mode);
+
+// Returns 0: not shaded (no coverage / alpha test), 1: shaded, `out` valid, 2: rejected by the early depth test.
+template <class S>
+RDP_HD int shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_index, const PrimSetup &p, const Span &sp,
+                       const PassState &st, const StaticModes<S> &m, const EarlyDepth &early, Shaded &out)
 {
 	const uint32_t rf = m.rf;
 	const uint8_t *tmem = ctx.tmem + size_t(p.tmem_instance) * kTmemBytes;
@@ -1019,7 +1032,7 @@ RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 	if (rf & RF_COPY)
 	{
 		if (x < sp.start_x || x > sp.end_x)
-			return false;
+			return 0;
 
 		int dx = flip ? (x - sp.start_x) : (sp.end_x - x);
 		int dx_mask, dx_shift;
@@ -1046,21 +1059,25 @@ RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 		out.kind = 2;
 		const uint32_t fb_bytes = ctx.fb_fmt == FB_I4 ? 0u : (ctx.fb_fmt == FB_I8 ? 1u : (ctx.fb_fmt == FB_RGBA8888 ? 4u : 2u));
 		if ((rf & RF_ALPHA_TEST) && fb_bytes == 2 && (texel & 1) == 0)
-			return false;
-		return true;
+			return 0;
+		return 1;
 	}
 
 	int coverage = compute_coverage(sp, x);
 	if (coverage == 0)
-		return false;
+		return 0;
 	int coverage_count = pop_count(uint32_t(coverage));
 	const bool aa = (rf & RF_AA) != 0;
 	if (!aa && (coverage & 1) == 0)
-		return false;
+		return 0;
 
 	const int dx = x - sp.base_x;
 	const int direction = flip ? 1 : -1;
 	const bool uses_lod = (rf & RF_USES_LOD) != 0;
+
+	const int z = interpolate_depth(sp, p, dx, coverage);
+	if ((m.bf & BF_Z_COMPARE) && !(rf & RF_CVG_TIMES_ALPHA) && depth_early_reject(z, p, early, coverage_count, m.bf, m.z_mode()))
+		return 2;
 
 	CombinerRegs regs;
 	regs.shade = interpolate_shade(sp, p, dx, coverage);
@@ -1092,8 +1109,6 @@ RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 			divide_st(perspective, ys >> 16, yt >> 16, yw >> 16, s_dy, t_dy, persp_overflow);
 		}
 	}
-	const int z = interpolate_depth(sp, p, dx, coverage);
-
 	uint32_t tile0 = uint32_t(p.tile) & 7u;
 	uint32_t tile1 = (tile0 + 1u) & 7u;
 	const uint32_t max_level = uint32_t(p.tile) >> 3;
@@ -1165,13 +1180,13 @@ RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 	}
 
 	if (aa && coverage_count == 0)
-		return false;
+		return 0;
 
 	if (rf & RF_ALPHA_TEST)
 	{
 		const int threshold = (rf & RF_ALPHA_TEST_DITHER) ? int(noise & 0xffu) : int(st.blend_color[3]);
 		if (alpha_ref < threshold)
-			return false;
+			return 0;
 	}
 
 	out.r = combined.x & 0xff;
@@ -1183,6 +1198,6 @@ RDP_HD bool shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 	out.coverage = coverage_count;
 	out.shade_alpha = imin(regs.shade.w + alpha_dith, 0xff);
 	out.kind = 0;
-	return true;
+	return 1;
 }
 }

@@ -306,4 +306,5 @@ int rdpb_record_mark(rdpb_device *) { return -1; }
 int rdpb_record_end(rdpb_device *) { return -1; }
 uint32_t rdpb_record_steps(rdpb_device *) { return 0; }
 int rdpb_replay_step(rdpb_device *, uint32_t) { return -1; }
+int rdpb_replay_interleaved(rdpb_device *const *, uint32_t, uint32_t, uint32_t) { return -1; }
 }
