@@ -268,11 +268,250 @@ struct TileWalker
 	}
 };
 
-template <class S>
-__global__ void __launch_bounds__(kTileWarpsPerBlock * 32, S::min_blocks_per_sm) k_tiles(PassBuffers b, FbInfo fb)
+// ---- deferred tile walker ------------------------------------------------------------------------------------
+// Same tile / list / mask-phase structure as TileWalker, but the fragments (pixel, primitive) of up to 32 list
+// entries are processed in four phases instead of one primitive at a time (rdp_blend.cuh, defer_*):
+//
+//   enumerate  every fragment of the batch gets a slot; slots are ordered by primitive, then pixel
+//   A          lane k <-> slot k: coverage mask + Z                      -- full lanes whatever the triangle shapes
+//   B          lane p <-> pixel p walks its own fragments in order: depth test, Z / coverage update
+//   compact    surviving slots are packed (warp ballot prefix)
+//   C          lane k <-> survivor k: texture + combiner                 -- full lanes, and nothing hidden is shaded
+//   D          lane p <-> pixel p walks its survivors in order: blender against the running memory colour
+//
+// The in-order walker runs ~11 of 32 lanes through texturing on the small triangles of a 3-D scene (a triangle
+// covers a third of an 8x4 tile on average); here the expensive phases A and C run converged over dense slots and
+// only the two cheap ordered phases B and D depend on how many fragments one pixel has.
+constexpr uint32_t kDeferCapacity = 256; // fragment slots per batch (>= 32: one list entry always fits)
+
+struct alignas(16) DeferWarp
 {
-	__shared__ uint16_t s_list[kTileWarpsPerBlock][kTileListCapacity];
-	uint16_t *list = s_list[threadIdx.x >> 5];
+	uint2 result[kDeferCapacity];  // C -> D: packed shaded colour of a slot
+	uint32_t cand[kDeferCapacity]; // A -> B: candidate word; B -> C, D: survivor record
+	uint32_t desc[kDeferCapacity]; // slot -> entry << 5 | pixel; after compaction: survivor -> slot << 16 | entry << 5 | pixel
+	uint32_t pixmask[32], base[32], prim[32], span_base[32], ids[32], lines[32], dzw[32]; // per list entry of the chunk
+	uint16_t list[kTileListCapacity];
+};
+
+template <class S>
+struct DeferredWalker
+{
+	const PassBuffers &b;
+	const FbInfo &fb;
+	const ShadeContext &ctx;
+	const FbView &view;
+	PixelState &px;
+	DeferWarp &w;
+	uint32_t lane;
+	int x0, y0, x, y;
+	uint32_t inside_mask;
+	uint32_t shaded;
+
+	__device__ __forceinline__ uint32_t slot_of(uint32_t entry, uint32_t lt) const
+	{
+		return w.base[entry] + uint32_t(__popc(w.pixmask[entry] & lt));
+	}
+
+	__device__ __forceinline__ void run(const uint16_t *list, uint32_t n)
+	{
+		const uint32_t lt = (1u << lane) - 1u;
+		for (uint32_t c = 0; c < n; c += 32u)
+		{
+			// ---- mask phase: lane j <-> list[c + j] (as TileWalker) ----
+			uint4 hdr = make_uint4(0u, 0u, 0u, 0u);
+			uint32_t pixmask = 0, my_prim = 0;
+			if (c + lane < n)
+			{
+				my_prim = list[c + lane];
+				const PrimSetup *pp = b.prims + my_prim;
+				hdr = *reinterpret_cast<const uint4 *>(&pp->span_base);
+				const int line_lo = int(int16_t(hdr.z & 0xffffu)), line_hi = int(int16_t(hdr.z >> 16));
+#pragma unroll
+				for (int r = 0; r < int(kTileH); r++)
+				{
+					const int yy = y0 + r;
+					if (yy < line_lo || yy > line_hi)
+						continue;
+					const Span *sp = b.spans + (hdr.x + uint32_t(yy - line_lo));
+					const uint2 sh = *reinterpret_cast<const uint2 *>(&sp->start_x);
+					if ((sh.y >> 16) == 0u) // !valid
+						continue;
+					const int lo = max(int(int16_t(sh.x & 0xffffu)) - x0, 0);
+					const int hi = min(int(int16_t(sh.x >> 16)) - x0, int(kTileW) - 1);
+					if (lo > hi)
+						continue;
+					pixmask |= (((2u << hi) - 1u) & ~((1u << lo) - 1u)) << (r * int(kTileW));
+					prefetch_l1(sp);
+				}
+				pixmask &= inside_mask;
+				if (pixmask)
+				{
+					prefetch_l1(pp);
+					prefetch_l1(reinterpret_cast<const uint8_t *>(pp) + 128);
+				}
+			}
+			w.pixmask[lane] = pixmask;
+			w.prim[lane] = my_prim;
+			w.span_base[lane] = hdr.x;
+			w.ids[lane] = hdr.y;
+			w.lines[lane] = hdr.z;
+			w.dzw[lane] = hdr.w;
+			uint32_t live = __ballot_sync(0xffffffffu, pixmask != 0u);
+			__syncwarp();
+
+			while (live)
+			{
+				// ---- enumerate: as many whole list entries as fit the slot arrays ----
+				uint32_t count = 0, mine = 0; // mine: entries with a fragment on this lane's pixel
+				while (live)
+				{
+					const uint32_t j = uint32_t(__ffs(int(live)) - 1);
+					const uint32_t pm = w.pixmask[j];
+					const uint32_t np = uint32_t(__popc(pm));
+					if (count + np > kDeferCapacity)
+						break;
+					live &= live - 1u;
+					if (lane == j)
+						w.base[j] = count;
+					if ((pm >> lane) & 1u)
+					{
+						w.desc[count + uint32_t(__popc(pm & lt))] = (j << 5) | lane;
+						mine |= 1u << j;
+					}
+					count += np;
+				}
+				__syncwarp();
+
+				// ---- A: coverage + Z of every fragment ----
+				for (uint32_t k = lane; k < count; k += 32u)
+				{
+					const uint32_t d = w.desc[k];
+					const uint32_t j = d >> 5, pix = d & 31u;
+					const int fx = x0 + int(pix & 7u), fy = y0 + int(pix >> 3);
+					const int line_lo = int(int16_t(w.lines[j] & 0xffffu));
+					const Span *gs = b.spans + (w.span_base[j] + uint32_t(fy - line_lo));
+					const PrimSetup *gp = b.prims + w.prim[j];
+					const uint4 *q = reinterpret_cast<const uint4 *>(gs);
+					const uint4 e = __ldg(q + 2), h = __ldg(q + 3);
+					Span sp;
+					sp.stzw[2] = __ldg(&gs->stzw[2]);
+					sp.xl[0] = uint16_t(e.x); sp.xl[1] = uint16_t(e.x >> 16); sp.xl[2] = uint16_t(e.y); sp.xl[3] = uint16_t(e.y >> 16);
+					sp.xr[0] = uint16_t(e.z); sp.xr[1] = uint16_t(e.z >> 16); sp.xr[2] = uint16_t(e.w); sp.xr[3] = uint16_t(e.w >> 16);
+					sp.start_x = int16_t(h.x); sp.end_x = int16_t(h.x >> 16);
+					sp.base_x = int(h.z);
+					PrimSetup p;
+					p.dstzw_dx[2] = __ldg(&gp->dstzw_dx[2]);
+					p.dstzw_dy[2] = __ldg(&gp->dstzw_dy[2]);
+					w.cand[k] = defer_candidate<S>(b.states[w.ids[j] & 0xffffu], p, sp, fx);
+				}
+				__syncwarp();
+
+				// ---- B: ordered depth stage, one pixel per lane ----
+				uint32_t surv = 0;
+				for (uint32_t t = mine; t; t &= t - 1u)
+				{
+					const uint32_t j = uint32_t(__ffs(int(t)) - 1);
+					const uint32_t k = slot_of(j, lt);
+					const uint32_t cand = w.cand[k];
+					if (!(cand & DC_VALID))
+						continue;
+					shaded++;
+					const PassState &st = b.states[w.ids[j] & 0xffffu];
+					if (cand & DC_FILL)
+					{
+						// The fill replaces the pixel: whatever earlier survivors would have blended is gone.
+						fill_pixel(view, px, st.fill_color);
+						for (uint32_t u = surv; u; u &= u - 1u)
+							w.cand[slot_of(uint32_t(__ffs(int(u)) - 1), lt)] = 0u;
+						surv = 0;
+						w.cand[k] = 0u;
+						continue;
+					}
+					const uint32_t dzw = w.dzw[j];
+					const uint32_t rec = defer_depth<S>(view, px, st, int(dzw & 0xffffu), int((dzw >> 16) & 0xffu), cand);
+					w.cand[k] = rec;
+					if (rec)
+						surv |= 1u << j;
+				}
+				__syncwarp();
+
+				// ---- compact the survivors (stable: still ordered by primitive, then pixel) ----
+				uint32_t n2 = 0;
+				for (uint32_t k0 = 0; k0 < count; k0 += 32u)
+				{
+					const uint32_t k = k0 + lane;
+					const bool alive = k < count && (w.cand[k] & DR_SURVIVE) != 0u;
+					const uint32_t d = alive ? w.desc[k] : 0u;
+					const uint32_t ballot = __ballot_sync(0xffffffffu, alive);
+					__syncwarp(); // every lane has read its descriptor before any slot below is overwritten
+					if (alive)
+						w.desc[n2 + uint32_t(__popc(ballot & lt))] = (k << 16) | d;
+					n2 += uint32_t(__popc(ballot));
+				}
+				__syncwarp();
+
+				// ---- C: shade the survivors ----
+				for (uint32_t k2 = lane; k2 < n2; k2 += 32u)
+				{
+					const uint32_t d = w.desc[k2];
+					const uint32_t k = d >> 16, j = (d >> 5) & 31u, pix = d & 31u;
+					const int fx = x0 + int(pix & 7u), fy = y0 + int(pix >> 3);
+					const uint32_t span_base = w.span_base[j], ids = w.ids[j], lines = w.lines[j], prim = w.prim[j];
+					const int line_lo = int(int16_t(lines & 0xffffu));
+					Span sp;
+					load_span(b.spans + (span_base + uint32_t(fy - line_lo)), sp);
+					PrimSetup p;
+					load_prim_for_shading(b.prims + prim, span_base, ids, lines, w.dzw[j], p);
+					uint32_t rx, ry;
+					defer_shade<S>(ctx, fx, fy, prim, p, sp, b.states[ids & 0xffffu], w.cand[k], rx, ry);
+					w.result[k] = make_uint2(rx, ry);
+				}
+				__syncwarp();
+
+				// ---- D: ordered blend stage, one pixel per lane ----
+				for (uint32_t t = surv; t; t &= t - 1u)
+				{
+					const uint32_t j = uint32_t(__ffs(int(t)) - 1);
+					const uint32_t k = slot_of(j, lt);
+					const uint2 res = w.result[k];
+					defer_blend<S>(view, px, b.states[w.ids[j] & 0xffffu], w.cand[k], res.x, res.y);
+				}
+				__syncwarp();
+			}
+		}
+	}
+};
+
+template <class S, bool DEFERRED>
+struct TileShared
+{
+	uint16_t list[kTileListCapacity];
+};
+template <class S>
+struct TileShared<S, true> : DeferWarp
+{
+};
+
+
+template <class S>
+__device__ __forceinline__ TileWalker<S> make_tile_walker(const PassBuffers &b, const FbInfo &fb, const ShadeContext &ctx, const FbView &view,
+                                                          PixelState &px, TileShared<S, false> &, uint32_t lane, int x0, int y0)
+{
+	return TileWalker<S>{ b, fb, ctx, view, px, lane, x0, y0, 0, 0, 0u, 0u };
+}
+template <class S>
+__device__ __forceinline__ DeferredWalker<S> make_tile_walker(const PassBuffers &b, const FbInfo &fb, const ShadeContext &ctx, const FbView &view,
+                                                              PixelState &px, TileShared<S, true> &sw, uint32_t lane, int x0, int y0)
+{
+	return DeferredWalker<S>{ b, fb, ctx, view, px, sw, lane, x0, y0, 0, 0, 0u, 0u };
+}
+
+template <class S, bool DEFERRED = false>
+__global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blocks_per_sm_deferred : S::min_blocks_per_sm) k_tiles(PassBuffers b, FbInfo fb)
+{
+	__shared__ TileShared<S, DEFERRED> s_warp[kTileWarpsPerBlock];
+	TileShared<S, DEFERRED> &sw = s_warp[threadIdx.x >> 5];
+	uint16_t *list = sw.list;
 
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t num_tiles = fb.tiles_x * fb.tiles_y;
@@ -310,7 +549,7 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, S::min_blocks_per_sm)
 		const uint32_t tx = tile % fb.tiles_x, ty = tile / fb.tiles_x;
 		FbView view;
 		PixelState px;
-		TileWalker<S> walk = { b, fb, ctx, view, px, lane, int(tx * kTileW), int(ty * kTileH), 0, 0, 0u, 0u };
+		auto walk = make_tile_walker<S>(b, fb, ctx, view, px, sw, lane, int(tx * kTileW), int(ty * kTileH));
 		walk.x = walk.x0 + int(lane & 7u);
 		walk.y = walk.y0 + int(lane >> 3);
 		walk.inside_mask = __ballot_sync(0xffffffffu, walk.x < int(fb.width) && walk.y < int(fb.height));
@@ -439,29 +678,41 @@ struct TileVariant
 	bool exact;
 	uint64_t comb_rgb;
 	uint32_t comb_alpha, blend_misc;
+	bool deferred; // runs the deferred pipeline: only for passes deferrable_pass() accepts
 	TileKernel kernel;
 };
 
-template <class S>
+template <class S, bool DEFERRED = false>
 static TileVariant make_variant(const char *name)
 {
+	static_assert(!DEFERRED || (S::rf_may & kRfNotDeferrable) == 0u || S::rf_may == ~0u,
+	              "a deferred feature class must exclude the states the deferred pipeline cannot run");
 	return { name, S::rf_may, S::rf_must, S::bf_may, S::bf_must, S::fmt_mask, S::tk_mask, S::exact, S::comb_rgb, S::comb_alpha,
-		     S::blend_misc, &k_tiles<S> };
+		     S::blend_misc, DEFERRED, &k_tiles<S, DEFERRED> };
 }
 
 #include "rdp_variants.inc"
 
 static_assert(sizeof(kTileVariants) / sizeof(kTileVariants[0]) <= 32, "grow rdpb_device::variant_blocks_per_sm");
 
-static const TileVariant *pick_tile_variant(const PassSummary *sum, uint32_t fmt)
+// Environment switches (read per pass, so tests can flip them): RDP_B200_FORCE_GENERIC pins the in-order uber-kernel,
+// RDP_B200_NO_DEFERRED keeps every pass on the in-order kernels, RDP_B200_FORCE_DEFERRED sends every deferrable
+// pass through the fully dynamic deferred kernel (how the conformance suites exercise it).
+static const TileVariant *pick_tile_variant(const PassSummary *sum, const FbInfo &fb)
 {
+	const uint32_t fmt = fb.fmt;
 	const size_t n = sizeof(kTileVariants) / sizeof(kTileVariants[0]);
 	if (!sum || getenv("RDP_B200_FORCE_GENERIC"))
 		return &kTileVariants[n - 1];
+	const bool deferrable = deferrable_pass(*sum, fb) && sum->num_shaded_states != 0 && !getenv("RDP_B200_NO_DEFERRED");
+	if (deferrable && getenv("RDP_B200_FORCE_DEFERRED"))
+		return &kTileVariants[n - 2];
 	for (size_t i = 0; i < n; i++)
 	{
 		const TileVariant &v = kTileVariants[i];
 		if (!(v.fmt_mask & (1u << fmt)))
+			continue;
+		if (v.deferred && !deferrable)
 			continue;
 		if (sum->num_shaded_states != 0)
 		{
@@ -1123,7 +1374,7 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 	op.kind = GOP_TILES;
 	op.fb = *static_cast<const FbInfo *>(fb_info);
 	const PassSummary *sum = static_cast<const PassSummary *>(summary);
-	op.variant = pick_tile_variant(sum, op.fb.fmt);
+	op.variant = pick_tile_variant(sum, op.fb);
 	dev->last_variant = op.variant;
 	if (dev->debug_summary && sum)
 		fprintf(stderr, "[rdp-b200] pass: prims=%u fmt=%u states=%u rf_or=%08x rf_and=%08x bf_or=%02x bf_and=%02x tk=%04x uniform=%u "

@@ -481,17 +481,34 @@ RDP_HD int blend_coverage(int coverage, int mem_coverage, bool blend_en, int mod
 	}
 }
 
-// memory_interfacing.h:488-571
+// memory_interfacing.h:488-571, split at the point where colour starts to matter:
+//   depth_stage  reads the pixel's depth, delta-Z and memory coverage; decides pass / blend enable / coverage
+//   blend_stage  reads the pixel's memory colour and the shaded colour; yields the dithered RGB to store
+// depth_blend_pixel runs both back to back (in-order path); the deferred tile kernel runs the depth stage of
+// every fragment of a batch first, shades only the survivors, and runs the blend stage afterwards.
+struct DepthStage
+{
+	DepthResult d;
+	int coverage;     // coverage count after the depth test (interpenetrating Z modulates it)
+	int mem_cvg_bits; // memory coverage in bits 7..5, as the blender's 2B input sees it
+};
+
+RDP_HD bool depth_stage(const FbView &fb, const PixelState &px, int z, int dz, int dz_compressed, int coverage, uint32_t bf,
+                        int z_mode, DepthStage &o)
+{
+	o.mem_cvg_bits = memory_coverage_bits(fb, px, bf);
+	o.coverage = coverage;
+	o.d = depth_test(z, dz, dz_compressed, px.depth, px.dz, o.coverage, o.mem_cvg_bits >> 5, bf, z_mode);
+	return o.d.pass && !((bf & BF_AA) && o.coverage == 0);
+}
+
 template <class M>
-RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup &p, const PassState &st,
-                              const M &m, const Shaded &sh)
+RDP_HD void blend_stage(const FbView &fb, const PixelState &px, const PassState &st, const M &m, const DepthResult &d,
+                        int mem_cvg_bits, int sr, int sg, int sb, int sa, int shade_alpha, int dither, int &r, int &g, int &b)
 {
 	const uint32_t bf = m.bf;
-	int coverage = sh.coverage;
-
 	// Decode what the blender sees as "memory colour".
 	BlendInputs in;
-	const int mem_cvg_bits = memory_coverage_bits(fb, px, bf);
 	switch (fb.fmt)
 	{
 	case FB_I4: in.mr = in.mg = in.mb = 0; break;
@@ -501,17 +518,9 @@ RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup 
 	default: in.mr = px.r; in.mg = px.g; in.mb = px.b; break;
 	}
 	in.ma = mem_cvg_bits;
-	const int mem_coverage = mem_cvg_bits >> 5;
+	in.pr = sr; in.pg = sg; in.pb = sb; in.pa = sa;
+	in.shade_alpha = shade_alpha;
 
-	const DepthResult d = depth_test(sh.z, p.dz, p.dz_compressed, px.depth, px.dz, coverage, mem_coverage, bf, m.z_mode());
-	const bool aa = (bf & BF_AA) != 0;
-	if (!d.pass || (aa && coverage == 0))
-		return;
-
-	in.pr = sh.r; in.pg = sh.g; in.pb = sh.b; in.pa = sh.a;
-	in.shade_alpha = sh.shade_alpha;
-
-	int r, g, b;
 	if (bf & BF_TWO_CYCLE)
 	{
 		blend_cycle(in, st, bf, m, 0, d, false, fb.blend_lut, r, g, b);
@@ -523,13 +532,29 @@ RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup 
 
 	if (bf & BF_DITHER)
 	{
-		r = dither_channel(r, sh.dither & 7);
-		g = dither_channel(g, (sh.dither >> 3) & 7);
-		b = dither_channel(b, (sh.dither >> 6) & 7);
+		r = dither_channel(r, dither & 7);
+		g = dither_channel(g, (dither >> 3) & 7);
+		b = dither_channel(b, (dither >> 6) & 7);
 	}
+	r &= 0xff;
+	g &= 0xff;
+	b &= 0xff;
+}
 
-	const int new_coverage = blend_coverage(coverage, mem_coverage, d.blend_en, m.cvg_mode());
-	write_color(fb, px, r & 0xff, g & 0xff, b & 0xff, new_coverage << 5);
+template <class M>
+RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup &p, const PassState &st,
+                              const M &m, const Shaded &sh)
+{
+	const uint32_t bf = m.bf;
+	DepthStage ds;
+	if (!depth_stage(fb, px, sh.z, p.dz, p.dz_compressed, sh.coverage, bf, m.z_mode(), ds))
+		return;
+
+	int r, g, b;
+	blend_stage(fb, px, st, m, ds.d, ds.mem_cvg_bits, sh.r, sh.g, sh.b, sh.a, sh.shade_alpha, sh.dither, r, g, b);
+
+	const int new_coverage = blend_coverage(ds.coverage, ds.mem_cvg_bits >> 5, ds.d.blend_en, m.cvg_mode());
+	write_color(fb, px, r, g, b, new_coverage << 5);
 
 	if (bf & BF_Z_UPDATE)
 	{
@@ -541,6 +566,116 @@ RDP_HD void depth_blend_pixel(const FbView &fb, PixelState &px, const PrimSetup 
 	}
 	else if (fb.alias)
 		alias_color_to_depth(fb, px);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deferred pipeline: the four per-item steps of the deferred tile kernel (backend_cuda.cu, k_tiles_deferred).
+//
+// A batch of (pixel, primitive) fragments of one tile is processed as
+//   A  candidate : coverage mask + interpolated Z of every fragment          (order-free, compacted over lanes)
+//   B  depth     : per pixel, in primitive order: depth test, Z / coverage update; survivors keep a record
+//   C  shade     : texture + combiner of the survivors only                   (order-free, compacted over lanes)
+//   D  blend     : per pixel, in primitive order: blender against the running memory colour
+// which is exact because depth_test / blend_coverage never read colour (depth_test.h:41-144, coverage.h:51-79) and
+// shading never reads the framebuffer.  Not valid for states whose coverage depends on the shaded alpha
+// (cvg_times_alpha), that can drop a fragment after shading (alpha test), for copy mode, or when the colour and
+// depth images alias; the host keeps such passes on the in-order kernel (kRfNotDeferrable).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kRfNotDeferrable = RF_COPY | RF_ALPHA_TEST | RF_CVG_TIMES_ALPHA;
+
+enum DeferBits : uint32_t
+{
+	// candidate word (phase A -> B)
+	DC_Z_MASK = 0x3ffffu,
+	DC_COV_SHIFT = 18, // 8-bit sub-sample mask
+	DC_VALID = 1u << 26,
+	DC_FILL = 1u << 27,
+	// survivor record (phase B -> C, D); bits 0..7 hold the sub-sample mask
+	DR_BLEND_EN = 1u << 8,
+	DR_CVG_WRAP = 1u << 9,
+	DR_SHIFT_A_SHIFT = 10, // 3 bits
+	DR_SHIFT_B_SHIFT = 13, // 3 bits
+	DR_MEM_CVG_SHIFT = 16, // 3 bits
+	DR_SURVIVE = 1u << 31,
+};
+
+// What phases A and C read of a primitive / span is a subset of the structs; callers fill only those fields.
+template <class S>
+RDP_HD uint32_t defer_candidate(const PassState &st, const PrimSetup &p, const Span &sp, int x)
+{
+	if (st.raster_flags & RF_FILL)
+		return (x >= sp.start_x && x <= sp.end_x) ? (DC_VALID | DC_FILL) : 0u;
+	StaticModes<S> m;
+	resolve_modes<S>(st, m);
+	const int coverage = shade_coverage(sp, x, m.rf);
+	if (coverage == 0)
+		return 0u;
+	const int z = interpolate_depth(sp, p, x - sp.base_x, coverage);
+	return uint32_t(z) | (uint32_t(coverage) << DC_COV_SHIFT) | DC_VALID;
+}
+
+// Returns the survivor record, 0 when the fragment is rejected.  Updates depth, delta-Z and coverage of the pixel.
+// Fill fragments never come here (the caller writes them with fill_pixel and forgets the pixel's earlier survivors).
+template <class S>
+RDP_HD uint32_t defer_depth(const FbView &fb, PixelState &px, const PassState &st, int dz, int dz_compressed, uint32_t cand)
+{
+	StaticModes<S> m;
+	resolve_modes<S>(st, m);
+	const uint32_t bf = m.bf;
+	const int z = int(cand & DC_Z_MASK);
+	const uint32_t cov8 = (cand >> DC_COV_SHIFT) & 0xffu;
+	DepthStage ds;
+	if (!depth_stage(fb, px, z, dz, dz_compressed, pop_count(cov8), bf, m.z_mode(), ds))
+		return 0u;
+
+	const int new_coverage = blend_coverage(ds.coverage, ds.mem_cvg_bits >> 5, ds.d.blend_en, m.cvg_mode());
+	if (fb.fmt != FB_I4)
+		px.a = new_coverage << 5;
+	px.color_dirty = true;
+	if (bf & BF_Z_UPDATE)
+	{
+		px.depth = z_compress(z);
+		px.dz = dz_compressed;
+		px.depth_dirty = true;
+	}
+	return DR_SURVIVE | cov8 | (ds.d.blend_en ? DR_BLEND_EN : 0u) | (ds.d.coverage_wrap ? DR_CVG_WRAP : 0u) |
+	       (uint32_t(ds.d.shift_a) << DR_SHIFT_A_SHIFT) | (uint32_t(ds.d.shift_b) << DR_SHIFT_B_SHIFT) |
+	       (uint32_t(ds.mem_cvg_bits >> 5) << DR_MEM_CVG_SHIFT);
+}
+
+// Shaded colour of a survivor, packed: x = r | g<<8 | b<<16 | a<<24, y = shade_alpha | rgb_dither<<8.
+template <class S>
+RDP_HD void defer_shade(const ShadeContext &ctx, int x, int y, uint32_t prim, const PrimSetup &p, const Span &sp,
+                        const PassState &st, uint32_t record, uint32_t &out_x, uint32_t &out_y)
+{
+	StaticModes<S> m;
+	resolve_modes<S>(st, m);
+	const int coverage = int(record & 0xffu);
+	int coverage_count = pop_count(uint32_t(coverage));
+	ShadedColor c;
+	shade_color<S>(ctx, x, y, prim, p, sp, st, m, coverage, coverage_count, c);
+	out_x = uint32_t(c.combined.x & 0xff) | (uint32_t(c.combined.y & 0xff) << 8) | (uint32_t(c.combined.z & 0xff) << 16) |
+	        (uint32_t(c.combined.w & 0xff) << 24);
+	out_y = uint32_t(c.shade_alpha & 0xff) | (uint32_t(c.rgb_dither & 0x1ff) << 8);
+}
+
+template <class S>
+RDP_HD void defer_blend(const FbView &fb, PixelState &px, const PassState &st, uint32_t record, uint32_t res_x, uint32_t res_y)
+{
+	StaticModes<S> m;
+	resolve_modes<S>(st, m);
+	DepthResult d;
+	d.pass = true;
+	d.blend_en = (record & DR_BLEND_EN) != 0;
+	d.coverage_wrap = (record & DR_CVG_WRAP) != 0;
+	d.shift_a = int((record >> DR_SHIFT_A_SHIFT) & 7u);
+	d.shift_b = int((record >> DR_SHIFT_B_SHIFT) & 7u);
+	int r, g, b;
+	blend_stage(fb, px, st, m, d, int((record >> DR_MEM_CVG_SHIFT) & 7u) << 5, int(res_x & 0xffu), int((res_x >> 8) & 0xffu),
+	            int((res_x >> 16) & 0xffu), int(res_x >> 24), int(res_y & 0xffu), int(res_y >> 8), r, g, b);
+	px.r = r;
+	px.g = g;
+	px.b = b;
 }
 
 // Walk one pixel through one binned primitive (shade, then fill / copy / depth-blend).

@@ -169,6 +169,108 @@ RDP_HD uint32_t pass_pixel_walk(const PassBuffers &b, const FbInfo &fb, const Fb
 	return shaded;
 }
 
+// The deferred pipeline (rdp_blend.cuh, defer_*) walked by a single pixel: batches of up to 32 binned primitives go
+// through candidate -> depth -> shade -> blend.  This is the scalar statement of what k_tiles_deferred does with
+// warp-wide compaction between the phases; the host simulator runs it so the phase split is checked against the
+// oracle without a GPU.  Only valid for passes deferrable_pass() accepts.
+template <class S>
+struct DeferredPixelWalk
+{
+	const PassBuffers &b;
+	const FbInfo &fb;
+	const FbView &view;
+	PixelState &px;
+	int x, y;
+	ShadeContext ctx;
+	uint32_t prim[32], record[32];
+	uint32_t count, shaded;
+
+	RDP_HD void flush()
+	{
+		uint32_t rx[32], ry[32];
+		for (uint32_t i = 0; i < count; i++) // phase C
+		{
+			const PrimSetup &p = b.prims[prim[i]];
+			const Span &sp = b.spans[p.span_base + uint32_t(y - p.line_lo)];
+			defer_shade<S>(ctx, x, y, prim[i], p, sp, b.states[p.state_id], record[i], rx[i], ry[i]);
+		}
+		for (uint32_t i = 0; i < count; i++) // phase D
+			defer_blend<S>(view, px, b.states[b.prims[prim[i]].state_id], record[i], rx[i], ry[i]);
+		count = 0;
+	}
+
+	RDP_HD void add(uint32_t index)
+	{
+		const PrimSetup &p = b.prims[index];
+		if (y < p.line_lo || y > p.line_hi)
+			return;
+		const Span &sp = b.spans[p.span_base + uint32_t(y - p.line_lo)];
+		if (!sp.valid)
+			return;
+		const PassState &st = b.states[p.state_id];
+		const uint32_t cand = defer_candidate<S>(st, p, sp, x); // phase A
+		if (!(cand & DC_VALID))
+			return;
+		shaded++;
+		if (cand & DC_FILL) // phase B
+		{
+			fill_pixel(view, px, st.fill_color);
+			count = 0; // the fill overwrites whatever the earlier survivors would have blended
+			return;
+		}
+		const uint32_t rec = defer_depth<S>(view, px, st, p.dz, p.dz_compressed, cand);
+		if (!rec)
+			return;
+		prim[count] = index;
+		record[count] = rec;
+		count++;
+	}
+};
+
+template <class S>
+RDP_HD uint32_t pass_pixel_walk_deferred(const PassBuffers &b, const FbInfo &fb, const FbView &view, PixelState &px, int x,
+                                         int y, uint32_t tile)
+{
+	DeferredPixelWalk<S> w = { b, fb, view, px, x, y };
+	w.ctx.prims = b.prims;
+	w.ctx.states = b.states;
+	w.ctx.spans = b.spans;
+	w.ctx.tmem = b.tmem_instances;
+	w.ctx.fb_fmt = view.fmt;
+	w.ctx.base_prim_index = fb.base_prim_index;
+	w.count = 0;
+	w.shaded = 0;
+
+	const uint32_t *coarse = b.coarse_mask + size_t(tile) * fb.coarse_stride;
+	const uint32_t *fine = b.fine_mask + size_t(tile) * fb.mask_stride;
+	for (uint32_t cw = 0; cw < fb.coarse_stride; cw++)
+	{
+		uint32_t cbits = coarse[cw];
+		while (cbits)
+		{
+			const int g = find_lsb(cbits);
+			cbits &= cbits - 1u;
+			const uint32_t group = cw * 32u + uint32_t(g);
+			uint32_t bits = fine[group];
+			while (bits)
+			{
+				const int i = find_lsb(bits);
+				bits &= bits - 1u;
+				w.add(group * 32u + uint32_t(i));
+			}
+			w.flush(); // one fine-mask word = one batch of up to 32 primitives
+		}
+	}
+	return w.shaded;
+}
+
+// A pass can take the deferred pipeline when no state in it ties coverage or survival to the shaded colour and
+// the colour and depth images are distinct.
+RDP_HD bool deferrable_pass(const PassSummary &sum, const FbInfo &fb)
+{
+	return (sum.rf_or & kRfNotDeferrable) == 0u && fb.color_addr != fb.depth_addr;
+}
+
 // Zero the mask words of one tile after its pixels are done, so the next pass starts from clean masks.
 RDP_HD void pass_tile_clear_masks(const PassBuffers &b, const FbInfo &fb, uint32_t tile)
 {

@@ -1015,10 +1015,22 @@ RDP_HD void dither_coefficients(int x, int y, int mode_rgb, int mode_alpha, uint
 template <class S>
 RDP_HD bool depth_early_reject(int z, const PrimSetup &p, const EarlyDepth &e, int coverage_count, uint32_t bf, int z_mode);
 
-// Returns 0: not shaded (no coverage / alpha test), 1: shaded, `out` valid, 2: rejected by the early depth test.
+// Colour half of shade_pixel: everything after coverage and depth -- shade interpolation, texture coordinates,
+// LOD, TMEM sampling, both combiner cycles, dither coefficients.  `coverage` is the 8-bit sub-sample mask of the
+// pixel (non-zero); `coverage_count` enters as its population count and leaves modulated by alpha when the state
+// asks for it.  Shared by the in-order path (shade_pixel) and the deferred tile kernel's compacted shade phase.
+struct ShadedColor
+{
+	Vec4 combined;   // combiner output, alpha already merged with coverage / dither
+	int alpha_ref;   // what the alpha test compares
+	int rgb_dither;  // 9-bit rgb dither pattern
+	int shade_alpha; // shade alpha + alpha dither (blender input 1B)
+	uint32_t noise;  // noise word the alpha-test dither reads
+};
+
 template <class S>
-RDP_HD int shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_index, const PrimSetup &p, const Span &sp,
-                       const PassState &st, const StaticModes<S> &m, const EarlyDepth &early, Shaded &out)
+RDP_HD void shade_color(const ShadeContext &ctx, int x, int y, uint32_t prim_index, const PrimSetup &p, const Span &sp,
+                        const PassState &st, const StaticModes<S> &m, int coverage, int &coverage_count, ShadedColor &out)
 {
 	const uint32_t rf = m.rf;
 	const uint8_t *tmem = ctx.tmem + size_t(p.tmem_instance) * kTmemBytes;
@@ -1029,55 +1041,9 @@ RDP_HD int shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_inde
 	if (rf & RF_NOISE)
 		noise = noise_hash(uint32_t(x), uint32_t(y), prim_index + ctx.base_prim_index);
 
-	if (rf & RF_COPY)
-	{
-		if (x < sp.start_x || x > sp.end_x)
-			return 0;
-
-		int dx = flip ? (x - sp.start_x) : (sp.end_x - x);
-		int dx_mask, dx_shift;
-		switch (ctx.fb_fmt)
-		{
-		case FB_I4: dx_mask = 0; dx_shift = 0; break;
-		case FB_I8: dx_mask = ~7; dx_shift = 3; break;
-		case FB_RGBA8888: dx_mask = 0; dx_shift = 1; break; // copy into 32bpp is undefined on hardware
-		default: dx_mask = ~3; dx_shift = 2; break;
-		}
-		const int snapped_dx = dx & dx_mask;
-		const int s_offset = dx - snapped_dx;
-		const int lerp_dx = (dx >> dx_shift) * (flip ? 1 : -1);
-		const int s = int(uint32_t(sp.stzw[0]) + uint32_t(p.dstzw_dx[0] & ~0x1f) * uint32_t(lerp_dx)) >> 16;
-		const int t = int(uint32_t(sp.stzw[1]) + uint32_t(p.dstzw_dx[1] & ~0x1f) * uint32_t(lerp_dx)) >> 16;
-		const int w = int(uint32_t(sp.stzw[3]) + uint32_t(p.dstzw_dx[3] & ~0x1f) * uint32_t(lerp_dx)) >> 16;
-		int ps, pt;
-		bool ovf = false;
-		divide_st(perspective, s, t, w, ps, pt, ovf);
-
-		const TileDesc &tile = st.tiles[p.tile & 7u];
-		const int texel = copy_fetch(tile, tmem, ps, pt, s_offset, (rf & RF_TLUT) != 0, ctx.fb_fmt);
-		out.raw = uint32_t(texel);
-		out.kind = 2;
-		const uint32_t fb_bytes = ctx.fb_fmt == FB_I4 ? 0u : (ctx.fb_fmt == FB_I8 ? 1u : (ctx.fb_fmt == FB_RGBA8888 ? 4u : 2u));
-		if ((rf & RF_ALPHA_TEST) && fb_bytes == 2 && (texel & 1) == 0)
-			return 0;
-		return 1;
-	}
-
-	int coverage = compute_coverage(sp, x);
-	if (coverage == 0)
-		return 0;
-	int coverage_count = pop_count(uint32_t(coverage));
-	const bool aa = (rf & RF_AA) != 0;
-	if (!aa && (coverage & 1) == 0)
-		return 0;
-
 	const int dx = x - sp.base_x;
 	const int direction = flip ? 1 : -1;
 	const bool uses_lod = (rf & RF_USES_LOD) != 0;
-
-	const int z = interpolate_depth(sp, p, dx, coverage);
-	if ((m.bf & BF_Z_COMPARE) && !(rf & RF_CVG_TIMES_ALPHA) && depth_early_reject(z, p, early, coverage_count, m.bf, m.z_mode()))
-		return 2;
 
 	CombinerRegs regs;
 	regs.shade = interpolate_shade(sp, p, dx, coverage);
@@ -1152,14 +1118,12 @@ RDP_HD int shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_inde
 			regs.texel1 = sample_texture<S::tk_mask>(st.tiles[tile1], tmem, s, t, rf, bilerp1, convert_one, st.convert, regs.texel0);
 	}
 
-	int rgb_dith, alpha_dith;
-	dither_coefficients(x, (rf & RF_INTERLACE) ? (y >> 1) : y, m.dither_rgb(), m.dither_alpha(), noise, rgb_dith, alpha_dith);
+	int alpha_dith;
+	dither_coefficients(x, (rf & RF_INTERLACE) ? (y >> 1) : y, m.dither_rgb(), m.dither_alpha(), noise, out.rgb_dither, alpha_dith);
 
-	Vec4 combined;
-	int alpha_ref;
 	if (rf & RF_TWO_CYCLE)
 	{
-		regs.combined = combiner_first_cycle(regs, st, m, alpha_dith, coverage_count, rf, alpha_ref);
+		regs.combined = combiner_first_cycle(regs, st, m, alpha_dith, coverage_count, rf, out.alpha_ref);
 		// Pipelining: TEXEL1 is seen as TEXEL0 by the second cycle and vice versa.
 		const Vec4 tmp = regs.texel0;
 		regs.texel0 = regs.texel1;
@@ -1171,32 +1135,101 @@ RDP_HD int shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_inde
 			// NB: the reseed also changes the noise seen by the alpha-test dither below (noise.h keeps one seed).
 			noise = n2;
 		}
-		combined = combiner_last_cycle(regs, st, m, alpha_dith, coverage_count, rf);
+		out.combined = combiner_last_cycle(regs, st, m, alpha_dith, coverage_count, rf);
 	}
 	else
 	{
-		combined = combiner_last_cycle(regs, st, m, alpha_dith, coverage_count, rf);
-		alpha_ref = combined.w;
+		out.combined = combiner_last_cycle(regs, st, m, alpha_dith, coverage_count, rf);
+		out.alpha_ref = out.combined.w;
+	}
+	out.shade_alpha = imin(regs.shade.w + alpha_dith, 0xff);
+	out.noise = noise;
+}
+
+// Coverage half: the 8-bit sub-sample mask of pixel x on this span, 0 when the primitive does not shade it
+// (no sample covered, or -- without AA -- the first sample not covered).
+RDP_HD int shade_coverage(const Span &sp, int x, uint32_t rf)
+{
+	const int coverage = compute_coverage(sp, x);
+	if (!(rf & RF_AA) && (coverage & 1) == 0)
+		return 0;
+	return coverage;
+}
+
+// Returns 0: not shaded (no coverage / alpha test), 1: shaded, `out` valid, 2: rejected by the early depth test.
+template <class S>
+RDP_HD int shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_index, const PrimSetup &p, const Span &sp,
+                       const PassState &st, const StaticModes<S> &m, const EarlyDepth &early, Shaded &out)
+{
+	const uint32_t rf = m.rf;
+
+	if (rf & RF_COPY)
+	{
+		const uint8_t *tmem = ctx.tmem + size_t(p.tmem_instance) * kTmemBytes;
+		const bool flip = (p.flags & SF_FLIP) != 0;
+		const bool perspective = (rf & RF_PERSPECTIVE) != 0;
+		if (x < sp.start_x || x > sp.end_x)
+			return 0;
+
+		int dx = flip ? (x - sp.start_x) : (sp.end_x - x);
+		int dx_mask, dx_shift;
+		switch (ctx.fb_fmt)
+		{
+		case FB_I4: dx_mask = 0; dx_shift = 0; break;
+		case FB_I8: dx_mask = ~7; dx_shift = 3; break;
+		case FB_RGBA8888: dx_mask = 0; dx_shift = 1; break; // copy into 32bpp is undefined on hardware
+		default: dx_mask = ~3; dx_shift = 2; break;
+		}
+		const int snapped_dx = dx & dx_mask;
+		const int s_offset = dx - snapped_dx;
+		const int lerp_dx = (dx >> dx_shift) * (flip ? 1 : -1);
+		const int s = int(uint32_t(sp.stzw[0]) + uint32_t(p.dstzw_dx[0] & ~0x1f) * uint32_t(lerp_dx)) >> 16;
+		const int t = int(uint32_t(sp.stzw[1]) + uint32_t(p.dstzw_dx[1] & ~0x1f) * uint32_t(lerp_dx)) >> 16;
+		const int w = int(uint32_t(sp.stzw[3]) + uint32_t(p.dstzw_dx[3] & ~0x1f) * uint32_t(lerp_dx)) >> 16;
+		int ps, pt;
+		bool ovf = false;
+		divide_st(perspective, s, t, w, ps, pt, ovf);
+
+		const TileDesc &tile = st.tiles[p.tile & 7u];
+		const int texel = copy_fetch(tile, tmem, ps, pt, s_offset, (rf & RF_TLUT) != 0, ctx.fb_fmt);
+		out.raw = uint32_t(texel);
+		out.kind = 2;
+		const uint32_t fb_bytes = ctx.fb_fmt == FB_I4 ? 0u : (ctx.fb_fmt == FB_I8 ? 1u : (ctx.fb_fmt == FB_RGBA8888 ? 4u : 2u));
+		if ((rf & RF_ALPHA_TEST) && fb_bytes == 2 && (texel & 1) == 0)
+			return 0;
+		return 1;
 	}
 
-	if (aa && coverage_count == 0)
+	const int coverage = shade_coverage(sp, x, rf);
+	if (coverage == 0)
+		return 0;
+	int coverage_count = pop_count(uint32_t(coverage));
+
+	const int z = interpolate_depth(sp, p, x - sp.base_x, coverage);
+	if ((m.bf & BF_Z_COMPARE) && !(rf & RF_CVG_TIMES_ALPHA) && depth_early_reject(z, p, early, coverage_count, m.bf, m.z_mode()))
+		return 2;
+
+	ShadedColor c;
+	shade_color<S>(ctx, x, y, prim_index, p, sp, st, m, coverage, coverage_count, c);
+
+	if ((rf & RF_AA) && coverage_count == 0)
 		return 0;
 
 	if (rf & RF_ALPHA_TEST)
 	{
-		const int threshold = (rf & RF_ALPHA_TEST_DITHER) ? int(noise & 0xffu) : int(st.blend_color[3]);
-		if (alpha_ref < threshold)
+		const int threshold = (rf & RF_ALPHA_TEST_DITHER) ? int(c.noise & 0xffu) : int(st.blend_color[3]);
+		if (c.alpha_ref < threshold)
 			return 0;
 	}
 
-	out.r = combined.x & 0xff;
-	out.g = combined.y & 0xff;
-	out.b = combined.z & 0xff;
-	out.a = combined.w & 0xff;
+	out.r = c.combined.x & 0xff;
+	out.g = c.combined.y & 0xff;
+	out.b = c.combined.z & 0xff;
+	out.a = c.combined.w & 0xff;
 	out.z = z;
-	out.dither = rgb_dith;
+	out.dither = c.rgb_dither;
 	out.coverage = coverage_count;
-	out.shade_alpha = imin(regs.shade.w + alpha_dith, 0xff);
+	out.shade_alpha = c.shade_alpha;
 	out.kind = 0;
 	return 1;
 }

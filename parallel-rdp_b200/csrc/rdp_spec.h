@@ -104,6 +104,8 @@ struct Spec
 	// Resident 128-thread blocks per SM the tile kernel is compiled for: 8 (<= 64 registers) when the state is exact,
 	// 5 (<= 96 registers) for the feature classes and the uber-kernel.
 	static constexpr int min_blocks_per_sm = EXACT ? 8 : 5;
+	// The deferred tile kernel (k_tiles<S, true>) keeps ~5 KiB of fragment slots per warp in shared memory.
+	static constexpr int min_blocks_per_sm_deferred = EXACT ? 6 : 4;
 };
 
 // Fully dynamic: the uber-kernel fallback (ref shaders/ubershader.comp).

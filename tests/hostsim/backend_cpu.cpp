@@ -32,6 +32,8 @@ struct rdpb_device
 	std::vector<uint32_t> vi_stage[3];
 	std::vector<uint32_t> vi_out, vi_prev;
 	uint64_t launches = 0;
+	uint64_t deferred_passes = 0;
+	bool last_deferred = false;
 	unsigned long long counters[8] = {};
 	std::string error;
 
@@ -183,7 +185,7 @@ int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 	return 0;
 }
 
-const char *rdpb_last_tile_variant(rdpb_device *) { return "generic"; }
+const char *rdpb_last_tile_variant(rdpb_device *dev) { return dev->last_deferred ? "generic+deferred" : "generic"; }
 
 int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary)
 {
@@ -199,6 +201,12 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 		        sum->modes_uniform, (unsigned long long)sum->comb_rgb, sum->comb_alpha, sum->blend_misc);
 	}
 	PassBuffers b = dev->buffers();
+	// RDP_HOSTSIM_DEFERRED=1: eligible passes take the scalar statement of the deferred tile pipeline instead of
+	// the in-order walk (tests/test_hostsim_conformance.py runs the suites both ways).
+	const bool deferred = summary && getenv("RDP_HOSTSIM_DEFERRED") && deferrable_pass(*static_cast<const PassSummary *>(summary), fb);
+	dev->last_deferred = deferred;
+	if (deferred)
+		dev->deferred_passes++;
 	for (uint32_t ty = 0; ty < fb.tiles_y; ty++)
 	{
 		for (uint32_t tx = 0; tx < fb.tiles_x; tx++)
@@ -219,7 +227,8 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 					FbView view;
 					PixelState px;
 					pass_pixel_begin<SpecGeneric>(b, fb, view, px, x, y);
-					dev->counters[1] += pass_pixel_walk<SpecGeneric>(b, fb, view, px, x, y, tile);
+					dev->counters[1] += deferred ? pass_pixel_walk_deferred<SpecGeneric>(b, fb, view, px, x, y, tile)
+					                             : pass_pixel_walk<SpecGeneric>(b, fb, view, px, x, y, tile);
 					pass_pixel_end(fb, view, px, x, y);
 				}
 			}

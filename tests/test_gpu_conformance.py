@@ -36,6 +36,24 @@ def test_gpu_matches_oracle(name):
         assert digests[:n] == GOLDEN["digests"][name]
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_gpu_deferred_matches_oracle(name, monkeypatch):
+    """Same suites with every deferrable pass forced through the deferred tile kernel (dynamic instantiation)."""
+    monkeypatch.setenv("RDP_B200_FORCE_DEFERRED", "1")
+    v = cf.SUITES[name]
+    iters = 2 if v.primitive_count > 1 else 6
+    sbs = SideBySide("cuda", with_oracle=angrylion.available())
+    try:
+        digests = []
+        errs = cf.run_rasterization(sbs, v, iters, digests=digests)
+    finally:
+        sbs.close()
+    assert not errs, errs
+    if name in GOLDEN["digests"]:
+        n = min(GOLDEN["iterations"], iters)
+        assert digests[:n] == GOLDEN["digests"][name][:n]
+
+
 @pytest.mark.parametrize("name", sorted(cf.LOAD_SUITES))
 def test_gpu_texture_loads(name):
     if not angrylion.available():

@@ -42,6 +42,29 @@ def test_hostsim_matches_oracle(name):
     assert digests == GOLDEN["digests"][name]
 
 
+# The deferred tile pipeline's phase split (rdp_blend.cuh defer_*), in its scalar form, on every suite it accepts.
+DEFERRED_SUITES = [n for n in CPU_SUITES if not any(k in n for k in ("copy-", "alpha-test", "cvg-times-alpha"))] + [
+    "depth-compare-opaque", "depth-compare-transparent", "interpolation-color-texture-rgba16", "fill-rect",
+]
+
+
+@pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", sorted(set(DEFERRED_SUITES)))
+def test_hostsim_deferred_matches_oracle(name, monkeypatch):
+    monkeypatch.setenv("RDP_HOSTSIM_DEFERRED", "1")
+    sbs = SideBySide("hostsim")
+    try:
+        digests = []
+        errs = cf.run_rasterization(sbs, cf.SUITES[name], GOLDEN["iterations"], digests=digests)
+        variant = sbs.gpu.last_tile_variant()
+    finally:
+        sbs.close()
+    assert not errs, errs
+    assert digests == GOLDEN["digests"][name]
+    if name in ("depth-compare-opaque", "interpolation-color-texture-rgba16", "combiner-2cycle"):
+        assert variant == "generic+deferred"
+
+
 @pytest.mark.parametrize("name", ["fill-16", "interpolation-color-texture-rgba16", "depth-compare-opaque"])
 def test_hostsim_matches_golden_without_oracle(name):
     sbs = SideBySide("hostsim", with_oracle=False)

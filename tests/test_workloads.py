@@ -61,7 +61,7 @@ def test_hostsim_workload_matches_oracle(which, size):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("which,size,variant", [("c2", 5000, "zb-opa-tex-modulate-2c/rgba32"), ("c3", 64, "xlu-sprite-ci8-tlut-1c/rgba16")])
+@pytest.mark.parametrize("which,size,variant", [("c2", 5000, "zb-opa-tex-modulate-2c/rgba32+deferred"), ("c3", 64, "xlu-sprite-ci8-tlut-1c/rgba16")])
 def test_gpu_workload_matches_oracle_full_size(which, size, variant):
     """BASELINE.json's full frame sizes, 3 frames, byte-compared against the oracle; also pins which instantiation ran."""
     errs, variants = _run_side_by_side("cuda", which, 3, size)
@@ -69,11 +69,13 @@ def test_gpu_workload_matches_oracle_full_size(which, size, variant):
     assert variants == {variant}
 
 
-def _render_digest(which, count, size, force_generic):
+def _render_digest(which, count, size, force_generic, env=None):
     import hashlib
     old = os.environ.pop("RDP_B200_FORCE_GENERIC", None)
     if force_generic:
         os.environ["RDP_B200_FORCE_GENERIC"] = "1"
+    for k in env or ():
+        os.environ[k] = "1"
     try:
         sbs = SideBySide("cuda", rdram_size=wl.RDRAM_SIZE, hidden_size=wl.HIDDEN_SIZE, with_oracle=False)
         try:
@@ -91,6 +93,8 @@ def _render_digest(which, count, size, force_generic):
             sbs.close()
     finally:
         os.environ.pop("RDP_B200_FORCE_GENERIC", None)
+        for k in env or ():
+            os.environ.pop(k, None)
         if old is not None:
             os.environ["RDP_B200_FORCE_GENERIC"] = old
 
@@ -104,3 +108,16 @@ def test_gpu_specialised_equals_generic(which, size):
     assert names_b == {"generic"}
     assert "generic" not in names_a
     assert a == b
+
+
+@pytest.mark.gpu
+def test_gpu_deferred_equals_in_order():
+    """The deferred tile pipeline (coverage/Z -> ordered depth -> compacted shading -> ordered blend) against the
+    in-order kernels on the full C2 frame: specialised deferred, specialised in-order, dynamic deferred."""
+    a, names_a = _render_digest("c2", 4, 5000, force_generic=False)
+    b, names_b = _render_digest("c2", 4, 5000, force_generic=False, env=["RDP_B200_NO_DEFERRED"])
+    c, names_c = _render_digest("c2", 4, 5000, force_generic=False, env=["RDP_B200_FORCE_DEFERRED"])
+    assert names_a == {"zb-opa-tex-modulate-2c/rgba32+deferred"}
+    assert names_b == {"zb-opa-tex-modulate-2c/rgba32"}
+    assert names_c == {"generic+deferred"}
+    assert a == b == c
