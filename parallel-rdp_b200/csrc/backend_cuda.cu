@@ -268,6 +268,15 @@ struct TileWalker
 	}
 };
 
+// The metrics counters are spread over kCounterSlots (tiles, shaded) pairs so that thousands of warps finishing
+// together do not serialise on one L2 address; rdpb_counters_read folds them.
+constexpr uint32_t kCounterSlots = 32;
+constexpr uint32_t kCounterWords = 8 + 2 * kCounterSlots;
+__device__ __forceinline__ unsigned long long *counter_slot(const PassBuffers &b, uint32_t who)
+{
+	return b.counters + 8 + 2 * (who & (kCounterSlots - 1u));
+}
+
 // ---- deferred tile walker ------------------------------------------------------------------------------------
 // Same tile / list / mask-phase structure as TileWalker, but the fragments (pixel, primitive) of up to 32 list
 // entries are processed in four phases instead of one primitive at a time (rdp_blend.cuh, defer_*):
@@ -357,12 +366,38 @@ struct DeferredWalker
 			w.lines[lane] = hdr.z;
 			w.dzw[lane] = hdr.w;
 			uint32_t live = __ballot_sync(0xffffffffu, pixmask != 0u);
+			// First slot of every entry if the whole chunk fits one batch (the usual case): exclusive prefix sum.
+			const uint32_t np_own = uint32_t(__popc(pixmask));
+			uint32_t incl = np_own;
+#pragma unroll
+			for (int off = 1; off < 32; off <<= 1)
+			{
+				const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+				if (lane >= uint32_t(off))
+					incl += v;
+			}
+			const uint32_t chunk_total = __shfl_sync(0xffffffffu, incl, 31);
+			w.base[lane] = incl - np_own;
 			__syncwarp();
 
 			while (live)
 			{
 				// ---- enumerate: as many whole list entries as fit the slot arrays ----
 				uint32_t count = 0, mine = 0; // mine: entries with a fragment on this lane's pixel
+				if (chunk_total <= kDeferCapacity)
+				{
+					for (; live; live &= live - 1u)
+					{
+						const uint32_t j = uint32_t(__ffs(int(live)) - 1);
+						const uint32_t pm = w.pixmask[j];
+						if ((pm >> lane) & 1u)
+						{
+							w.desc[w.base[j] + uint32_t(__popc(pm & lt))] = (j << 5) | lane;
+							mine |= 1u << j;
+						}
+					}
+					count = chunk_total;
+				}
 				while (live)
 				{
 					const uint32_t j = uint32_t(__ffs(int(live)) - 1);
@@ -527,23 +562,80 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 		b.job_counter[0] = 0; // this pass's span jobs are consumed; the next pass allocates from zero
 
+	// Single-round gather: when the pass has at most 32 * kGatherWords mask words per tile (8192 primitives) lane L owns
+	// the contiguous words [L * words_per_lane, (L + 1) * words_per_lane), so one load round and one warp prefix sum
+	// list the whole tile in submission order.  Larger passes, and tiles with more than kTileListCapacity entries,
+	// take the coarse-mask walk below.
+	constexpr uint32_t kGatherWords = 8;
+	const uint32_t words_per_lane = (fb.mask_stride + 31u) / 32u;
+	const bool one_round = words_per_lane <= kGatherWords;
+
 	uint32_t tiles_done = 0, shaded_total = 0;
+	// The tile counter is read one tile ahead: the atomic's round trip overlaps the current tile's work.
+	uint32_t next_tile = 0;
+	if (lane == 0)
+		next_tile = atomicAdd(&b.job_counter[1], 1u);
 	for (;;)
 	{
-		uint32_t tile = 0;
-		if (lane == 0)
-			tile = atomicAdd(&b.job_counter[1], 1u);
-		tile = __shfl_sync(0xffffffffu, tile, 0);
+		const uint32_t tile = __shfl_sync(0xffffffffu, next_tile, 0);
 		if (tile >= num_tiles)
 			break;
+		if (lane == 0)
+			next_tile = atomicAdd(&b.job_counter[1], 1u);
 
 		uint32_t *coarse = b.coarse_mask + size_t(tile) * fb.coarse_stride;
 		uint32_t *fine = b.fine_mask + size_t(tile) * fb.mask_stride;
-		uint32_t any = 0;
-		for (uint32_t cw = 0; cw < fb.coarse_stride; cw++)
-			any |= coarse[cw];
-		if (!any)
-			continue;
+		uint32_t listed = 0; // entries of `list` produced by the single-round gather
+		if (one_round)
+		{
+			uint32_t wv[kGatherWords];
+			const uint32_t first = lane * words_per_lane;
+			uint32_t n = 0;
+#pragma unroll
+			for (uint32_t i = 0; i < kGatherWords; i++)
+			{
+				wv[i] = (i < words_per_lane && first + i < fb.mask_stride) ? fine[first + i] : 0u;
+				n += uint32_t(__popc(wv[i]));
+			}
+			if (__ballot_sync(0xffffffffu, n != 0u) == 0u)
+				continue;
+			uint32_t incl = n;
+#pragma unroll
+			for (int off = 1; off < 32; off <<= 1)
+			{
+				const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+				if (lane >= uint32_t(off))
+					incl += v;
+			}
+			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+			if (total <= kTileListCapacity)
+			{
+				uint32_t at = incl - n;
+#pragma unroll
+				for (uint32_t i = 0; i < kGatherWords; i++)
+				{
+					uint32_t w = wv[i];
+					if (w)
+						fine[first + i] = 0u; // consumed: the next pass starts from clean masks
+					while (w)
+					{
+						list[at++] = uint16_t((first + i) * 32u + uint32_t(__ffs(int(w)) - 1));
+						w &= w - 1u;
+					}
+				}
+				if (lane < fb.coarse_stride)
+					coarse[lane] = 0u;
+				listed = total;
+			}
+		}
+		else
+		{
+			uint32_t any = 0;
+			for (uint32_t cw = 0; cw < fb.coarse_stride; cw++)
+				any |= coarse[cw];
+			if (!any)
+				continue;
+		}
 		tiles_done++;
 
 		const uint32_t tx = tile % fb.tiles_x, ty = tile / fb.tiles_x;
@@ -555,55 +647,64 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 		walk.inside_mask = __ballot_sync(0xffffffffu, walk.x < int(fb.width) && walk.y < int(fb.height));
 		pass_pixel_begin<S>(b, fb, view, px, walk.x, walk.y);
 
-		// Gather / process until the tile's masks are exhausted.  `w` holds this lane's not-yet-listed bits of the
-		// current round (coarse word cw summarises fine words cw*32 .. cw*32+31: one lane-parallel round).
-		uint32_t cw = 0, w = 0, idx = 0;
-		for (;;)
+		if (listed)
 		{
-			uint32_t count = 0;
-			while (count < kTileListCapacity)
+			__syncwarp();
+			walk.run(list, listed);
+			__syncwarp();
+		}
+		else
+		{
+			// Gather / process until the tile's masks are exhausted.  `w` holds this lane's not-yet-listed bits of the
+			// current round (coarse word cw summarises fine words cw*32 .. cw*32+31: one lane-parallel round).
+			uint32_t cw = 0, w = 0, idx = 0;
+			for (;;)
 			{
-				if (__ballot_sync(0xffffffffu, w != 0u) == 0u)
+				uint32_t count = 0;
+				while (count < kTileListCapacity)
 				{
-					while (cw < fb.coarse_stride && coarse[cw] == 0u)
+					if (__ballot_sync(0xffffffffu, w != 0u) == 0u)
+					{
+						while (cw < fb.coarse_stride && coarse[cw] == 0u)
+							cw++;
+						if (cw >= fb.coarse_stride)
+							break;
+						idx = cw * 32u + lane;
+						w = idx < fb.mask_stride ? fine[idx] : 0u;
+						if (w)
+							fine[idx] = 0u;
+						__syncwarp();
+						if (lane == 0)
+							coarse[cw] = 0u;
 						cw++;
-					if (cw >= fb.coarse_stride)
-						break;
-					idx = cw * 32u + lane;
-					w = idx < fb.mask_stride ? fine[idx] : 0u;
-					if (w)
-						fine[idx] = 0u; // consumed: the next pass starts from clean masks
-					__syncwarp();
-					if (lane == 0)
-						coarse[cw] = 0u;
-					cw++;
-				}
-				const uint32_t n = uint32_t(__popc(w));
-				uint32_t incl = n;
+					}
+					const uint32_t n = uint32_t(__popc(w));
+					uint32_t incl = n;
 #pragma unroll
-				for (int off = 1; off < 32; off <<= 1)
-				{
-					const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
-					if (lane >= uint32_t(off))
-						incl += v;
+					for (int off = 1; off < 32; off <<= 1)
+					{
+						const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+						if (lane >= uint32_t(off))
+							incl += v;
+					}
+					const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+					const uint32_t space = kTileListCapacity - count;
+					// Bits are listed in submission order; whatever does not fit stays in `w` for the next list.
+					uint32_t at = incl - n;
+					while (w && at < space)
+					{
+						list[count + at] = uint16_t(idx * 32u + uint32_t(__ffs(int(w)) - 1));
+						w &= w - 1u;
+						at++;
+					}
+					count += min(total, space);
 				}
-				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-				const uint32_t space = kTileListCapacity - count;
-				// Bits are listed in submission order; whatever does not fit stays in `w` for the next list.
-				uint32_t at = incl - n;
-				while (w && at < space)
-				{
-					list[count + at] = uint16_t(idx * 32u + uint32_t(__ffs(int(w)) - 1));
-					w &= w - 1u;
-					at++;
-				}
-				count += min(total, space);
+				if (count == 0u)
+					break;
+				__syncwarp();
+				walk.run(list, count);
+				__syncwarp();
 			}
-			if (count == 0u)
-				break;
-			__syncwarp();
-			walk.run(list, count);
-			__syncwarp();
 		}
 		shaded_total += walk.shaded;
 
@@ -614,11 +715,95 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 	const uint32_t warp_total = __reduce_add_sync(0xffffffffu, shaded_total);
 	if (lane == 0)
 	{
-		if (warp_total)
-			atomicAdd(&b.counters[1], (unsigned long long)warp_total);
+		unsigned long long *slot = counter_slot(b, blockIdx.x * kTileWarpsPerBlock + (threadIdx.x >> 5));
 		if (tiles_done)
-			atomicAdd(&b.counters[0], (unsigned long long)tiles_done);
+			atomicAdd(&slot[0], (unsigned long long)tiles_done);
+		if (warp_total)
+			atomicAdd(&slot[1], (unsigned long long)warp_total);
 	}
+}
+
+// Fill-only passes with a handful of primitives (screen and Z clears: the first pass of nearly every frame) skip
+// the tile machinery: one thread per pixel tests the pass's fill primitives in order against their span headers
+// and stores once.  Nothing is read from the framebuffer (the fill pipe replaces the pixel, memory_interfacing.h:
+// 440-486) and the chain of dependent loads is primitive header -> span header, instead of tile counter -> masks ->
+// list -> headers -> spans as in k_tiles.  The thread on each 8x4 tile's corner clears the tile's bin masks, which
+// the span kernel filled as usual.
+constexpr uint32_t kFillPassMaxPrims = 8;
+
+__global__ void __launch_bounds__(256) k_fill_pass(PassBuffers b, FbInfo fb)
+{
+	__shared__ uint32_t s_count[2];
+	if (threadIdx.x < 2)
+		s_count[threadIdx.x] = 0;
+	__syncthreads();
+	// A 256-thread block covers 32 x 8 pixels = 4 x 2 tiles.
+	const int x = int(blockIdx.x * 32u + (threadIdx.x & 31u));
+	const int y = int(blockIdx.y * 8u + (threadIdx.x >> 5));
+	const uint32_t tile_row = uint32_t(y) / kTileH;
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+		b.job_counter[0] = 0;
+
+	uint32_t tiles_done = 0;
+	if ((x & int(kTileW - 1)) == 0 && (y & int(kTileH - 1)) == 0 && uint32_t(x) / kTileW < fb.tiles_x && tile_row < fb.tiles_y)
+	{
+		const size_t tile = size_t(tile_row) * fb.tiles_x + uint32_t(x) / kTileW;
+		uint32_t any = 0;
+		for (uint32_t i = 0; i < fb.mask_stride; i++)
+		{
+			any |= b.fine_mask[tile * fb.mask_stride + i];
+			b.fine_mask[tile * fb.mask_stride + i] = 0u;
+		}
+		for (uint32_t i = 0; i < fb.coarse_stride; i++)
+			b.coarse_mask[tile * fb.coarse_stride + i] = 0u;
+		tiles_done = any ? 1u : 0u;
+	}
+
+	uint32_t shaded = 0;
+	if (x < int(fb.width) && y < int(fb.height))
+	{
+		FbView view;
+		view.rdram = b.rdram;
+		view.hidden = b.hidden;
+		view.blend_lut = b.blend_lut;
+		view.fmt = fb.fmt;
+		view.rdram_size = fb.rdram_size;
+		view.alias = fb.color_addr == fb.depth_addr;
+		PixelState px;
+		px.r = px.g = px.b = px.a = 0;
+		px.depth = px.dz = 0;
+		px.color_dirty = px.depth_dirty = false;
+		const uint32_t shift = view.fmt == FB_RGBA8888 ? 2u : ((view.fmt == FB_RGBA5551 || view.fmt == FB_IA88) ? 1u : 0u);
+		px.color_index = (fb.color_addr >> shift) + fb.width * uint32_t(y) + uint32_t(x);
+
+		for (uint32_t i = 0; i < fb.num_prims; i++)
+		{
+			const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(&b.prims[i].span_base));
+			const int line_lo = int(int16_t(hdr.z & 0xffffu)), line_hi = int(int16_t(hdr.z >> 16));
+			if (y < line_lo || y > line_hi)
+				continue;
+			const Span *sp = b.spans + (hdr.x + uint32_t(y - line_lo));
+			const uint2 sh = *reinterpret_cast<const uint2 *>(&sp->start_x);
+			if ((sh.y >> 16) == 0u || x < int(int16_t(sh.x & 0xffffu)) || x > int(int16_t(sh.x >> 16)))
+				continue;
+			fill_pixel(view, px, b.states[hdr.y & 0xffffu].fill_color);
+			shaded++;
+		}
+		store_color(view, px, px.color_index);
+	}
+
+	const uint32_t warp_shaded = __reduce_add_sync(0xffffffffu, shaded);
+	const uint32_t warp_tiles = __reduce_add_sync(0xffffffffu, tiles_done);
+	if ((threadIdx.x & 31u) == 0)
+	{
+		if (warp_tiles)
+			atomicAdd(&s_count[0], warp_tiles);
+		if (warp_shaded)
+			atomicAdd(&s_count[1], warp_shaded);
+	}
+	__syncthreads();
+	if (threadIdx.x < 2 && s_count[threadIdx.x])
+		atomicAdd(&counter_slot(b, blockIdx.x + 5u * blockIdx.y)[threadIdx.x], (unsigned long long)s_count[threadIdx.x]);
 }
 
 // VI filter: a 32x8 block computes the AA / dither-reconstruction result ("fetch") of its pixels plus one halo
@@ -695,6 +880,9 @@ static TileVariant make_variant(const char *name)
 
 static_assert(sizeof(kTileVariants) / sizeof(kTileVariants[0]) <= 32, "grow rdpb_device::variant_blocks_per_sm");
 
+// Not a tile kernel: fill-only passes of at most kFillPassMaxPrims primitives (launched per pixel, see k_fill_pass).
+static const TileVariant kFillPassVariant = { "fill-pass", 0u, 0u, 0u, 0u, 0x1fu, 0u, false, 0ull, 0u, 0u, false, &k_fill_pass };
+
 // Environment switches (read per pass, so tests can flip them): RDP_B200_FORCE_GENERIC pins the in-order uber-kernel,
 // RDP_B200_NO_DEFERRED keeps every pass on the in-order kernels, RDP_B200_FORCE_DEFERRED sends every deferrable
 // pass through the fully dynamic deferred kernel (how the conformance suites exercise it).
@@ -704,6 +892,8 @@ static const TileVariant *pick_tile_variant(const PassSummary *sum, const FbInfo
 	const size_t n = sizeof(kTileVariants) / sizeof(kTileVariants[0]);
 	if (!sum || getenv("RDP_B200_FORCE_GENERIC"))
 		return &kTileVariants[n - 1];
+	if (sum->num_shaded_states == 0 && fb.num_prims <= kFillPassMaxPrims && !getenv("RDP_B200_NO_FILL_PASS"))
+		return &kFillPassVariant;
 	const bool deferrable = deferrable_pass(*sum, fb) && sum->num_shaded_states != 0 && !getenv("RDP_B200_NO_DEFERRED");
 	if (deferrable && getenv("RDP_B200_FORCE_DEFERRED"))
 		return &kTileVariants[n - 2];
@@ -913,6 +1103,15 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	case GOP_TILES:
 	{
 		const int s = prof_begin(dev, RDPB_KERNEL_TILES);
+		if (op.variant == &kFillPassVariant)
+		{
+			// Pixel grid, rounded up to whole tiles so that every tile's masks are cleared.
+			const dim3 grid((op.fb.tiles_x * kTileW + 31u) / 32u, (op.fb.tiles_y + 1u) / 2u);
+			k_fill_pass<<<grid, 256, 0, dev->stream>>>(dev->buffers(op), op.fb);
+			prof_end(dev, s);
+			dev->launches++;
+			break;
+		}
 		const uint32_t tiles = op.fb.tiles_x * op.fb.tiles_y;
 		// Persistent grid: exactly as many blocks as can be resident (occupancy of this instantiation x SMs).
 		const size_t vi = size_t(op.variant - kTileVariants);
@@ -1061,7 +1260,7 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	need(cudaMalloc(&dev->tmem_instances, size_t(kTmemBytes) * (kMaxUploadsPerPass + 1)), "cudaMalloc tmem instances");
 	need(cudaMalloc(&dev->blend_lut, 0x8000), "cudaMalloc blend lut");
 	need(cudaMalloc(&dev->gamma_lut, 256 + 256 * 64), "cudaMalloc gamma lut");
-	need(cudaMalloc(&dev->d_counters, 8 * sizeof(unsigned long long)), "cudaMalloc counters");
+	need(cudaMalloc(&dev->d_counters, kCounterWords * sizeof(unsigned long long)), "cudaMalloc counters");
 	for (unsigned i = 0; i < kStagingSlots; i++)
 	{
 		need(cudaMalloc(&dev->d_words[i], size_t(kMaxPassWords) * 4), "cudaMalloc words");
@@ -1100,7 +1299,7 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		need(cudaMemsetAsync(dev->d_fine, 0, fine_bytes, dev->stream), "memset fine");
 		need(cudaMemsetAsync(dev->d_coarse, 0, coarse_bytes, dev->stream), "memset coarse");
 		need(cudaMemsetAsync(dev->d_job_counter, 0, 256, dev->stream), "memset job counter");
-		need(cudaMemsetAsync(dev->d_counters, 0, 8 * sizeof(unsigned long long), dev->stream), "memset counters");
+		need(cudaMemsetAsync(dev->d_counters, 0, kCounterWords * sizeof(unsigned long long), dev->stream), "memset counters");
 		need(cudaMemsetAsync(dev->vi_out[0], 0, max_out, dev->stream), "memset vi out");
 		need(cudaMemsetAsync(dev->vi_out[1], 0, max_out, dev->stream), "memset vi out");
 		need(cudaMemsetAsync(dev->tmem_instances, 0, size_t(kTmemBytes) * (kMaxUploadsPerPass + 1), dev->stream), "memset tmem instances");
@@ -1555,10 +1754,18 @@ int rdpb_profile_read(rdpb_device *dev, int kind, uint32_t *launches, double *to
 int rdpb_counters_read(rdpb_device *dev, uint64_t *out8, int reset)
 {
 	cudaSetDevice(dev->ordinal);
-	CK(cudaMemcpyAsync(out8, dev->d_counters, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, dev->stream));
+	uint64_t all[kCounterWords];
+	CK(cudaMemcpyAsync(all, dev->d_counters, sizeof(all), cudaMemcpyDeviceToHost, dev->stream));
 	CK(cudaStreamSynchronize(dev->stream));
+	for (uint32_t i = 0; i < 8; i++)
+		out8[i] = all[i];
+	for (uint32_t s = 0; s < kCounterSlots; s++)
+	{
+		out8[0] += all[8 + 2 * s];
+		out8[1] += all[8 + 2 * s + 1];
+	}
 	if (reset)
-		CK(cudaMemsetAsync(dev->d_counters, 0, 8 * sizeof(uint64_t), dev->stream));
+		CK(cudaMemsetAsync(dev->d_counters, 0, sizeof(all), dev->stream));
 	return 0;
 }
 

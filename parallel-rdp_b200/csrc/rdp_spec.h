@@ -105,7 +105,7 @@ struct Spec
 	// 5 (<= 96 registers) for the feature classes and the uber-kernel.
 	static constexpr int min_blocks_per_sm = EXACT ? 8 : 5;
 	// The deferred tile kernel (k_tiles<S, true>) keeps ~5 KiB of fragment slots per warp in shared memory.
-	static constexpr int min_blocks_per_sm_deferred = EXACT ? 6 : 4;
+	static constexpr int min_blocks_per_sm_deferred = EXACT ? 8 : 4;
 };
 
 // Fully dynamic: the uber-kernel fallback (ref shaders/ubershader.comp).
