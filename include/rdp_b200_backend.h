@@ -105,7 +105,7 @@ uint64_t rdpb_launch_count(rdpb_device *dev);
 enum
 {
 	RDPB_KERNEL_FRONT = 0, /* texture-load replay + primitive set-up, one launch */
-	RDPB_KERNEL_RESERVED = 1,
+	RDPB_KERNEL_FILL_PASS = 1, /* per-pixel kernel that replaces the tile kernel on small fill-only passes */
 	RDPB_KERNEL_SPAN_BIN = 2,
 	RDPB_KERNEL_TILES = 3,
 	RDPB_KERNEL_VI_FILTER = 4,

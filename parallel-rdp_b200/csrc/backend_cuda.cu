@@ -147,6 +147,16 @@ __global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
 constexpr uint32_t kTileWarpsPerBlock = 4;
 constexpr uint32_t kTileListCapacity = 128;
 
+// The tile counter is bumped with atom.inc (wrap bound 2^31 - 1, far above any tile count, so a plain increment):
+// ptxas turns atom.add -- and atom.inc with an all-ones bound -- into a warp-aggregated atomic whose result is
+// broadcast by a shuffle right away, and that shuffle would wait for the very round trip the look-ahead overlaps.
+__device__ __forceinline__ uint32_t fetch_inc_async(uint32_t *p)
+{
+	uint32_t old;
+	asm volatile("atom.global.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "l"(p));
+	return old;
+}
+
 __device__ __forceinline__ void prefetch_l1(const void *p)
 {
 	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -293,13 +303,40 @@ __device__ __forceinline__ unsigned long long *counter_slot(const PassBuffers &b
 // only the two cheap ordered phases B and D depend on how many fragments one pixel has.
 constexpr uint32_t kDeferCapacity = 256; // fragment slots per batch (>= 32: one list entry always fits)
 
+// Second word of a shaded result (shade alpha + dither pattern): only states that dither or feed shade alpha to
+// the blender read it, so specialisations that cannot do either do not pay the shared memory for it.
+template <bool NEEDED>
+struct DeferResultAux
+{
+	uint32_t aux[kDeferCapacity];
+	__device__ __forceinline__ void put(uint32_t k, uint32_t v) { aux[k] = v; }
+	__device__ __forceinline__ uint32_t get(uint32_t k) const { return aux[k]; }
+};
+template <>
+struct DeferResultAux<false>
+{
+	__device__ __forceinline__ void put(uint32_t, uint32_t) {}
+	__device__ __forceinline__ uint32_t get(uint32_t) const { return 0u; }
+};
+
 struct alignas(16) DeferWarp
 {
-	uint2 result[kDeferCapacity];  // C -> D: packed shaded colour of a slot
+	uint32_t result[kDeferCapacity];  // C -> D: packed shaded colour of a slot (r | g<<8 | b<<16 | a<<24)
 	uint32_t cand[kDeferCapacity]; // A -> B: candidate word; B -> C, D: survivor record
 	uint32_t desc[kDeferCapacity]; // slot -> entry << 5 | pixel; after compaction: survivor -> slot << 16 | entry << 5 | pixel
 	uint32_t pixmask[32], base[32], prim[32], span_base[32], ids[32], lines[32], dzw[32]; // per list entry of the chunk
 	uint16_t list[kTileListCapacity];
+};
+
+// Per-warp shared memory of the tile kernel: just the primitive list for the in-order walker.
+template <class S, bool DEFERRED>
+struct TileShared
+{
+	uint16_t list[kTileListCapacity];
+};
+template <class S>
+struct TileShared<S, true> : DeferWarp, DeferResultAux<S::blend_reads_aux>
+{
 };
 
 template <class S>
@@ -310,7 +347,7 @@ struct DeferredWalker
 	const ShadeContext &ctx;
 	const FbView &view;
 	PixelState &px;
-	DeferWarp &w;
+	TileShared<S, true> &w;
 	uint32_t lane;
 	int x0, y0, x, y;
 	uint32_t inside_mask;
@@ -499,7 +536,8 @@ struct DeferredWalker
 					load_prim_for_shading(b.prims + prim, span_base, ids, lines, w.dzw[j], p);
 					uint32_t rx, ry;
 					defer_shade<S>(ctx, fx, fy, prim, p, sp, b.states[ids & 0xffffu], w.cand[k], rx, ry);
-					w.result[k] = make_uint2(rx, ry);
+					w.result[k] = rx;
+					w.put(k, ry);
 				}
 				__syncwarp();
 
@@ -508,8 +546,7 @@ struct DeferredWalker
 				{
 					const uint32_t j = uint32_t(__ffs(int(t)) - 1);
 					const uint32_t k = slot_of(j, lt);
-					const uint2 res = w.result[k];
-					defer_blend<S>(view, px, b.states[w.ids[j] & 0xffffu], w.cand[k], res.x, res.y);
+					defer_blend<S>(view, px, b.states[w.ids[j] & 0xffffu], w.cand[k], w.result[k], w.get(k));
 				}
 				__syncwarp();
 			}
@@ -517,15 +554,6 @@ struct DeferredWalker
 	}
 };
 
-template <class S, bool DEFERRED>
-struct TileShared
-{
-	uint16_t list[kTileListCapacity];
-};
-template <class S>
-struct TileShared<S, true> : DeferWarp
-{
-};
 
 
 template <class S>
@@ -574,14 +602,14 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 	// The tile counter is read one tile ahead: the atomic's round trip overlaps the current tile's work.
 	uint32_t next_tile = 0;
 	if (lane == 0)
-		next_tile = atomicAdd(&b.job_counter[1], 1u);
+		next_tile = fetch_inc_async(&b.job_counter[1]);
 	for (;;)
 	{
 		const uint32_t tile = __shfl_sync(0xffffffffu, next_tile, 0);
 		if (tile >= num_tiles)
 			break;
 		if (lane == 0)
-			next_tile = atomicAdd(&b.job_counter[1], 1u);
+			next_tile = fetch_inc_async(&b.job_counter[1]);
 
 		uint32_t *coarse = b.coarse_mask + size_t(tile) * fb.coarse_stride;
 		uint32_t *fine = b.fine_mask + size_t(tile) * fb.mask_stride;
@@ -646,6 +674,29 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 		walk.y = walk.y0 + int(lane >> 3);
 		walk.inside_mask = __ballot_sync(0xffffffffu, walk.x < int(fb.width) && walk.y < int(fb.height));
 		pass_pixel_begin<S>(b, fb, view, px, walk.x, walk.y);
+
+		// Warm L1 with what the front of the next tile reads (its mask words, its pixels): those are the first links of
+		// the chain of dependent loads every tile starts with.  The tile index was requested a whole tile ago.
+		{
+			const uint32_t ahead = __shfl_sync(0xffffffffu, next_tile, 0);
+			if (ahead < num_tiles)
+			{
+				if (one_round && lane * words_per_lane < fb.mask_stride)
+					prefetch_l1(b.fine_mask + size_t(ahead) * fb.mask_stride + lane * words_per_lane);
+				const uint32_t ax = (ahead % fb.tiles_x) * kTileW + (lane & 7u), ay = (ahead / fb.tiles_x) * kTileH + (lane >> 3);
+				if (ax < fb.width && ay < fb.height)
+				{
+					const uint32_t pix = fb.width * ay + ax;
+					const uint32_t shift = view.fmt == FB_RGBA8888 ? 2u : ((view.fmt == FB_RGBA5551 || view.fmt == FB_IA88) ? 1u : 0u);
+					const uint32_t caddr = (fb.color_addr + (pix << shift)) & (fb.rdram_size - 1u);
+					const uint32_t daddr = (fb.depth_addr + (pix << 1)) & (fb.rdram_size - 1u);
+					prefetch_l1(b.rdram + caddr);
+					prefetch_l1(b.hidden + (caddr >> 1));
+					prefetch_l1(b.rdram + daddr);
+					prefetch_l1(b.hidden + (daddr >> 1));
+				}
+			}
+		}
 
 		if (listed)
 		{
@@ -737,59 +788,64 @@ __global__ void __launch_bounds__(256) k_fill_pass(PassBuffers b, FbInfo fb)
 	if (threadIdx.x < 2)
 		s_count[threadIdx.x] = 0;
 	__syncthreads();
-	// A 256-thread block covers 32 x 8 pixels = 4 x 2 tiles.
-	const int x = int(blockIdx.x * 32u + (threadIdx.x & 31u));
+	// A 256-thread block covers 64 x 8 pixels = 8 x 2 tiles, two pixels (x, x + 32) per thread: 640 x 480 is 600 blocks,
+	// one resident wave on 148 SMs.
 	const int y = int(blockIdx.y * 8u + (threadIdx.x >> 5));
 	const uint32_t tile_row = uint32_t(y) / kTileH;
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
 		b.job_counter[0] = 0;
 
-	uint32_t tiles_done = 0;
-	if ((x & int(kTileW - 1)) == 0 && (y & int(kTileH - 1)) == 0 && uint32_t(x) / kTileW < fb.tiles_x && tile_row < fb.tiles_y)
-	{
-		const size_t tile = size_t(tile_row) * fb.tiles_x + uint32_t(x) / kTileW;
-		uint32_t any = 0;
-		for (uint32_t i = 0; i < fb.mask_stride; i++)
-		{
-			any |= b.fine_mask[tile * fb.mask_stride + i];
-			b.fine_mask[tile * fb.mask_stride + i] = 0u;
-		}
-		for (uint32_t i = 0; i < fb.coarse_stride; i++)
-			b.coarse_mask[tile * fb.coarse_stride + i] = 0u;
-		tiles_done = any ? 1u : 0u;
-	}
+	FbView view;
+	view.rdram = b.rdram;
+	view.hidden = b.hidden;
+	view.blend_lut = b.blend_lut;
+	view.fmt = fb.fmt;
+	view.rdram_size = fb.rdram_size;
+	view.alias = fb.color_addr == fb.depth_addr;
+	const uint32_t shift = view.fmt == FB_RGBA8888 ? 2u : ((view.fmt == FB_RGBA5551 || view.fmt == FB_IA88) ? 1u : 0u);
 
-	uint32_t shaded = 0;
-	if (x < int(fb.width) && y < int(fb.height))
+	uint32_t tiles_done = 0, shaded = 0;
+#pragma unroll
+	for (int half = 0; half < 2; half++)
 	{
-		FbView view;
-		view.rdram = b.rdram;
-		view.hidden = b.hidden;
-		view.blend_lut = b.blend_lut;
-		view.fmt = fb.fmt;
-		view.rdram_size = fb.rdram_size;
-		view.alias = fb.color_addr == fb.depth_addr;
-		PixelState px;
-		px.r = px.g = px.b = px.a = 0;
-		px.depth = px.dz = 0;
-		px.color_dirty = px.depth_dirty = false;
-		const uint32_t shift = view.fmt == FB_RGBA8888 ? 2u : ((view.fmt == FB_RGBA5551 || view.fmt == FB_IA88) ? 1u : 0u);
-		px.color_index = (fb.color_addr >> shift) + fb.width * uint32_t(y) + uint32_t(x);
-
-		for (uint32_t i = 0; i < fb.num_prims; i++)
+		const int x = int(blockIdx.x * 64u + uint32_t(half) * 32u + (threadIdx.x & 31u));
+		if ((x & int(kTileW - 1)) == 0 && (y & int(kTileH - 1)) == 0 && uint32_t(x) / kTileW < fb.tiles_x && tile_row < fb.tiles_y)
 		{
-			const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(&b.prims[i].span_base));
-			const int line_lo = int(int16_t(hdr.z & 0xffffu)), line_hi = int(int16_t(hdr.z >> 16));
-			if (y < line_lo || y > line_hi)
-				continue;
-			const Span *sp = b.spans + (hdr.x + uint32_t(y - line_lo));
-			const uint2 sh = *reinterpret_cast<const uint2 *>(&sp->start_x);
-			if ((sh.y >> 16) == 0u || x < int(int16_t(sh.x & 0xffffu)) || x > int(int16_t(sh.x >> 16)))
-				continue;
-			fill_pixel(view, px, b.states[hdr.y & 0xffffu].fill_color);
-			shaded++;
+			const size_t tile = size_t(tile_row) * fb.tiles_x + uint32_t(x) / kTileW;
+			uint32_t any = 0;
+			for (uint32_t i = 0; i < fb.mask_stride; i++)
+			{
+				any |= b.fine_mask[tile * fb.mask_stride + i];
+				b.fine_mask[tile * fb.mask_stride + i] = 0u;
+			}
+			for (uint32_t i = 0; i < fb.coarse_stride; i++)
+				b.coarse_mask[tile * fb.coarse_stride + i] = 0u;
+			tiles_done += any ? 1u : 0u;
 		}
-		store_color(view, px, px.color_index);
+
+		if (x < int(fb.width) && y < int(fb.height))
+		{
+			PixelState px;
+			px.r = px.g = px.b = px.a = 0;
+			px.depth = px.dz = 0;
+			px.color_dirty = px.depth_dirty = false;
+			px.color_index = (fb.color_addr >> shift) + fb.width * uint32_t(y) + uint32_t(x);
+
+			for (uint32_t i = 0; i < fb.num_prims; i++)
+			{
+				const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(&b.prims[i].span_base));
+				const int line_lo = int(int16_t(hdr.z & 0xffffu)), line_hi = int(int16_t(hdr.z >> 16));
+				if (y < line_lo || y > line_hi)
+					continue;
+				const Span *sp = b.spans + (hdr.x + uint32_t(y - line_lo));
+				const uint2 sh = *reinterpret_cast<const uint2 *>(&sp->start_x);
+				if ((sh.y >> 16) == 0u || x < int(int16_t(sh.x & 0xffffu)) || x > int(int16_t(sh.x >> 16)))
+					continue;
+				fill_pixel(view, px, b.states[hdr.y & 0xffffu].fill_color);
+				shaded++;
+			}
+			store_color(view, px, px.color_index);
+		}
 	}
 
 	const uint32_t warp_shaded = __reduce_add_sync(0xffffffffu, shaded);
@@ -806,28 +862,45 @@ __global__ void __launch_bounds__(256) k_fill_pass(PassBuffers b, FbInfo fb)
 		atomicAdd(&counter_slot(b, blockIdx.x + 5u * blockIdx.y)[threadIdx.x], (unsigned long long)s_count[threadIdx.x]);
 }
 
-// VI filter: a 32x8 block computes the AA / dither-reconstruction result ("fetch") of its pixels plus one halo
-// column on each side into shared memory, then the divot median reads its three inputs from there -- each fetch
-// result (up to nine RDRAM reads) is computed once instead of three times.
+// VI filter: a 32x8 block first decodes its framebuffer neighbourhood (38 x 10 pixels: the AA / dither filters
+// reach two columns and one row out, and the divot needs the filter result one more column out) into shared
+// memory, computes the AA / dither-reconstruction result ("fetch") of its pixels plus one halo column on each
+// side from there, and then the divot median reads its three inputs from shared memory as well.  Every
+// framebuffer pixel is decoded once per block and every fetch result computed once, instead of ~9 and 3 times.
+struct ViSharedReader
+{
+	const uint32_t (*vram)[40];
+	int x0, y0; // framebuffer coordinates of vram[0][0]
+	__device__ __forceinline__ ViColor operator()(int x, int y) const { return vi_unpack(vram[y - y0][x - x0]); }
+};
+
 __global__ void __launch_bounds__(256) k_vi_filter(ViFrame f, ViBuffers b)
 {
+	__shared__ uint32_t s_vram[10][40];
 	__shared__ uint32_t s_fetch[8][34];
 	const int tx = int(threadIdx.x), ty = int(threadIdx.y);
-	const int x = int(blockIdx.x) * 32 + tx;
-	const int y = int(blockIdx.y) * 8 + ty;
+	const int bx = int(blockIdx.x) * 32, by = int(blockIdx.y) * 8;
+	const int x = bx + tx, y = by + ty;
 	const bool bug = blockIdx.z != 0;
+	const int tid = ty * 32 + tx;
 
-	ViColor c = vi_fetch_pixel(f, b, x, y, bug);
+	for (int i = tid; i < 380; i += 256)
+	{
+		const int ry = i / 38, rx = i - ry * 38;
+		s_vram[ry][rx] = vi_pack(vi_read_vram(f, b, bx - 3 + rx, by - 1 + ry));
+	}
+	__syncthreads();
+	const ViSharedReader read = { s_vram, bx - 3, by - 1 };
+
+	ViColor c = vi_fetch_core(f, read, x, y, bug);
 	if (f.status & VI_STATUS_DIVOT)
 	{
 		// Fetch results fit 8 bits per channel (the dither filter cannot leave [0, 255]), so packing is lossless.
 		s_fetch[ty][tx + 1] = vi_pack(c);
-		const int tid = ty * 32 + tx;
 		if (tid < 16)
 		{
 			const int row = tid >> 1, right = tid & 1;
-			const int hx = int(blockIdx.x) * 32 + (right ? 32 : -1);
-			s_fetch[row][right ? 33 : 0] = vi_pack(vi_fetch_pixel(f, b, hx, int(blockIdx.y) * 8 + row, bug));
+			s_fetch[row][right ? 33 : 0] = vi_pack(vi_fetch_core(f, read, right ? bx + 32 : bx - 1, by + row, bug));
 		}
 		__syncthreads();
 		const ViColor l = vi_unpack(s_fetch[ty][tx]);
@@ -1102,11 +1175,11 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	}
 	case GOP_TILES:
 	{
-		const int s = prof_begin(dev, RDPB_KERNEL_TILES);
+		const int s = prof_begin(dev, op.variant == &kFillPassVariant ? RDPB_KERNEL_FILL_PASS : RDPB_KERNEL_TILES);
 		if (op.variant == &kFillPassVariant)
 		{
 			// Pixel grid, rounded up to whole tiles so that every tile's masks are cleared.
-			const dim3 grid((op.fb.tiles_x * kTileW + 31u) / 32u, (op.fb.tiles_y + 1u) / 2u);
+			const dim3 grid((op.fb.tiles_x * kTileW + 63u) / 64u, (op.fb.tiles_y + 1u) / 2u);
 			k_fill_pass<<<grid, 256, 0, dev->stream>>>(dev->buffers(op), op.fb);
 			prof_end(dev, s);
 			dev->launches++;

@@ -141,25 +141,29 @@ RDP_HD int vi_clamp1(int v) { return iclamp(v, -1, 1); }
 
 // vi_fetch.frag: AA filter (partial coverage) or dither reconstruction (full coverage) at framebuffer pixel (x, y).
 // `bug` selects the variant the oracle produces when it re-reads a line ("fetch bug").
-RDP_HD ViColor vi_fetch_pixel(const ViFrame &f, const ViBuffers &b, int x, int y, bool bug)
+// `read(x, y)` yields the decoded framebuffer pixel: straight from RDRAM (vi_fetch_pixel below), or from a block's
+// shared-memory copy of its neighbourhood in the CUDA filter kernel, where every pixel is then decoded once
+// instead of once per consumer.
+template <class Reader>
+RDP_HD ViColor vi_fetch_core(const ViFrame &f, const Reader &read, int x, int y, bool bug)
 {
-	const ViColor mid = vi_read_vram(f, b, x, y);
+	const ViColor mid = read(x, y);
 	ViColor out = mid;
 
 	if (mid.a != 7)
 	{
 		int lo[3] = { mid.r, mid.g, mid.b }, hi[3] = { mid.r, mid.g, mid.b };
 		int lo2[3] = { mid.r, mid.g, mid.b }, hi2[3] = { mid.r, mid.g, mid.b };
-		const ViColor to_left = vi_read_vram(f, b, x - 2, y);
-		const ViColor to_right = vi_read_vram(f, b, x + 2, y);
-		vi_track_neighbor(vi_read_vram(f, b, x - 1, y - 1), lo, hi, lo2, hi2);
-		vi_track_neighbor(vi_read_vram(f, b, x + 1, y - 1), lo, hi, lo2, hi2);
+		const ViColor to_left = read(x - 2, y);
+		const ViColor to_right = read(x + 2, y);
+		vi_track_neighbor(read(x - 1, y - 1), lo, hi, lo2, hi2);
+		vi_track_neighbor(read(x + 1, y - 1), lo, hi, lo2, hi2);
 		vi_track_neighbor(to_left, lo, hi, lo2, hi2);
 		vi_track_neighbor(to_right, lo, hi, lo2, hi2);
 		if (!bug)
 		{
-			vi_track_neighbor(vi_read_vram(f, b, x - 1, y + 1), lo, hi, lo2, hi2);
-			vi_track_neighbor(vi_read_vram(f, b, x + 1, y + 1), lo, hi, lo2, hi2);
+			vi_track_neighbor(read(x - 1, y + 1), lo, hi, lo2, hi2);
+			vi_track_neighbor(read(x + 1, y + 1), lo, hi, lo2, hi2);
 		}
 		else
 		{
@@ -193,7 +197,7 @@ RDP_HD ViColor vi_fetch_pixel(const ViFrame &f, const ViBuffers &b, int x, int y
 		{
 			for (int dx = -1; dx <= 1; dx++)
 			{
-				const ViColor c = vi_read_vram(f, b, x + dx, y + dy);
+				const ViColor c = read(x + dx, y + dy);
 				acc[0] += vi_clamp1((c.r >> 3) - base[0]);
 				acc[1] += vi_clamp1((c.g >> 3) - base[1]);
 				acc[2] += vi_clamp1((c.b >> 3) - base[2]);
@@ -203,7 +207,7 @@ RDP_HD ViColor vi_fetch_pixel(const ViFrame &f, const ViBuffers &b, int x, int y
 		{
 			for (int dx = -1; dx <= 1; dx++)
 			{
-				const ViColor c = vi_read_vram(f, b, x + dx, y + 1);
+				const ViColor c = read(x + dx, y + 1);
 				acc[0] += vi_clamp1((c.r >> 3) - base[0]);
 				acc[1] += vi_clamp1((c.g >> 3) - base[1]);
 				acc[2] += vi_clamp1((c.b >> 3) - base[2]);
@@ -213,7 +217,7 @@ RDP_HD ViColor vi_fetch_pixel(const ViFrame &f, const ViBuffers &b, int x, int y
 		{
 			for (int dx = -1; dx <= 1; dx += 2)
 			{
-				const ViColor c = vi_read_vram(f, b, x + dx, y);
+				const ViColor c = read(x + dx, y);
 				acc[0] += vi_clamp1((c.r >> 3) - base[0]);
 				acc[1] += vi_clamp1((c.g >> 3) - base[1]);
 				acc[2] += vi_clamp1((c.b >> 3) - base[2]);
@@ -228,6 +232,19 @@ RDP_HD ViColor vi_fetch_pixel(const ViFrame &f, const ViBuffers &b, int x, int y
 	}
 	out.a = mid.a;
 	return out;
+}
+
+struct ViVramReader
+{
+	const ViFrame &f;
+	const ViBuffers &b;
+	RDP_HD ViColor operator()(int x, int y) const { return vi_read_vram(f, b, x, y); }
+};
+
+RDP_HD ViColor vi_fetch_pixel(const ViFrame &f, const ViBuffers &b, int x, int y, bool bug)
+{
+	const ViVramReader read = { f, b };
+	return vi_fetch_core(f, read, x, y, bug);
 }
 
 RDP_HD int vi_median3(int l, int c, int r)
