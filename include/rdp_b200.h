@@ -130,6 +130,52 @@ void rdp_b200_host_timing(rdp_b200_processor *p, double out3[3]);
 /* The backend device handle (rdpb_device*, include/rdp_b200_backend.h) for the measurement entry points. */
 void *rdp_b200_backend_device(rdp_b200_processor *p);
 
+/* ---- RDPDUMP2 command-stream dumps (replaces the reference's rdp_dump.cpp:29-185 DumpPlayer and
+ * parallel-rdp/rdp_dump_write.cpp:34-151 RDPDumpWriter; same file format, files are interchangeable) ------------- */
+typedef struct rdp_b200_dump_player rdp_b200_dump_player;
+typedef struct rdp_b200_dump_writer rdp_b200_dump_writer;
+
+enum
+{
+	RDP_B200_DUMP_RDP_COMMAND = 2,         /* arg0 = op, words / num_words */
+	RDP_B200_DUMP_SET_VI_REGISTER = 3,     /* arg0 = register index, arg1 = value */
+	RDP_B200_DUMP_END_FRAME = 4,
+	RDP_B200_DUMP_SIGNAL_COMPLETE = 5,
+	RDP_B200_DUMP_EOF = 6,
+	RDP_B200_DUMP_UPDATE_RDRAM = 7,        /* data / size = the whole current RDRAM image */
+	RDP_B200_DUMP_UPDATE_HIDDEN_RDRAM = 9  /* data / size = the whole current hidden RDRAM image */
+};
+
+typedef struct rdp_b200_dump_event
+{
+	uint32_t kind, arg0, arg1, num_words;
+	const uint32_t *words; /* valid until the next call on the same player */
+	const uint8_t *data;
+	size_t size;
+} rdp_b200_dump_event;
+
+/* NULL when the file is missing or not an RDPDUMP2 dump of 4/8 MiB RDRAM + 4 MiB hidden RDRAM (ref: rdp_dump.cpp:60-63). */
+rdp_b200_dump_player *rdp_b200_dump_open(const char *path);
+void rdp_b200_dump_close(rdp_b200_dump_player *d);
+size_t rdp_b200_dump_rdram_size(const rdp_b200_dump_player *d);
+size_t rdp_b200_dump_hidden_rdram_size(const rdp_b200_dump_player *d);
+int rdp_b200_dump_rewind(rdp_b200_dump_player *d);
+/* Next record; 0 at the end of the file or on a malformed record (ref: DumpPlayer::iterate). */
+int rdp_b200_dump_next(rdp_b200_dump_player *d, rdp_b200_dump_event *ev);
+/* Feed records into a processor (the reference's ParallelReplayer, replayer_driver_parallel.cpp:113-160) until an
+ * END_FRAME, SIGNAL_COMPLETE or EOF record, which is returned in *stop (SIGNAL_COMPLETE flushes first).  Returns the
+ * number of RDP commands enqueued, -1 on a malformed file. */
+long rdp_b200_dump_replay(rdp_b200_dump_player *d, rdp_b200_processor *p, rdp_b200_dump_event *stop);
+
+rdp_b200_dump_writer *rdp_b200_dump_writer_open(const char *path, uint32_t rdram_size, uint32_t hidden_rdram_size);
+void rdp_b200_dump_writer_flush_dram(rdp_b200_dump_writer *w, const void *rdram, uint32_t size);
+void rdp_b200_dump_writer_flush_hidden_dram(rdp_b200_dump_writer *w, const void *hidden, uint32_t size);
+void rdp_b200_dump_writer_command(rdp_b200_dump_writer *w, uint32_t op, const uint32_t *words, uint32_t num_words);
+void rdp_b200_dump_writer_set_vi_register(rdp_b200_dump_writer *w, uint32_t reg, uint32_t value);
+void rdp_b200_dump_writer_end_frame(rdp_b200_dump_writer *w);
+void rdp_b200_dump_writer_signal_complete(rdp_b200_dump_writer *w);
+void rdp_b200_dump_writer_close(rdp_b200_dump_writer *w); /* writes EOF */
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,21 @@ def _bind(lib):
         "rdp_b200_cuda_stream": (P, [P]),
         "rdp_b200_last_tile_variant": (C.c_char_p, [P]),
         "rdp_b200_host_timing": (None, [P, P]),
+        "rdp_b200_dump_open": (P, [C.c_char_p]),
+        "rdp_b200_dump_close": (None, [P]),
+        "rdp_b200_dump_rdram_size": (SZ, [P]),
+        "rdp_b200_dump_hidden_rdram_size": (SZ, [P]),
+        "rdp_b200_dump_rewind": (C.c_int, [P]),
+        "rdp_b200_dump_next": (C.c_int, [P, P]),
+        "rdp_b200_dump_replay": (C.c_long, [P, P, P]),
+        "rdp_b200_dump_writer_open": (P, [C.c_char_p, U32, U32]),
+        "rdp_b200_dump_writer_flush_dram": (None, [P, P, U32]),
+        "rdp_b200_dump_writer_flush_hidden_dram": (None, [P, P, U32]),
+        "rdp_b200_dump_writer_command": (None, [P, U32, P, U32]),
+        "rdp_b200_dump_writer_set_vi_register": (None, [P, U32, U32]),
+        "rdp_b200_dump_writer_end_frame": (None, [P]),
+        "rdp_b200_dump_writer_signal_complete": (None, [P]),
+        "rdp_b200_dump_writer_close": (None, [P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -234,3 +249,89 @@ class CommandProcessor:
 
     def cuda_stream(self) -> int:
         return self.lib.rdp_b200_cuda_stream(self._h) or 0
+
+
+# ---- RDPDUMP2 dumps (include/rdp_b200.h; reference: rdp_dump.cpp, parallel-rdp/rdp_dump_write.cpp) -------------------
+DUMP_RDP_COMMAND, DUMP_SET_VI_REGISTER, DUMP_END_FRAME, DUMP_SIGNAL_COMPLETE, DUMP_EOF = 2, 3, 4, 5, 6
+DUMP_UPDATE_RDRAM, DUMP_UPDATE_HIDDEN_RDRAM = 7, 9
+
+
+class DumpEvent(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("arg0", C.c_uint32), ("arg1", C.c_uint32), ("num_words", C.c_uint32),
+                ("words", C.POINTER(C.c_uint32)), ("data", C.POINTER(C.c_uint8)), ("size", C.c_size_t)]
+
+
+class DumpPlayer:
+    """Mirror of RDP::DumpPlayer: iterate over the records of an RDPDUMP2 file."""
+
+    def __init__(self, path: str, library: str | None = None):
+        self.lib = load_library(library)
+        self._h = self.lib.rdp_b200_dump_open(os.fsencode(path))
+        if not self._h:
+            raise ValueError(f"{path}: not a readable RDPDUMP2 file")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.rdp_b200_dump_close(self._h)
+            self._h = None
+
+    def get_rdram_size(self) -> int:
+        return self.lib.rdp_b200_dump_rdram_size(self._h)
+
+    def get_hidden_rdram_size(self) -> int:
+        return self.lib.rdp_b200_dump_hidden_rdram_size(self._h)
+
+    def rewind(self) -> bool:
+        return bool(self.lib.rdp_b200_dump_rewind(self._h))
+
+    def next_event(self):
+        """(kind, arg0, arg1, payload) or None at the end; payload is a numpy copy of the words / image."""
+        ev = DumpEvent()
+        if not self.lib.rdp_b200_dump_next(self._h, C.byref(ev)):
+            return None
+        payload = None
+        if ev.kind == DUMP_RDP_COMMAND:
+            payload = np.ctypeslib.as_array(ev.words, shape=(ev.num_words,)).copy() if ev.num_words else np.zeros(0, np.uint32)
+        elif ev.kind in (DUMP_UPDATE_RDRAM, DUMP_UPDATE_HIDDEN_RDRAM):
+            payload = np.ctypeslib.as_array(ev.data, shape=(ev.size,)).copy()
+        return ev.kind, ev.arg0, ev.arg1, payload
+
+    def replay(self, processor: "CommandProcessor"):
+        """Feed records into `processor` up to the next END_FRAME / SIGNAL_COMPLETE / EOF: (commands, stop_kind)."""
+        ev = DumpEvent()
+        n = self.lib.rdp_b200_dump_replay(self._h, processor._h, C.byref(ev))
+        return n, (ev.kind if n >= 0 else None)
+
+
+class DumpWriter:
+    """Mirror of RDP::RDPDumpWriter."""
+
+    def __init__(self, path: str, rdram_size: int, hidden_rdram_size: int, library: str | None = None):
+        self.lib = load_library(library)
+        self._h = self.lib.rdp_b200_dump_writer_open(os.fsencode(path), rdram_size, hidden_rdram_size)
+        if not self._h:
+            raise OSError(f"cannot create {path}")
+
+    def flush_dram(self, rdram: np.ndarray):
+        self.lib.rdp_b200_dump_writer_flush_dram(self._h, rdram.ctypes.data, rdram.size)
+
+    def flush_hidden_dram(self, hidden: np.ndarray):
+        self.lib.rdp_b200_dump_writer_flush_hidden_dram(self._h, hidden.ctypes.data, hidden.size)
+
+    def emit_command(self, op: int, words: np.ndarray):
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        self.lib.rdp_b200_dump_writer_command(self._h, op, words.ctypes.data, words.size)
+
+    def set_vi_register(self, reg: int, value: int):
+        self.lib.rdp_b200_dump_writer_set_vi_register(self._h, reg, value)
+
+    def end_frame(self):
+        self.lib.rdp_b200_dump_writer_end_frame(self._h)
+
+    def signal_complete(self):
+        self.lib.rdp_b200_dump_writer_signal_complete(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.rdp_b200_dump_writer_close(self._h)
+            self._h = None

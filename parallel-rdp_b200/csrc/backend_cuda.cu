@@ -198,6 +198,63 @@ __device__ __forceinline__ void load_prim_for_shading(const PrimSetup *g, uint32
 	p.dz_compressed = uint8_t(dzw >> 16);
 }
 
+// What the front of the next tile reads first (its mask words and its pixels), as addresses to warm L1 with.  The
+// walkers issue the prefetches late in the current tile -- before the last stretch of shading -- so that the lines
+// are still resident when the next tile starts (a whole tile ahead they would be evicted again).
+constexpr uint32_t kGatherWords = 8; // fine-mask words one lane owns in the single-round gather
+
+struct NextTilePrefetch
+{
+	uint32_t tile;   // 0xffffffff: no next tile
+	uint32_t staged; // tile whose mask words stage_masks() copied to shared memory, 0xffffffff: none
+	bool pending;    // issue() still to run for `tile`
+
+	// L1 prefetch of the next tile's pixels (and of its mask words unless they get staged).
+	__device__ __forceinline__ void issue(const PassBuffers &b, const FbInfo &fb, uint32_t fmt, uint32_t lane, bool masks)
+	{
+		if (!pending || tile == 0xffffffffu)
+			return;
+		pending = false;
+		const uint32_t words_per_lane = (fb.mask_stride + 31u) / 32u;
+		if (masks && words_per_lane <= kGatherWords && lane * words_per_lane < fb.mask_stride)
+			prefetch_l1(b.fine_mask + size_t(tile) * fb.mask_stride + lane * words_per_lane);
+		const uint32_t ax = (tile % fb.tiles_x) * kTileW + (lane & 7u), ay = (tile / fb.tiles_x) * kTileH + (lane >> 3);
+		if (ax < fb.width && ay < fb.height)
+		{
+			const uint32_t pix = fb.width * ay + ax;
+			const uint32_t shift = fmt == FB_RGBA8888 ? 2u : ((fmt == FB_RGBA5551 || fmt == FB_IA88) ? 1u : 0u);
+			const uint32_t caddr = (fb.color_addr + (pix << shift)) & (fb.rdram_size - 1u);
+			const uint32_t daddr = (fb.depth_addr + (pix << 1)) & (fb.rdram_size - 1u);
+			prefetch_l1(b.rdram + caddr);
+			prefetch_l1(b.hidden + (caddr >> 1));
+			prefetch_l1(b.rdram + daddr);
+			prefetch_l1(b.hidden + (daddr >> 1));
+		}
+	}
+
+	// Asynchronous copy (cp.async, no registers held) of the next tile's mask words into `dst[lane * kGatherWords + i]`,
+	// a shared-memory array the current tile no longer needs; the tile loop waits for the copy when it gets there.
+	__device__ __forceinline__ void stage_masks(const PassBuffers &b, const FbInfo &fb, uint32_t lane, uint32_t *dst)
+	{
+		const uint32_t words_per_lane = (fb.mask_stride + 31u) / 32u;
+		if (tile == 0xffffffffu || words_per_lane > kGatherWords)
+			return;
+		const uint32_t first = lane * words_per_lane;
+		const uint32_t *src = b.fine_mask + size_t(tile) * fb.mask_stride + first;
+		const uint32_t sdst = uint32_t(__cvta_generic_to_shared(dst + lane * kGatherWords));
+#pragma unroll
+		for (uint32_t i = 0; i < kGatherWords; i++)
+		{
+			if (i < words_per_lane && first + i < fb.mask_stride)
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 4u * i), "l"(src + i) : "memory");
+			else
+				dst[lane * kGatherWords + i] = 0u;
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		staged = tile;
+	}
+};
+
 template <class S>
 struct TileWalker
 {
@@ -210,6 +267,7 @@ struct TileWalker
 	int x0, y0, x, y;
 	uint32_t inside_mask;
 	uint32_t shaded;
+	NextTilePrefetch next;
 
 	// Mask + shade phases over list[0..n).
 	__device__ __forceinline__ void run(const uint16_t *list, uint32_t n)
@@ -252,6 +310,8 @@ struct TileWalker
 
 			// ---- shade phase: live primitives in order ----
 			uint32_t live = __ballot_sync(0xffffffffu, pixmask != 0u);
+			if (c + 32u >= n)
+				next.issue(b, fb, view.fmt, lane, true);
 			while (live)
 			{
 				const int j = __ffs(int(live)) - 1;
@@ -352,6 +412,8 @@ struct DeferredWalker
 	int x0, y0, x, y;
 	uint32_t inside_mask;
 	uint32_t shaded;
+	NextTilePrefetch next;
+	bool stage_next = false; // the whole tile is one run() call: its end may stage the next tile's masks in w.desc
 
 	__device__ __forceinline__ uint32_t slot_of(uint32_t entry, uint32_t lt) const
 	{
@@ -522,6 +584,9 @@ struct DeferredWalker
 				}
 				__syncwarp();
 
+				if (c + 32u >= n && live == 0u)
+					next.issue(b, fb, view.fmt, lane, !stage_next);
+
 				// ---- C: shade the survivors ----
 				for (uint32_t k2 = lane; k2 < n2; k2 += 32u)
 				{
@@ -540,6 +605,10 @@ struct DeferredWalker
 					w.put(k, ry);
 				}
 				__syncwarp();
+
+				// The survivor list is consumed: its storage takes the next tile's mask words while D runs.
+				if (stage_next && c + 32u >= n && live == 0u)
+					next.stage_masks(b, fb, lane, w.desc);
 
 				// ---- D: ordered blend stage, one pixel per lane ----
 				for (uint32_t t = surv; t; t &= t - 1u)
@@ -560,14 +629,23 @@ template <class S>
 __device__ __forceinline__ TileWalker<S> make_tile_walker(const PassBuffers &b, const FbInfo &fb, const ShadeContext &ctx, const FbView &view,
                                                           PixelState &px, TileShared<S, false> &, uint32_t lane, int x0, int y0)
 {
-	return TileWalker<S>{ b, fb, ctx, view, px, lane, x0, y0, 0, 0, 0u, 0u };
+	return TileWalker<S>{ b, fb, ctx, view, px, lane, x0, y0, 0, 0, 0u, 0u, { 0xffffffffu, 0xffffffffu, false } };
 }
 template <class S>
 __device__ __forceinline__ DeferredWalker<S> make_tile_walker(const PassBuffers &b, const FbInfo &fb, const ShadeContext &ctx, const FbView &view,
                                                               PixelState &px, TileShared<S, true> &sw, uint32_t lane, int x0, int y0)
 {
-	return DeferredWalker<S>{ b, fb, ctx, view, px, sw, lane, x0, y0, 0, 0, 0u, 0u };
+	return DeferredWalker<S>{ b, fb, ctx, view, px, sw, lane, x0, y0, 0, 0, 0u, 0u, { 0xffffffffu, 0xffffffffu, false } };
 }
+
+template <class S>
+__device__ __forceinline__ void allow_staging(TileWalker<S> &) {}
+template <class S>
+__device__ __forceinline__ void allow_staging(DeferredWalker<S> &w) { w.stage_next = true; }
+template <class S>
+__device__ __forceinline__ const uint32_t *staged_words(const TileShared<S, false> &) { return nullptr; }
+template <class S>
+__device__ __forceinline__ const uint32_t *staged_words(const TileShared<S, true> &sw) { return sw.desc; }
 
 template <class S, bool DEFERRED = false>
 __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blocks_per_sm_deferred : S::min_blocks_per_sm) k_tiles(PassBuffers b, FbInfo fb)
@@ -594,11 +672,11 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 	// the contiguous words [L * words_per_lane, (L + 1) * words_per_lane), so one load round and one warp prefix sum
 	// list the whole tile in submission order.  Larger passes, and tiles with more than kTileListCapacity entries,
 	// take the coarse-mask walk below.
-	constexpr uint32_t kGatherWords = 8;
 	const uint32_t words_per_lane = (fb.mask_stride + 31u) / 32u;
 	const bool one_round = words_per_lane <= kGatherWords;
 
 	uint32_t tiles_done = 0, shaded_total = 0;
+	uint32_t staged_tile = 0xffffffffu; // tile whose mask words wait in shared memory (deferred walker only)
 	// The tile counter is read one tile ahead: the atomic's round trip overlaps the current tile's work.
 	uint32_t next_tile = 0;
 	if (lane == 0)
@@ -619,11 +697,27 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 			uint32_t wv[kGatherWords];
 			const uint32_t first = lane * words_per_lane;
 			uint32_t n = 0;
-#pragma unroll
-			for (uint32_t i = 0; i < kGatherWords; i++)
+			if (staged_tile == tile)
 			{
-				wv[i] = (i < words_per_lane && first + i < fb.mask_stride) ? fine[first + i] : 0u;
-				n += uint32_t(__popc(wv[i]));
+				// The previous tile's walker copied these words to shared memory while it was blending.
+				asm volatile("cp.async.wait_all;" ::: "memory");
+				__syncwarp();
+#pragma unroll
+				for (uint32_t i = 0; i < kGatherWords; i++)
+				{
+					wv[i] = staged_words(sw)[lane * kGatherWords + i];
+					n += uint32_t(__popc(wv[i]));
+				}
+				__syncwarp();
+			}
+			else
+			{
+#pragma unroll
+				for (uint32_t i = 0; i < kGatherWords; i++)
+				{
+					wv[i] = (i < words_per_lane && first + i < fb.mask_stride) ? fine[first + i] : 0u;
+					n += uint32_t(__popc(wv[i]));
+				}
 			}
 			if (__ballot_sync(0xffffffffu, n != 0u) == 0u)
 				continue;
@@ -675,34 +769,21 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 		walk.inside_mask = __ballot_sync(0xffffffffu, walk.x < int(fb.width) && walk.y < int(fb.height));
 		pass_pixel_begin<S>(b, fb, view, px, walk.x, walk.y);
 
-		// Warm L1 with what the front of the next tile reads (its mask words, its pixels): those are the first links of
-		// the chain of dependent loads every tile starts with.  The tile index was requested a whole tile ago.
+		// The walker prefetches what the front of the next tile reads late in this tile.  (The tile index was requested
+		// a whole tile ago, so reading it here does not wait.)
 		{
 			const uint32_t ahead = __shfl_sync(0xffffffffu, next_tile, 0);
-			if (ahead < num_tiles)
-			{
-				if (one_round && lane * words_per_lane < fb.mask_stride)
-					prefetch_l1(b.fine_mask + size_t(ahead) * fb.mask_stride + lane * words_per_lane);
-				const uint32_t ax = (ahead % fb.tiles_x) * kTileW + (lane & 7u), ay = (ahead / fb.tiles_x) * kTileH + (lane >> 3);
-				if (ax < fb.width && ay < fb.height)
-				{
-					const uint32_t pix = fb.width * ay + ax;
-					const uint32_t shift = view.fmt == FB_RGBA8888 ? 2u : ((view.fmt == FB_RGBA5551 || view.fmt == FB_IA88) ? 1u : 0u);
-					const uint32_t caddr = (fb.color_addr + (pix << shift)) & (fb.rdram_size - 1u);
-					const uint32_t daddr = (fb.depth_addr + (pix << 1)) & (fb.rdram_size - 1u);
-					prefetch_l1(b.rdram + caddr);
-					prefetch_l1(b.hidden + (caddr >> 1));
-					prefetch_l1(b.rdram + daddr);
-					prefetch_l1(b.hidden + (daddr >> 1));
-				}
-			}
+			walk.next.tile = ahead < num_tiles ? ahead : 0xffffffffu;
+			walk.next.pending = true;
 		}
 
 		if (listed)
 		{
 			__syncwarp();
+			allow_staging(walk);
 			walk.run(list, listed);
 			__syncwarp();
+			staged_tile = walk.next.staged;
 		}
 		else
 		{

@@ -1,6 +1,7 @@
 // c_api.cpp -- extern "C" wrappers declared in include/rdp_b200.h over RDP::CommandProcessor.
 #include "rdp_b200.h"
 #include "rdp_device.hpp"
+#include "rdp_dump.hpp"
 #include <string.h>
 
 using namespace RDP;
@@ -12,6 +13,15 @@ struct rdp_b200_processor
 		: impl(DeviceConfig{dev}, rdram, off, size, hidden, flags)
 	{
 	}
+};
+
+struct rdp_b200_dump_player
+{
+	DumpPlayer impl;
+};
+struct rdp_b200_dump_writer
+{
+	RDPDumpWriter impl;
 };
 
 static ScanoutOptions convert_options(const rdp_b200_scanout_options *o)
@@ -133,4 +143,91 @@ void rdp_b200_host_timing(rdp_b200_processor *p, double out3[3]) { p->impl.get_h
 void *rdp_b200_backend_device(rdp_b200_processor *p) { return p->impl.get_backend_device(); }
 const char *rdp_b200_last_tile_variant(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_last_tile_variant(p->impl.get_backend_device()) : ""; }
 void *rdp_b200_cuda_stream(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_stream(p->impl.get_backend_device()) : nullptr; }
+
+// ---- RDPDUMP2 ------------------------------------------------------------------------------------------------
+rdp_b200_dump_player *rdp_b200_dump_open(const char *path)
+{
+	auto *d = new rdp_b200_dump_player;
+	if (!d->impl.load_dump(path))
+	{
+		delete d;
+		return nullptr;
+	}
+	return d;
+}
+void rdp_b200_dump_close(rdp_b200_dump_player *d) { delete d; }
+size_t rdp_b200_dump_rdram_size(const rdp_b200_dump_player *d) { return d->impl.get_rdram_size(); }
+size_t rdp_b200_dump_hidden_rdram_size(const rdp_b200_dump_player *d) { return d->impl.get_hidden_rdram_size(); }
+int rdp_b200_dump_rewind(rdp_b200_dump_player *d) { return d->impl.rewind() ? 1 : 0; }
+
+int rdp_b200_dump_next(rdp_b200_dump_player *d, rdp_b200_dump_event *ev)
+{
+	DumpEvent e;
+	if (!d->impl.next_event(e))
+		return 0;
+	ev->kind = uint32_t(e.kind);
+	ev->arg0 = e.arg0;
+	ev->arg1 = e.arg1;
+	ev->num_words = e.num_words;
+	ev->words = e.words;
+	ev->data = e.data;
+	ev->size = e.size;
+	return 1;
+}
+
+long rdp_b200_dump_replay(rdp_b200_dump_player *d, rdp_b200_processor *p, rdp_b200_dump_event *stop)
+{
+	long commands = 0;
+	rdp_b200_dump_event ev;
+	while (rdp_b200_dump_next(d, &ev))
+	{
+		switch (ev.kind)
+		{
+		case RDP_B200_DUMP_RDP_COMMAND:
+			p->impl.enqueue_command(ev.num_words, ev.words);
+			commands++;
+			break;
+		case RDP_B200_DUMP_SET_VI_REGISTER:
+			p->impl.set_vi_register(VIRegister(ev.arg0), ev.arg1);
+			break;
+		case RDP_B200_DUMP_UPDATE_RDRAM:
+			p->impl.idle();
+			memcpy(p->impl.begin_read_rdram(), ev.data, ev.size < p->impl.get_rdram_size() ? ev.size : p->impl.get_rdram_size());
+			p->impl.end_write_rdram();
+			break;
+		case RDP_B200_DUMP_UPDATE_HIDDEN_RDRAM:
+			p->impl.idle();
+			memcpy(p->impl.begin_read_hidden_rdram(), ev.data,
+			       ev.size < p->impl.get_hidden_rdram_size() ? ev.size : p->impl.get_hidden_rdram_size());
+			p->impl.end_write_hidden_rdram();
+			break;
+		case RDP_B200_DUMP_SIGNAL_COMPLETE:
+			p->impl.flush();
+			/* fall through */
+		default: // END_FRAME, EOF
+			if (stop)
+				*stop = ev;
+			return commands;
+		}
+	}
+	return -1;
+}
+
+rdp_b200_dump_writer *rdp_b200_dump_writer_open(const char *path, uint32_t rdram_size, uint32_t hidden_rdram_size)
+{
+	auto *w = new rdp_b200_dump_writer;
+	if (!w->impl.init(path, rdram_size, hidden_rdram_size))
+	{
+		delete w;
+		return nullptr;
+	}
+	return w;
+}
+void rdp_b200_dump_writer_flush_dram(rdp_b200_dump_writer *w, const void *rdram, uint32_t size) { w->impl.flush_dram(rdram, size); }
+void rdp_b200_dump_writer_flush_hidden_dram(rdp_b200_dump_writer *w, const void *hidden, uint32_t size) { w->impl.flush_hidden_dram(hidden, size); }
+void rdp_b200_dump_writer_command(rdp_b200_dump_writer *w, uint32_t op, const uint32_t *words, uint32_t n) { w->impl.emit_command(op, words, n); }
+void rdp_b200_dump_writer_set_vi_register(rdp_b200_dump_writer *w, uint32_t reg, uint32_t value) { w->impl.set_vi_register(reg, value); }
+void rdp_b200_dump_writer_end_frame(rdp_b200_dump_writer *w) { w->impl.end_frame(); }
+void rdp_b200_dump_writer_signal_complete(rdp_b200_dump_writer *w) { w->impl.signal_complete(); }
+void rdp_b200_dump_writer_close(rdp_b200_dump_writer *w) { delete w; }
 }
