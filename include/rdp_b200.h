@@ -130,6 +130,16 @@ void rdp_b200_host_timing(rdp_b200_processor *p, double out3[3]);
 /* The backend device handle (rdpb_device*, include/rdp_b200_backend.h) for the measurement entry points. */
 void *rdp_b200_backend_device(rdp_b200_processor *p);
 
+/* ---- Internal upscaling (RDP_B200_FLAG_UPSCALING_2X/4X/8X; ref rdp_device.hpp:43-51, rdp_renderer.cpp:545-600) -------
+ * Eligible passes are rendered a second time at S x S the resolution into a separate upscaled domain of S*S RDRAM
+ * "slices"; native RDRAM keeps the bit-exact native-resolution result.  Upscaled pixel (x, y) of a framebuffer is
+ * native pixel (x / S, y / S) of slice (y % S) * S + x % S (ref shaders/memory_interfacing.h:286-302). */
+unsigned rdp_b200_upscaling_factor(rdp_b200_processor *p); /* 1 when off */
+uint64_t rdp_b200_upscaled_pass_count(rdp_b200_processor *p);
+/* Idles, then copies the upscaled domain to the host: S*S images of get_rdram_size() bytes into rdram_dst and S*S
+ * images of get_rdram_size() / 2 bytes into hidden_dst (either may be NULL).  Returns 0, -1 when upscaling is off. */
+int rdp_b200_read_upscaled_rdram(rdp_b200_processor *p, void *rdram_dst, void *hidden_dst);
+
 /* ---- RDPDUMP2 command-stream dumps (replaces the reference's rdp_dump.cpp:29-185 DumpPlayer and
  * parallel-rdp/rdp_dump_write.cpp:34-151 RDPDumpWriter; same file format, files are interchangeable) ------------- */
 typedef struct rdp_b200_dump_player rdp_b200_dump_player;

@@ -98,6 +98,17 @@ int rdpb_wait(rdpb_device *dev, uint64_t value);     /* blocks the calling threa
 int rdpb_sync(rdpb_device *dev);
 void *rdpb_stream(rdpb_device *dev);                 /* cudaStream_t for interop/benchmark timing */
 
+/* ---- Internal upscaling (replaces rdp_renderer.cpp:545-600 buffers, :1943-2084 domain updates) ------------------
+ * The upscaled domain is S*S "slices" of RDRAM and hidden RDRAM (S = 1 << scale_log2, 1..3) plus a native-sized
+ * shadow of RDRAM.  A pass that is rendered upscaled is submitted twice: at native resolution as always, bracketed by
+ * rdpb_launch_upscale_sync(PRE / POST), then again through rdpb_launch_span_bin / rdpb_launch_tiles with an FbInfo whose
+ * scale_log2 is set and whose width / height / tile counts are in upscaled pixels. */
+int rdpb_upscaling_init(rdpb_device *dev, uint32_t scale_log2);
+enum { RDPB_UPSCALE_SYNC_PRE = 0, RDPB_UPSCALE_SYNC_POST = 1 };
+int rdpb_launch_upscale_sync(rdpb_device *dev, const void *native_fb_info, int stage);
+/* Blocking read-back of the whole upscaled domain: S*S images of rdram_size bytes, S*S images of rdram_size / 2 bytes. */
+int rdpb_upscaled_read(rdpb_device *dev, void *rdram_dst, void *hidden_dst);
+
 /* Instrumentation: number of kernels launched since creation. */
 uint64_t rdpb_launch_count(rdpb_device *dev);
 

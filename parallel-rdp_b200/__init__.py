@@ -70,6 +70,9 @@ def _bind(lib):
         "rdp_b200_cuda_stream": (P, [P]),
         "rdp_b200_last_tile_variant": (C.c_char_p, [P]),
         "rdp_b200_host_timing": (None, [P, P]),
+        "rdp_b200_upscaling_factor": (C.c_uint, [P]),
+        "rdp_b200_upscaled_pass_count": (U64, [P]),
+        "rdp_b200_read_upscaled_rdram": (C.c_int, [P, P, P]),
         "rdp_b200_dump_open": (P, [C.c_char_p]),
         "rdp_b200_dump_close": (None, [P]),
         "rdp_b200_dump_rdram_size": (SZ, [P]),
@@ -243,6 +246,24 @@ class CommandProcessor:
         out = (C.c_double * 3)()
         self.lib.rdp_b200_host_timing(self._h, out)
         return {"ring_busy_s": out[0], "submit_s": out[1], "scanout_s": out[2], "parse_s": out[0] - out[1] - out[2]}
+
+    def upscaling_factor(self) -> int:
+        return self.lib.rdp_b200_upscaling_factor(self._h)
+
+    def upscaled_pass_count(self) -> int:
+        return self.lib.rdp_b200_upscaled_pass_count(self._h)
+
+    def read_upscaled_rdram(self):
+        """(rdram, hidden): uint8 arrays of shape (S*S, rdram_size) and (S*S, rdram_size // 2) -- one row per slice."""
+        s = self.upscaling_factor()
+        if s == 1:
+            raise RuntimeError("internal upscaling is off")
+        n = self.lib.rdp_b200_get_rdram_size(self._h)
+        rdram = np.empty((s * s, n), np.uint8)
+        hidden = np.empty((s * s, n // 2), np.uint8)
+        if self.lib.rdp_b200_read_upscaled_rdram(self._h, rdram.ctypes.data, hidden.ctypes.data) != 0:
+            raise RuntimeError("rdp_b200_read_upscaled_rdram failed")
+        return rdram, hidden
 
     def last_tile_variant(self) -> str:
         return self.lib.rdp_b200_last_tile_variant(self._h).decode()

@@ -103,30 +103,39 @@ __global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
 	const uint32_t prim = job & 0xffffu;
 	const PrimSetup &p = b.prims[prim];
 
+	// With internal upscaling (fb.scale_log2) the job's 32 native lines are 32 * S lines of the upscaled image,
+	// walked in S rounds of 32; the upscaled tile kernel's tile counter is reset here, in stream order after the
+	// native tile kernel that left it exhausted.
+	const int sl = int(fb.scale_log2);
+	if (sl && blockIdx.x == 0 && threadIdx.x == 0)
+		b.job_counter[1] = 0;
 	const int first = int(p.line_lo) & ~int(kTileH - 1);
-	const int y = first + int(job >> 16) * int(kSpanJobLines) + lane;
 	const int sub = lane & int(kTileH - 1);
+	for (int round = 0; round < (1 << sl); round++)
+	{
+		const int y = ((first + int(job >> 16) * int(kSpanJobLines)) << sl) + round * 32 + lane;
 
-	int lo, hi;
-	pass_span_line(b, fb, p, y, lo, hi);
-	int mn = lo <= hi ? lo : 0x7fffffff;
-	int mx = lo <= hi ? hi : -1;
+		int lo, hi;
+		pass_span_line(b, fb, p, y, lo, hi, sl);
+		int mn = lo <= hi ? lo : 0x7fffffff;
+		int mx = lo <= hi ? hi : -1;
 #pragma unroll
-	for (int off = 1; off < int(kTileH); off <<= 1)
-	{
-		mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-		mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-	}
-	if (mn <= mx)
-	{
-		const uint32_t group = prim >> 5, bit = 1u << (prim & 31u);
-		const uint32_t cgroup = group >> 5, cbit = 1u << (group & 31u);
-		const uint32_t row = uint32_t(y / int(kTileH)) * fb.tiles_x;
-		for (int tx = (mn >> 3) + sub; tx <= (mx >> 3); tx += int(kTileH))
+		for (int off = 1; off < int(kTileH); off <<= 1)
 		{
-			const size_t tile = row + uint32_t(tx);
-			atomicOr(&b.fine_mask[tile * fb.mask_stride + group], bit);
-			atomicOr(&b.coarse_mask[tile * fb.coarse_stride + cgroup], cbit);
+			mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+			mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+		}
+		if (mn <= mx)
+		{
+			const uint32_t group = prim >> 5, bit = 1u << (prim & 31u);
+			const uint32_t cgroup = group >> 5, cbit = 1u << (group & 31u);
+			const uint32_t row = uint32_t(y / int(kTileH)) * fb.tiles_x;
+			for (int tx = (mn >> 3) + sub; tx <= (mx >> 3); tx += int(kTileH))
+			{
+				const size_t tile = row + uint32_t(tx);
+				atomicOr(&b.fine_mask[tile * fb.mask_stride + group], bit);
+				atomicOr(&b.coarse_mask[tile * fb.coarse_stride + cgroup], cbit);
+			}
 		}
 	}
 }
@@ -219,7 +228,7 @@ struct NextTilePrefetch
 		if (masks && words_per_lane <= kGatherWords && lane * words_per_lane < fb.mask_stride)
 			prefetch_l1(b.fine_mask + size_t(tile) * fb.mask_stride + lane * words_per_lane);
 		const uint32_t ax = (tile % fb.tiles_x) * kTileW + (lane & 7u), ay = (tile / fb.tiles_x) * kTileH + (lane >> 3);
-		if (ax < fb.width && ay < fb.height)
+		if (ax < fb.width && ay < fb.height && fb.scale_log2 == 0u)
 		{
 			const uint32_t pix = fb.width * ay + ax;
 			const uint32_t shift = fmt == FB_RGBA8888 ? 2u : ((fmt == FB_RGBA5551 || fmt == FB_IA88) ? 1u : 0u);
@@ -268,6 +277,7 @@ struct TileWalker
 	uint32_t inside_mask;
 	uint32_t shaded;
 	NextTilePrefetch next;
+	int sl = 0; // log2 of the internal upscaling factor: non-zero only in the upscaled instantiation of k_tiles
 
 	// Mask + shade phases over list[0..n).
 	__device__ __forceinline__ void run(const uint16_t *list, uint32_t n)
@@ -282,14 +292,14 @@ struct TileWalker
 				my_prim = list[c + lane];
 				const PrimSetup *pp = b.prims + my_prim;
 				hdr = *reinterpret_cast<const uint4 *>(&pp->span_base);
-				const int line_lo = int(int16_t(hdr.z & 0xffffu)), line_hi = int(int16_t(hdr.z >> 16));
+				const int line_lo = int(int16_t(hdr.z & 0xffffu)) << sl, line_hi = (int(int16_t(hdr.z >> 16)) << sl) + ((1 << sl) - 1);
 #pragma unroll
 				for (int r = 0; r < int(kTileH); r++)
 				{
 					const int yy = y0 + r;
 					if (yy < line_lo || yy > line_hi)
 						continue;
-					const Span *sp = b.spans + (hdr.x + uint32_t(yy - line_lo));
+					const Span *sp = b.spans + ((hdr.x << sl) + uint32_t(yy - line_lo));
 					const uint2 sh = *reinterpret_cast<const uint2 *>(&sp->start_x);
 					if ((sh.y >> 16) == 0u) // !valid
 						continue;
@@ -324,9 +334,9 @@ struct TileWalker
 				const uint32_t dzw = __shfl_sync(0xffffffffu, hdr.w, j);
 				if ((pm >> lane) & 1u)
 				{
-					const int line_lo = int(int16_t(lines & 0xffffu));
+					const int line_lo = int(int16_t(lines & 0xffffu)) << sl;
 					Span sp;
-					load_span(b.spans + (span_base + uint32_t(y - line_lo)), sp);
+					load_span(b.spans + ((span_base << sl) + uint32_t(y - line_lo)), sp);
 					PrimSetup p;
 					load_prim_for_shading(b.prims + prim, span_base, ids, lines, dzw, p);
 					const PassState &st = b.states[ids & 0xffffu];
@@ -639,6 +649,10 @@ __device__ __forceinline__ DeferredWalker<S> make_tile_walker(const PassBuffers 
 }
 
 template <class S>
+__device__ __forceinline__ void set_walker_scale(TileWalker<S> &w, int sl) { w.sl = sl; }
+template <class S>
+__device__ __forceinline__ void set_walker_scale(DeferredWalker<S> &, int) {}
+template <class S>
 __device__ __forceinline__ void allow_staging(TileWalker<S> &) {}
 template <class S>
 __device__ __forceinline__ void allow_staging(DeferredWalker<S> &w) { w.stage_next = true; }
@@ -647,9 +661,12 @@ __device__ __forceinline__ const uint32_t *staged_words(const TileShared<S, fals
 template <class S>
 __device__ __forceinline__ const uint32_t *staged_words(const TileShared<S, true> &sw) { return sw.desc; }
 
-template <class S, bool DEFERRED = false>
+template <class S, bool DEFERRED = false, bool UPSCALED = false>
 __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blocks_per_sm_deferred : S::min_blocks_per_sm) k_tiles(PassBuffers b, FbInfo fb)
 {
+	static_assert(!(DEFERRED && UPSCALED), "upscaled passes run the in-order walker");
+	// A literal 0 everywhere but in the upscaled instantiation: the scale shifts fold away.
+	const int sl = UPSCALED ? int(fb.scale_log2) : 0;
 	__shared__ TileShared<S, DEFERRED> s_warp[kTileWarpsPerBlock];
 	TileShared<S, DEFERRED> &sw = s_warp[threadIdx.x >> 5];
 	uint16_t *list = sw.list;
@@ -664,6 +681,7 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 	ctx.tmem = b.tmem_instances;
 	ctx.fb_fmt = resolve_fb_fmt<S>(fb.fmt);
 	ctx.base_prim_index = fb.base_prim_index;
+	ctx.scale_log2 = sl;
 
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 		b.job_counter[0] = 0; // this pass's span jobs are consumed; the next pass allocates from zero
@@ -767,7 +785,8 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 		walk.x = walk.x0 + int(lane & 7u);
 		walk.y = walk.y0 + int(lane >> 3);
 		walk.inside_mask = __ballot_sync(0xffffffffu, walk.x < int(fb.width) && walk.y < int(fb.height));
-		pass_pixel_begin<S>(b, fb, view, px, walk.x, walk.y);
+		set_walker_scale(walk, sl);
+		pass_pixel_begin<S>(b, fb, view, px, walk.x, walk.y, sl);
 
 		// The walker prefetches what the front of the next tile reads late in this tile.  (The tile index was requested
 		// a whole tile ago, so reading it here does not wait.)
@@ -840,7 +859,7 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 		}
 		shaded_total += walk.shaded;
 
-		pass_pixel_end(fb, view, px, walk.x, walk.y);
+		pass_pixel_end(fb, view, px, walk.x, walk.y, sl);
 	}
 
 	// One atomic per warp keeps the metrics essentially free.
@@ -943,6 +962,13 @@ __global__ void __launch_bounds__(256) k_fill_pass(PassBuffers b, FbInfo fb)
 		atomicAdd(&counter_slot(b, blockIdx.x + 5u * blockIdx.y)[threadIdx.x], (unsigned long long)s_count[threadIdx.x]);
 }
 
+// Internal upscaling: PRE / POST synchronisation of the upscaled domain with native RDRAM (rdp_pass.cuh,
+// upscale_sync_pixel), one thread per framebuffer pixel.
+__global__ void __launch_bounds__(256) k_upscale_sync(UpscaleSync u, int post)
+{
+	upscale_sync_pixel(u, blockIdx.x * blockDim.x + threadIdx.x, post != 0);
+}
+
 // VI filter: a 32x8 block first decodes its framebuffer neighbourhood (38 x 10 pixels: the AA / dither filters
 // reach two columns and one row out, and the divot needs the filter result one more column out) into shared
 // memory, computes the AA / dither-reconstruction result ("fetch") of its pixels plus one halo column on each
@@ -1032,7 +1058,11 @@ static TileVariant make_variant(const char *name)
 
 #include "rdp_variants.inc"
 
-static_assert(sizeof(kTileVariants) / sizeof(kTileVariants[0]) <= 32, "grow rdpb_device::variant_blocks_per_sm");
+static_assert(sizeof(kTileVariants) / sizeof(kTileVariants[0]) <= 31, "grow rdpb_device::variant_blocks_per_sm (slot 31 is the upscaled kernel)");
+
+// Upscaled passes: the dynamic in-order kernel with run-time scale (one instantiation serves 2x / 4x / 8x).
+static const TileVariant kUpscaledVariant = { "generic/upscaled", ~0u, 0u, ~0u, 0u, 0x1fu, ~0u, false, 0ull, 0u, 0u, false,
+	                                          &k_tiles<SpecGeneric, false, true> };
 
 // Not a tile kernel: fill-only passes of at most kFillPassMaxPrims primitives (launched per pixel, see k_fill_pass).
 static const TileVariant kFillPassVariant = { "fill-pass", 0u, 0u, 0u, 0u, 0x1fu, 0u, false, 0ull, 0u, 0u, false, &k_fill_pass };
@@ -1042,6 +1072,8 @@ static const TileVariant kFillPassVariant = { "fill-pass", 0u, 0u, 0u, 0u, 0x1fu
 // pass through the fully dynamic deferred kernel (how the conformance suites exercise it).
 static const TileVariant *pick_tile_variant(const PassSummary *sum, const FbInfo &fb)
 {
+	if (fb.scale_log2)
+		return &kUpscaledVariant;
 	const uint32_t fmt = fb.fmt;
 	const size_t n = sizeof(kTileVariants) / sizeof(kTileVariants[0]);
 	if (!sum || getenv("RDP_B200_FORCE_GENERIC"))
@@ -1082,6 +1114,7 @@ enum OpKind
 	GOP_SPAN = RDPB_KERNEL_SPAN_BIN,
 	GOP_TILES = RDPB_KERNEL_TILES,
 	GOP_VI = RDPB_KERNEL_VI_FILTER, // issues filter + scale
+	GOP_UPSCALE_SYNC = 100,         // PRE / POST synchronisation of the upscaled domain (count = stage)
 };
 
 struct GpuOp
@@ -1132,6 +1165,11 @@ struct rdpb_device
 	uint8_t *d_inputs[kStagingSlots] = {};  // records | states | texture-load descriptors
 	PrimSetup *d_prims = nullptr;
 	Span *d_spans = nullptr;
+	// internal upscaling: S*S slices of RDRAM / hidden RDRAM, the native-sized shadow, the upscaled pass's spans + masks
+	uint32_t scale_log2 = 0;
+	uint8_t *up_rdram = nullptr, *up_hidden = nullptr, *up_reference = nullptr;
+	Span *up_spans = nullptr;
+	uint32_t *up_fine = nullptr, *up_coarse = nullptr;
 	uint32_t *d_fine = nullptr, *d_coarse = nullptr;
 	uint32_t *d_jobs = nullptr, *d_job_counter = nullptr;
 
@@ -1191,6 +1229,15 @@ struct rdpb_device
 		b.hidden = hidden;
 		b.blend_lut = blend_lut;
 		b.counters = d_counters;
+		if (op.fb.scale_log2)
+		{
+			// An upscaled pass renders into the upscaled domain from its own spans and masks.
+			b.spans = up_spans;
+			b.fine_mask = up_fine;
+			b.coarse_mask = up_coarse;
+			b.rdram = up_rdram;
+			b.hidden = up_hidden;
+		}
 		return b;
 	}
 };
@@ -1268,7 +1315,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		}
 		const uint32_t tiles = op.fb.tiles_x * op.fb.tiles_y;
 		// Persistent grid: exactly as many blocks as can be resident (occupancy of this instantiation x SMs).
-		const size_t vi = size_t(op.variant - kTileVariants);
+		const size_t vi = op.variant == &kUpscaledVariant ? 31 : size_t(op.variant - kTileVariants);
 		if (!dev->variant_blocks_per_sm[vi])
 		{
 			int n = 0;
@@ -1280,6 +1327,25 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		const uint32_t blocks = std::min((tiles + kTileWarpsPerBlock - 1) / kTileWarpsPerBlock, dev->num_sms * per_sm);
 		op.variant->kernel<<<blocks, kTileWarpsPerBlock * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
 		prof_end(dev, s);
+		dev->launches++;
+		break;
+	}
+	case GOP_UPSCALE_SYNC:
+	{
+		UpscaleSync u;
+		u.rdram = dev->rdram;
+		u.hidden = dev->hidden;
+		u.reference = dev->up_reference;
+		u.up_rdram = dev->up_rdram;
+		u.up_hidden = dev->up_hidden;
+		u.rdram_size = op.fb.rdram_size;
+		u.num_slices = 1u << (2 * dev->scale_log2);
+		u.size_log2 = op.fb.fmt == FB_RGBA8888 ? 2u : ((op.fb.fmt == FB_RGBA5551 || op.fb.fmt == FB_IA88) ? 1u : 0u);
+		u.fb_index = op.fb.color_addr >> u.size_log2;
+		u.depth_index = op.fb.depth_addr >> 1;
+		u.num_pixels = op.fb.width * op.fb.height;
+		u.alias = op.fb.color_addr == op.fb.depth_addr;
+		k_upscale_sync<<<(u.num_pixels + 255u) / 256u, 256, 0, dev->stream>>>(u, int(op.count));
 		dev->launches++;
 		break;
 	}
@@ -1502,6 +1568,12 @@ void rdpb_device_destroy(rdpb_device *dev)
 	}
 	cudaFree(dev->d_prims);
 	cudaFree(dev->d_spans);
+	cudaFree(dev->up_rdram);
+	cudaFree(dev->up_hidden);
+	cudaFree(dev->up_reference);
+	cudaFree(dev->up_spans);
+	cudaFree(dev->up_fine);
+	cudaFree(dev->up_coarse);
 	cudaFree(dev->d_fine);
 	cudaFree(dev->d_coarse);
 	cudaFree(dev->d_jobs);
@@ -1745,6 +1817,56 @@ int rdpb_pass_end(rdpb_device *dev)
 	const unsigned i = dev->staging_index;
 	CK(cudaEventRecord(dev->kernels_done[i], dev->stream));
 	dev->kernels_in_flight[i] = true;
+	return 0;
+}
+
+int rdpb_upscaling_init(rdpb_device *dev, uint32_t scale_log2)
+{
+	cudaSetDevice(dev->ordinal);
+	if (scale_log2 < 1 || scale_log2 > 3 || dev->scale_log2)
+		return -1;
+	const size_t slices = size_t(1) << (2 * scale_log2);
+	const size_t hidden_stride = dev->rdram_size >> 1;
+	const size_t fine_bytes = (size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 32) * 4) << (2 * scale_log2);
+	const size_t coarse_bytes = (size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 1024) * 4) << (2 * scale_log2);
+	CK(cudaMalloc(&dev->up_rdram, slices * dev->rdram_size));
+	CK(cudaMalloc(&dev->up_hidden, slices * hidden_stride));
+	CK(cudaMalloc(&dev->up_reference, dev->rdram_size));
+	CK(cudaMalloc(&dev->up_spans, (size_t(kMaxSpansPerPass) << scale_log2) * sizeof(Span)));
+	CK(cudaMalloc(&dev->up_fine, fine_bytes));
+	CK(cudaMalloc(&dev->up_coarse, coarse_bytes));
+	CK(cudaMemsetAsync(dev->up_rdram, 0, slices * dev->rdram_size, dev->stream));
+	CK(cudaMemsetAsync(dev->up_hidden, 3, slices * hidden_stride, dev->stream)); // ref rdp_renderer.cpp:593
+	CK(cudaMemsetAsync(dev->up_reference, 0, dev->rdram_size, dev->stream));
+	CK(cudaMemsetAsync(dev->up_fine, 0, fine_bytes, dev->stream));
+	CK(cudaMemsetAsync(dev->up_coarse, 0, coarse_bytes, dev->stream));
+	dev->scale_log2 = scale_log2;
+	return 0;
+}
+
+int rdpb_launch_upscale_sync(rdpb_device *dev, const void *fb_info, int stage)
+{
+	cudaSetDevice(dev->ordinal);
+	if (!dev->scale_log2)
+		return 0;
+	GpuOp op = {};
+	op.kind = GOP_UPSCALE_SYNC;
+	op.fb = *static_cast<const FbInfo *>(fb_info);
+	op.count = uint32_t(stage);
+	return submit(dev, op);
+}
+
+int rdpb_upscaled_read(rdpb_device *dev, void *rdram_dst, void *hidden_dst)
+{
+	cudaSetDevice(dev->ordinal);
+	if (!dev->scale_log2)
+		return -1;
+	const size_t slices = size_t(1) << (2 * dev->scale_log2);
+	CK(cudaStreamSynchronize(dev->stream));
+	if (rdram_dst)
+		CK(cudaMemcpy(rdram_dst, dev->up_rdram, slices * dev->rdram_size, cudaMemcpyDeviceToHost));
+	if (hidden_dst)
+		CK(cudaMemcpy(hidden_dst, dev->up_hidden, slices * (dev->rdram_size >> 1), cudaMemcpyDeviceToHost));
 	return 0;
 }
 

@@ -715,9 +715,11 @@ template <class S>
 RDP_HD bool process_pixel_primitive(const ShadeContext &ctx, const FbView &fb, PixelState &px, int x, int y, uint32_t prim)
 {
 	const PrimSetup &p = ctx.prims[prim];
-	if (y < p.line_lo || y > p.line_hi)
+	const int sl = ctx.scale_log2;
+	const int line_lo = int(p.line_lo) << sl, line_hi = (int(p.line_hi) << sl) + ((1 << sl) - 1);
+	if (y < line_lo || y > line_hi)
 		return false;
-	const Span &sp = ctx.spans[p.span_base + uint32_t(y - p.line_lo)];
+	const Span &sp = ctx.spans[(p.span_base << sl) + uint32_t(y - line_lo)];
 	if (!sp.valid)
 		return false;
 	return process_pixel_span<S>(ctx, fb, px, x, y, prim, p, sp, ctx.states[p.state_id]);

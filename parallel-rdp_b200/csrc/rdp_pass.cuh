@@ -63,16 +63,20 @@ RDP_HD void pass_setup_prim(const PassBuffers &b, uint32_t i)
 
 // ---- stage 3 -------------------------------------------------------------------------------------
 // Edge-walk scanline y of a primitive.  Returns the inclusive pixel range to bin (lo > hi: nothing).
-RDP_HD void pass_span_line(const PassBuffers &b, const FbInfo &fb, const PrimSetup &p, int y, int &bin_lo, int &bin_hi)
+// With internal upscaling (sl = log2 S) y is a scanline of the upscaled image: a primitive then owns S times as many
+// span slots, starting at S * span_base, for lines S * line_lo .. S * (line_hi + 1) + S - 1.
+RDP_HD void pass_span_line(const PassBuffers &b, const FbInfo &fb, const PrimSetup &p, int y, int &bin_lo, int &bin_hi, int sl = 0)
 {
 	bin_lo = 1;
 	bin_hi = 0;
-	if (y < p.line_lo || y > p.line_hi + 1)
+	const int S = 1 << sl;
+	const int line_lo = int(p.line_lo) << sl, line_hi = (int(p.line_hi) << sl) + (S - 1);
+	if (y < line_lo || y > line_hi + S)
 		return;
 	Span sp;
-	compute_span(p, b.states[p.state_id], y, sp);
-	b.spans[p.span_base + uint32_t(y - p.line_lo)] = sp;
-	if (y <= p.line_hi && sp.valid && y >= 0 && y < int(fb.height))
+	compute_span(p, b.states[p.state_id], y, sp, sl);
+	b.spans[(p.span_base << sl) + uint32_t(y - line_lo)] = sp;
+	if (y <= line_hi && sp.valid && y >= 0 && y < int(fb.height))
 	{
 		bin_lo = imax(int(sp.start_x), 0);
 		bin_hi = imin(int(sp.end_x), int(fb.width) - 1);
@@ -98,11 +102,14 @@ RDP_HD void pass_bin_row(const FbInfo &fb, uint32_t prim, int tile_y, int x_lo, 
 }
 
 // ---- stage 4 -------------------------------------------------------------------------------------
+// With internal upscaling the pass's RDRAM / hidden RDRAM are arrays of S*S "slices", each a whole image: upscaled
+// pixel (x, y) is native pixel (x / S, y / S) of slice (y % S) * S + x % S (memory_interfacing.h:286-302, 56-98).
 template <class S>
-RDP_HD void pass_pixel_begin(const PassBuffers &b, const FbInfo &fb, FbView &view, PixelState &px, int x, int y)
+RDP_HD void pass_pixel_begin(const PassBuffers &b, const FbInfo &fb, FbView &view, PixelState &px, int x, int y, int sl = 0)
 {
-	view.rdram = b.rdram;
-	view.hidden = b.hidden;
+	const uint32_t slice = (uint32_t(y) & ((1u << sl) - 1u)) * (1u << sl) + (uint32_t(x) & ((1u << sl) - 1u));
+	view.rdram = b.rdram + size_t(slice) * fb.rdram_size;
+	view.hidden = b.hidden + size_t(slice) * (fb.rdram_size >> 1);
 	view.blend_lut = b.blend_lut;
 	view.fmt = resolve_fb_fmt<S>(fb.fmt);
 	view.rdram_size = fb.rdram_size;
@@ -115,7 +122,7 @@ RDP_HD void pass_pixel_begin(const PassBuffers &b, const FbInfo &fb, FbView &vie
 	px.color_index = 0;
 	if (x < int(fb.width) && y < int(fb.height))
 	{
-		const uint32_t pix = fb.width * uint32_t(y) + uint32_t(x);
+		const uint32_t pix = (fb.width >> sl) * (uint32_t(y) >> sl) + (uint32_t(x) >> sl);
 		const uint32_t shift = view.fmt == FB_RGBA8888 ? 2u : ((view.fmt == FB_RGBA5551 || view.fmt == FB_IA88) ? 1u : 0u);
 		px.color_index = (fb.color_addr >> shift) + pix;
 		load_color(view, px, px.color_index);
@@ -123,11 +130,11 @@ RDP_HD void pass_pixel_begin(const PassBuffers &b, const FbInfo &fb, FbView &vie
 	}
 }
 
-RDP_HD void pass_pixel_end(const FbInfo &fb, const FbView &view, PixelState &px, int x, int y)
+RDP_HD void pass_pixel_end(const FbInfo &fb, const FbView &view, PixelState &px, int x, int y, int sl = 0)
 {
 	if (x >= int(fb.width) || y >= int(fb.height))
 		return;
-	const uint32_t pix = fb.width * uint32_t(y) + uint32_t(x);
+	const uint32_t pix = (fb.width >> sl) * (uint32_t(y) >> sl) + (uint32_t(x) >> sl);
 	store_color(view, px, px.color_index);
 	store_depth(view, px, (fb.depth_addr >> 1) + pix);
 }
@@ -145,6 +152,7 @@ RDP_HD uint32_t pass_pixel_walk(const PassBuffers &b, const FbInfo &fb, const Fb
 	ctx.tmem = b.tmem_instances;
 	ctx.fb_fmt = view.fmt;
 	ctx.base_prim_index = fb.base_prim_index;
+	ctx.scale_log2 = int(fb.scale_log2);
 
 	const uint32_t *coarse = b.coarse_mask + size_t(tile) * fb.coarse_stride;
 	const uint32_t *fine = b.fine_mask + size_t(tile) * fb.mask_stride;
@@ -238,6 +246,7 @@ RDP_HD uint32_t pass_pixel_walk_deferred(const PassBuffers &b, const FbInfo &fb,
 	w.ctx.tmem = b.tmem_instances;
 	w.ctx.fb_fmt = view.fmt;
 	w.ctx.base_prim_index = fb.base_prim_index;
+	w.ctx.scale_log2 = 0; // the deferred pipeline only runs native-resolution passes
 	w.count = 0;
 	w.shaded = 0;
 
@@ -269,6 +278,75 @@ RDP_HD uint32_t pass_pixel_walk_deferred(const PassBuffers &b, const FbInfo &fb,
 RDP_HD bool deferrable_pass(const PassSummary &sum, const FbInfo &fb)
 {
 	return (sum.rf_or & kRfNotDeferrable) == 0u && fb.color_addr != fb.depth_addr;
+}
+
+// ---- internal upscaling: keeping the upscaled domain in step with native RDRAM ------------------------------------
+// ref shaders/update_upscaled_domain_pre.comp:95-185 and _post.comp:75-120, called around the native-resolution
+// pass (rdp_renderer.cpp:2243-2245, 2268-2277).  `reference` is a native-sized shadow of what the upscaled domain
+// believes native RDRAM holds.  PRE, before the native pass renders: wherever the framebuffer or depth range of
+// native RDRAM differs from the shadow (the CPU, a texture-like write or another pass touched it), the native value and
+// its hidden bits are broadcast to all S*S slices.  POST, after the native pass: the shadow takes the pass's output,
+// so that rendered pixels are *not* broadcast over the separately rendered upscaled ones next time.
+struct UpscaleSync
+{
+	uint8_t *rdram, *hidden;       // native
+	uint8_t *reference;            // native-sized shadow
+	uint8_t *up_rdram, *up_hidden; // S*S slices of rdram_size / (rdram_size >> 1) bytes
+	uint32_t rdram_size;
+	uint32_t num_slices;
+	uint32_t fb_index, depth_index; // first element of the colour image (in pixels of its size) and of the depth image (16-bit)
+	uint32_t num_pixels;
+	uint32_t size_log2;  // colour pixel size: 0, 1, 2
+	uint32_t alias;      // colour and depth share an address
+};
+
+RDP_HD void upscale_sync_word(const UpscaleSync &u, uint32_t index, uint32_t size_log2, bool post)
+{
+	index &= (u.rdram_size >> size_log2) - 1u;
+	const size_t at = size_t(index) << size_log2;
+	uint32_t real = 0, ref = 0;
+	for (uint32_t k = 0; k < (1u << size_log2); k++)
+	{
+		real |= uint32_t(u.rdram[at + k]) << (8 * k);
+		ref |= uint32_t(u.reference[at + k]) << (8 * k);
+	}
+	if (real == ref)
+		return;
+	for (uint32_t k = 0; k < (1u << size_log2); k++)
+		u.reference[at + k] = u.rdram[at + k];
+	if (post)
+		return;
+	const size_t hidden_stride = u.rdram_size >> 1;
+	for (uint32_t s = 0; s < u.num_slices; s++)
+	{
+		uint8_t *dst = u.up_rdram + size_t(s) * u.rdram_size;
+		uint8_t *hid = u.up_hidden + size_t(s) * hidden_stride;
+		for (uint32_t k = 0; k < (1u << size_log2); k++)
+			dst[at + k] = u.rdram[at + k];
+		if (size_log2 == 0)
+		{
+			const uint32_t mirrored = index ^ 3u;
+			if (mirrored & 1u)
+				hid[mirrored >> 1] = u.hidden[mirrored >> 1];
+		}
+		else if (size_log2 == 1)
+			hid[index ^ 1u] = u.hidden[index ^ 1u];
+		else
+		{
+			hid[2u * index] = u.hidden[2u * index];
+			hid[2u * index + 1u] = u.hidden[2u * index + 1u];
+		}
+	}
+}
+
+// One thread per framebuffer pixel.
+RDP_HD void upscale_sync_pixel(const UpscaleSync &u, uint32_t i, bool post)
+{
+	if (i >= u.num_pixels)
+		return;
+	upscale_sync_word(u, u.fb_index + i, u.size_log2, post);
+	if (!u.alias)
+		upscale_sync_word(u, u.depth_index + i, 1u, post);
 }
 
 // Zero the mask words of one tile after its pixels are done, so the next pass starts from clean masks.

@@ -308,19 +308,35 @@ RDP_HD int quantize_edge_x(int x)
 	return (x >> 12) | ((x & 0xfff) != 0 ? 1 : 0);
 }
 
-// Edge-walk one scanline of one primitive.
-RDP_HD void compute_span(const PrimSetup &p, const PassState &st, int y, Span &out)
+// sign-extend the low `bits` bits (run-time width: 27 + log2(scale))
+RDP_HD int sign_extend_bits(uint32_t v, int bits)
 {
+	const int sh = 32 - bits;
+	return int(v << sh) >> sh;
+}
+
+// span_setup.comp:80-85: a derivative times a distance in scaled pixels -- whole native pixels step by the full
+// derivative, the sub-pixel remainder by the derivative quantised to the scale.
+RDP_HD uint32_t step_snapped(int d, int dist, int sl)
+{
+	return uint32_t(dist >> sl) * uint32_t(d) + uint32_t(dist & ((1 << sl) - 1)) * uint32_t(d >> sl);
+}
+
+// Edge-walk one scanline of one primitive.  `sl` = log2 of the internal upscaling factor: y is then a scanline of
+// the upscaled image and every X in the result is in upscaled pixels (span_setup.comp:87-227 with SCALING_LOG2).
+RDP_HD void compute_span(const PrimSetup &p, const PassState &st, int y, Span &out, int sl = 0)
+{
+	const int S = 1 << sl;
 	const bool flip = (p.flags & SF_FLIP) != 0;
 	const bool do_offset = (p.flags & SF_DO_OFFSET) != 0;
 	const bool skip_xfrac = (p.flags & SF_SKIP_XFRAC) != 0;
 
 	// Attributes stepped down the major edge to this scanline.
 	{
-		const int dy = y - (int(p.yh) >> 2);
-		int xh = int(uint32_t(p.xh) + uint32_t(dy) * (uint32_t(p.dxhdy) << 2));
+		const int dy = y - ((int(p.yh) >> 2) << sl);
+		int xh = int(uint32_t(p.xh) * uint32_t(S) + uint32_t(dy) * (uint32_t(p.dxhdy) << 2));
 		if (do_offset)
-			xh = int(uint32_t(xh) + 3u * uint32_t(p.dxhdy));
+			xh = int(uint32_t(xh) + uint32_t(3 * S) * uint32_t(p.dxhdy));
 
 		const int base_x = xh >> 15;
 		const int xfrac = skip_xfrac ? 0 : ((xh >> 7) & 0xff);
@@ -338,24 +354,24 @@ RDP_HD void compute_span(const PrimSetup &p, const PassState &st, int y, Span &o
 				dyh = p.dstzw_dy[i] & ~0x1ff;
 				diff_t = deh - (deh >> 2) - dyh + (dyh >> 2);
 			}
-			int c = int(uint32_t(p.rgba[i]) + uint32_t(p.drgba_de[i]) * uint32_t(dy));
-			c = int(uint32_t(c & ~0x1ff) + uint32_t(diff_c) - uint32_t((p.drgba_dx[i] >> 8) & ~1) * uint32_t(xfrac)) & ~0x3ff;
+			int c = int(uint32_t(p.rgba[i]) + step_snapped(p.drgba_de[i], dy, sl));
+			c = int(uint32_t(c & ~0x1ff) + uint32_t(diff_c) - step_snapped((p.drgba_dx[i] >> 8) & ~1, xfrac, sl)) & ~0x3ff;
 			out.rgba[i] = c;
 
-			int t = int(uint32_t(p.stzw[i]) + uint32_t(p.dstzw_de[i]) * uint32_t(dy));
-			t = int(uint32_t(t & ~0x1ff) + uint32_t(diff_t) - uint32_t((p.dstzw_dx[i] >> 8) & ~1) * uint32_t(xfrac)) & ~0x3ff;
+			int t = int(uint32_t(p.stzw[i]) + step_snapped(p.dstzw_de[i], dy, sl));
+			t = int(uint32_t(t & ~0x1ff) + uint32_t(diff_t) - step_snapped((p.dstzw_dx[i] >> 8) & ~1, xfrac, sl)) & ~0x3ff;
 			out.stzw[i] = t;
 		}
 		out.base_x = base_x;
 	}
 
 	// Edges at the four sub-scanlines.
-	const int yh_base = int(p.yh) & ~3;
-	const int ym_base = int(p.ym);
-	const int ylo = imax(int(p.yh), int(st.sc_ylo));
-	const int yhi = imin(int(p.yl), int(st.sc_yhi));
-	const int lo_scissor = int(st.sc_xlo) << 1;
-	const int hi_scissor = int(st.sc_xhi) << 1;
+	const int yh_base = (int(p.yh) & ~3) * S;
+	const int ym_base = int(p.ym) * S;
+	const int ylo = imax(int(p.yh), int(st.sc_ylo)) * S;
+	const int yhi = imin(int(p.yl), int(st.sc_yhi)) * S;
+	const int lo_scissor = (int(st.sc_xlo) << 1) * S;
+	const int hi_scissor = (int(st.sc_xhi) << 1) * S;
 
 	int xleft[4], xright[4];
 	bool invalid[4];
@@ -367,15 +383,15 @@ RDP_HD void compute_span(const PrimSetup &p, const PassState &st, int y, Span &o
 		const int ys = y * 4 + i;
 		const bool clip_y = ys < ylo || ys >= yhi;
 
-		int xh = int(uint32_t(p.xh) + uint32_t(ys - yh_base) * uint32_t(p.dxhdy));
-		int xm = int(uint32_t(p.xm) + uint32_t(ys - yh_base) * uint32_t(p.dxmdy));
-		int xl = int(uint32_t(p.xl) + uint32_t(ys - ym_base) * uint32_t(p.dxldy));
-		if (ys < int(p.ym))
+		int xh = int(uint32_t(p.xh) * uint32_t(S) + uint32_t(ys - yh_base) * uint32_t(p.dxhdy));
+		int xm = int(uint32_t(p.xm) * uint32_t(S) + uint32_t(ys - yh_base) * uint32_t(p.dxmdy));
+		int xl = int(uint32_t(p.xl) * uint32_t(S) + uint32_t(ys - ym_base) * uint32_t(p.dxldy));
+		if (ys < ym_base)
 			xl = xm;
 
-		// 27-bit wrap (the set-up already dropped one of the 28 bits).
-		xl = sign_extend<27>(uint32_t(xl));
-		xh = sign_extend<27>(uint32_t(xh));
+		// (27 + log2 scale)-bit wrap (the set-up already dropped one of the 28 bits for this headroom).
+		xl = sign_extend_bits(uint32_t(xl), 27 + sl);
+		xh = sign_extend_bits(uint32_t(xh), 27 + sl);
 
 		const int xh_q = quantize_edge_x(xh);
 		const int xl_q = quantize_edge_x(xl);
@@ -417,7 +433,7 @@ RDP_HD void compute_span(const PrimSetup &p, const PassState &st, int y, Span &o
 
 	bool valid = !all_invalid && !all_over && !all_under;
 	if (p.flags & SF_INTERLACE)
-		if ((y & 1) != ((p.flags & SF_KEEP_ODD) ? 1 : 0))
+		if (((y >> sl) & 1) != ((p.flags & SF_KEEP_ODD) ? 1 : 0))
 			valid = false;
 	out.valid = valid ? 1 : 0;
 	out.lodlength = int16_t(flip ? (end_x - out.base_x) : (out.base_x - start_x));

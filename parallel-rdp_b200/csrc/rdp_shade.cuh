@@ -58,6 +58,10 @@ struct ShadeContext
 	const uint8_t *tmem; // TMEM snapshots, kTmemBytes each
 	uint32_t fb_fmt;
 	uint32_t base_prim_index;
+	// log2 of the internal upscaling factor of this pass (0 at native resolution; a literal 0 in every kernel that is
+	// not the upscaled instantiation, so the extra shifts fold away).  Pixel coordinates, span indices and every X in a
+	// Span are then in upscaled pixels; ref shaders/shading.h:27-28, interpolation.h (SCALING_LOG2).
+	int scale_log2;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -224,32 +228,34 @@ RDP_HD void centroid_offset(int coverage, int &xoff, int &yoff)
 	xoff = ((first & 1) << 1) + (yoff & 1);
 }
 
-RDP_HD Vec4 interpolate_shade(const Span &sp, const PrimSetup &p, int dx, int coverage)
+RDP_HD Vec4 interpolate_shade(const Span &sp, const PrimSetup &p, int dx, int coverage, int sl = 0)
 {
 	int xoff, yoff;
 	centroid_offset(coverage, xoff, yoff);
 	int out[4];
 	for (int i = 0; i < 4; i++)
 	{
-		int c = int(uint32_t(sp.rgba[i]) + uint32_t(p.drgba_dx[i] & ~0x1f) * uint32_t(dx));
+		int c = int(uint32_t(sp.rgba[i]) + uint32_t((p.drgba_dx[i] & ~0x1f) >> sl) * uint32_t(dx));
 		int snapped = c >> 14;
-		snapped = int(uint32_t(snapped) << 2);
+		snapped = int(uint32_t(snapped) << (2 + sl));
 		snapped += xoff * (p.drgba_dx[i] >> 14) + yoff * (p.drgba_dy[i] >> 14);
-		snapped >>= 4;
+		snapped >>= 4 + sl;
 		out[i] = clamp_9bit(snapped);
 	}
 	return vec4(out[0], out[1], out[2], out[3]);
 }
 
-RDP_HD int interpolate_depth(const Span &sp, const PrimSetup &p, int dx, int coverage)
+RDP_HD int interpolate_depth(const Span &sp, const PrimSetup &p, int dx, int coverage, int sl = 0)
 {
 	int xoff, yoff;
 	centroid_offset(coverage, xoff, yoff);
-	int z = int(uint32_t(sp.stzw[2]) + uint32_t(p.dstzw_dx[2]) * uint32_t(dx));
+	// Whole native pixels step by dz/dx, the sub-pixel remainder by dz/dx quantised to the scale (interpolation.h:131).
+	int z = int(uint32_t(sp.stzw[2]) + uint32_t(p.dstzw_dx[2]) * uint32_t(dx >> sl) +
+	            uint32_t(p.dstzw_dx[2] >> sl) * uint32_t(dx & ((1 << sl) - 1)));
 	int snapped = z >> 10;
-	snapped = int(uint32_t(snapped) << 2);
+	snapped = int(uint32_t(snapped) << (2 + sl));
 	snapped += xoff * (p.dstzw_dx[2] >> 10) + yoff * (p.dstzw_dy[2] >> 10);
-	snapped >>= 5;
+	snapped >>= 5 + sl;
 	return clamp_depth(snapped);
 }
 
@@ -1041,12 +1047,13 @@ RDP_HD void shade_color(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 	if (rf & RF_NOISE)
 		noise = noise_hash(uint32_t(x), uint32_t(y), prim_index + ctx.base_prim_index);
 
+	const int sl = ctx.scale_log2;
 	const int dx = x - sp.base_x;
 	const int direction = flip ? 1 : -1;
 	const bool uses_lod = (rf & RF_USES_LOD) != 0;
 
 	CombinerRegs regs;
-	regs.shade = interpolate_shade(sp, p, dx, coverage);
+	regs.shade = interpolate_shade(sp, p, dx, coverage, sl);
 	regs.combined = splat4(0);
 	regs.texel0 = splat4(0);
 	regs.texel1 = splat4(0);
@@ -1058,7 +1065,7 @@ RDP_HD void shade_color(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 	int s_dx = 0, t_dx = 0, s_dy = 0, t_dy = 0;
 	bool persp_overflow = false;
 	{
-		const int ms = p.dstzw_dx[0] & ~0x1f, mt = p.dstzw_dx[1] & ~0x1f, mw = p.dstzw_dx[3] & ~0x1f;
+		const int ms = (p.dstzw_dx[0] & ~0x1f) >> sl, mt = (p.dstzw_dx[1] & ~0x1f) >> sl, mw = (p.dstzw_dx[3] & ~0x1f) >> sl;
 		const int rs = int(uint32_t(sp.stzw[0]) + uint32_t(ms) * uint32_t(dx));
 		const int rt = int(uint32_t(sp.stzw[1]) + uint32_t(mt) * uint32_t(dx));
 		const int rw = int(uint32_t(sp.stzw[3]) + uint32_t(mw) * uint32_t(dx));
@@ -1068,9 +1075,9 @@ RDP_HD void shade_color(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 			const int xs = int(uint32_t(rs) + uint32_t(direction * ms));
 			const int xt = int(uint32_t(rt) + uint32_t(direction * mt));
 			const int xw = int(uint32_t(rw) + uint32_t(direction * mw));
-			const int ys = int(uint32_t(rs) + uint32_t(p.dstzw_dy[0] & ~0x7fff));
-			const int yt = int(uint32_t(rt) + uint32_t(p.dstzw_dy[1] & ~0x7fff));
-			const int yw = int(uint32_t(rw) + uint32_t(p.dstzw_dy[3] & ~0x7fff));
+			const int ys = int(uint32_t(rs) + uint32_t((p.dstzw_dy[0] & ~0x7fff) >> sl));
+			const int yt = int(uint32_t(rt) + uint32_t((p.dstzw_dy[1] & ~0x7fff) >> sl));
+			const int yw = int(uint32_t(rw) + uint32_t((p.dstzw_dy[3] & ~0x7fff) >> sl));
 			divide_st(perspective, xs >> 16, xt >> 16, xw >> 16, s_dx, t_dx, persp_overflow);
 			divide_st(perspective, ys >> 16, yt >> 16, yw >> 16, s_dy, t_dy, persp_overflow);
 		}
@@ -1092,7 +1099,7 @@ RDP_HD void shade_color(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 	if (rf & RF_USES_PIPELINED_TEXEL1)
 	{
 		// 1-cycle mode reading TEXEL1 observes the next pixel's texel (or the next line's first pixel).
-		const Span &next = ctx.spans[p.span_base + uint32_t(y - p.line_lo + 1)];
+		const Span &next = ctx.spans[(p.span_base << sl) + uint32_t(y - (int(p.line_lo) << sl) + 1)];
 		const bool long_span = sp.lodlength >= 8;
 		const bool end_span = x == (flip ? sp.end_x : sp.start_x);
 		bool dummy = false;
@@ -1100,10 +1107,10 @@ RDP_HD void shade_color(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 			divide_st(perspective, next.stzw[0] >> 16, next.stzw[1] >> 16, next.stzw[3] >> 16, s, t, dummy);
 		else
 		{
-			const int ndx = dx + direction;
-			const int rs = int(uint32_t(sp.stzw[0]) + uint32_t(p.dstzw_dx[0] & ~0x1f) * uint32_t(ndx));
-			const int rt = int(uint32_t(sp.stzw[1]) + uint32_t(p.dstzw_dx[1] & ~0x1f) * uint32_t(ndx));
-			const int rw = int(uint32_t(sp.stzw[3]) + uint32_t(p.dstzw_dx[3] & ~0x1f) * uint32_t(ndx));
+			const int ndx = dx + (direction << sl);
+			const int rs = int(uint32_t(sp.stzw[0]) + uint32_t((p.dstzw_dx[0] & ~0x1f) >> sl) * uint32_t(ndx));
+			const int rt = int(uint32_t(sp.stzw[1]) + uint32_t((p.dstzw_dx[1] & ~0x1f) >> sl) * uint32_t(ndx));
+			const int rw = int(uint32_t(sp.stzw[3]) + uint32_t((p.dstzw_dx[3] & ~0x1f) >> sl) * uint32_t(ndx));
 			divide_st(perspective, rs >> 16, rt >> 16, rw >> 16, s, t, dummy);
 		}
 		tile1 = tile0;
@@ -1172,6 +1179,7 @@ RDP_HD int shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_inde
 			return 0;
 
 		int dx = flip ? (x - sp.start_x) : (sp.end_x - x);
+		dx >>= ctx.scale_log2; // the copy pipe duplicates pixels when upscaling (interpolation.h:60-61)
 		int dx_mask, dx_shift;
 		switch (ctx.fb_fmt)
 		{
@@ -1205,7 +1213,7 @@ RDP_HD int shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_inde
 		return 0;
 	int coverage_count = pop_count(uint32_t(coverage));
 
-	const int z = interpolate_depth(sp, p, x - sp.base_x, coverage);
+	const int z = interpolate_depth(sp, p, x - sp.base_x, coverage, ctx.scale_log2);
 	if ((m.bf & BF_Z_COMPARE) && !(rf & RF_CVG_TIMES_ALPHA) && depth_early_reject(z, p, early, coverage_count, m.bf, m.z_mode()))
 		return 2;
 

@@ -271,8 +271,20 @@ struct FbInfo
 	uint32_t coarse_stride; // 32-bit words of coarse mask per tile = ceil(mask_stride/32)
 	uint32_t tiles_x, tiles_y;
 	uint32_t num_jobs; // span jobs = sum over primitives of span_job_count()
-	uint32_t pad[3];
+	// log2 of the internal upscaling factor S of this pass.  When non-zero, width / height / tiles_x / tiles_y are in
+	// upscaled pixels, the pass reads and writes the upscaled RDRAM domain (S*S slices) and its own span / mask buffers;
+	// addresses, primitive records and scanline ranges stay native (ref rdp_renderer.cpp:1865-1868, 2138-2141).
+	uint32_t scale_log2;
+	uint32_t pad[2];
 };
+
+// Which passes are worth rendering upscaled: the reference's heuristic (rdp_renderer.cpp:3000-3012: only 16/32-bit
+// colour images at least 256 pixels wide can be what reaches the screen), plus our own range limit -- a Span keeps
+// its X edges as 16-bit x.3 values, so the upscaled width has to stay below 8192 pixels.
+RDP_HD bool pass_wants_upscaling(const FbInfo &fb, uint32_t scale_log2)
+{
+	return (fb.fmt == FB_RGBA5551 || fb.fmt == FB_RGBA8888) && fb.width >= 256u && (fb.width << scale_log2) < 8192u;
+}
 
 // A span job is one (primitive, 32-scanline chunk): one warp of the span/bin kernel.  Chunks start at the
 // primitive's first tile row so that every 4-lane group of a warp owns exactly one tile row.

@@ -144,6 +144,15 @@ void *rdp_b200_backend_device(rdp_b200_processor *p) { return p->impl.get_backen
 const char *rdp_b200_last_tile_variant(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_last_tile_variant(p->impl.get_backend_device()) : ""; }
 void *rdp_b200_cuda_stream(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_stream(p->impl.get_backend_device()) : nullptr; }
 
+// ---- internal upscaling ----
+unsigned rdp_b200_upscaling_factor(rdp_b200_processor *p) { return 1u << p->impl.get_upscaling_log2(); }
+uint64_t rdp_b200_upscaled_pass_count(rdp_b200_processor *p) { return p->impl.get_upscaled_pass_count(); }
+int rdp_b200_read_upscaled_rdram(rdp_b200_processor *p, void *rdram_dst, void *hidden_dst)
+{
+	p->impl.idle();
+	return p->impl.get_backend_device() ? rdpb_upscaled_read(p->impl.get_backend_device(), rdram_dst, hidden_dst) : -1;
+}
+
 // ---- RDPDUMP2 ------------------------------------------------------------------------------------------------
 rdp_b200_dump_player *rdp_b200_dump_open(const char *path)
 {

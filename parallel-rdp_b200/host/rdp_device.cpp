@@ -26,9 +26,8 @@ CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, 
 		return;
 	}
 
-	if (flags & (COMMAND_PROCESSOR_FLAG_UPSCALING_2X_BIT | COMMAND_PROCESSOR_FLAG_UPSCALING_4X_BIT |
-	             COMMAND_PROCESSOR_FLAG_UPSCALING_8X_BIT))
-		fprintf(stderr, "[rdp-b200] Internal upscaling is not implemented yet; rendering at native resolution.\n");
+	if (flags & (COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_READ_BACK_BIT | COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_DITHER_BIT))
+		fprintf(stderr, "[rdp-b200] Super-sampled read-back is not implemented; native RDRAM keeps the native-resolution result.\n");
 
 	device = rdpb_device_create(config.cuda_device, uint32_t(rdram_size), uint32_t(hidden_rdram_size));
 	if (!device)
@@ -56,6 +55,14 @@ CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, 
 	memset(rdpb_tmem_host_ptr(device), 0, kTmemBytes);
 
 	is_supported = renderer.init(device, rdram_size);
+	// Internal upscaling (ref rdp_device.cpp:136-147): the pass is rendered a second time into an upscaled domain.
+	if (is_supported)
+	{
+		const uint32_t up = (flags & COMMAND_PROCESSOR_FLAG_UPSCALING_8X_BIT) ? 3u :
+		                    (flags & COMMAND_PROCESSOR_FLAG_UPSCALING_4X_BIT) ? 2u :
+		                    (flags & COMMAND_PROCESSOR_FLAG_UPSCALING_2X_BIT) ? 1u : 0u;
+		renderer.set_upscaling(up);
+	}
 	vi.init(device, rdram_size);
 
 	if (const char *env = getenv("PARALLEL_RDP_SINGLE_THREADED_COMMAND"))

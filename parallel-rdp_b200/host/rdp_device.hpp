@@ -127,6 +127,8 @@ public:
 	rdpb_device *get_backend_device() { return device; }
 	uint64_t get_primitive_counter() const { return renderer.get_primitive_counter(); }
 	uint64_t get_pass_counter() const { return renderer.get_pass_counter(); }
+	uint32_t get_upscaling_log2() const { return renderer.get_upscaling_log2(); }
+	uint64_t get_upscaled_pass_count() const { return renderer.get_upscaled_pass_count(); }
 	// Seconds the command thread spent [0] executing ring records in total, [1] inside pass submission
 	// (Renderer::flush_queues), [2] inside queued scan-outs.  [0] - [1] - [2] is command parsing / pass recording.
 	void get_host_timing(double out[3]) const;

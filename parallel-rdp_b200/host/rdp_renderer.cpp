@@ -15,6 +15,19 @@ using namespace rdpb;
 
 namespace RDP
 {
+bool Renderer::set_upscaling(uint32_t log2)
+{
+	if (log2 == 0)
+		return true;
+	if (log2 > 3 || rdpb_upscaling_init(device, log2) != 0)
+	{
+		fprintf(stderr, "[rdp-b200] Cannot set up %ux internal upscaling; rendering at native resolution only.\n", 1u << log2);
+		return false;
+	}
+	upscale_log2 = log2;
+	return true;
+}
+
 bool Renderer::init(rdpb_device *device_, size_t rdram_size_)
 {
 	device = device_;
@@ -436,8 +449,28 @@ void Renderer::flush_queues()
 		info.tiles_y = (info.height + kTileH - 1) / kTileH;
 
 		info.num_jobs = num_jobs;
+		// Internal upscaling (ref rdp_renderer.cpp:2223-2342, 2955-2980): the pass is rendered at native resolution as
+		// always -- RDRAM stays bit-exact -- and then once more into the upscaled domain.  Around the native tile launch
+		// the upscaled domain picks up whatever changed in native RDRAM behind its back (PRE) and the shadow copy
+		// takes the pass's own output (POST).
+		const bool upscale = upscale_log2 != 0 && pass_wants_upscaling(info, upscale_log2);
 		rdpb_launch_span_bin(device, &info);
+		if (upscale)
+			rdpb_launch_upscale_sync(device, &info, RDPB_UPSCALE_SYNC_PRE);
 		rdpb_launch_tiles(device, &info, &summary);
+		if (upscale)
+		{
+			rdpb_launch_upscale_sync(device, &info, RDPB_UPSCALE_SYNC_POST);
+			FbInfo up = info;
+			up.scale_log2 = upscale_log2;
+			up.width = info.width << upscale_log2;
+			up.height = info.height << upscale_log2;
+			up.tiles_x = (up.width + kTileW - 1) / kTileW;
+			up.tiles_y = (up.height + kTileH - 1) / kTileH;
+			rdpb_launch_span_bin(device, &up);
+			rdpb_launch_tiles(device, &up, &summary);
+			upscaled_pass_counter++;
+		}
 
 		const uint32_t pixels = info.width * info.height;
 		const uint32_t bpp = fb.fmt == FBFormat::RGBA8888 ? 4 : ((fb.fmt == FBFormat::RGBA5551 || fb.fmt == FBFormat::IA88) ? 2 : 1);

@@ -81,6 +81,10 @@ class Renderer
 {
 public:
 	bool init(rdpb_device *device, size_t rdram_size);
+	// Internal upscaling factor 1 << log2 (0: off).  Allocates the upscaled domain in the backend.
+	bool set_upscaling(uint32_t log2);
+	uint32_t get_upscaling_log2() const { return upscale_log2; }
+	uint64_t get_upscaled_pass_count() const { return upscaled_pass_counter; }
 	void set_validation_interface(ValidationInterface *iface) { validation = iface; }
 
 	// Register state.  Callers mutate `regs` then call mark_state_dirty().
@@ -149,6 +153,8 @@ private:
 	void reset_summary();
 	uint32_t base_primitive_index = 0;
 	uint64_t pass_counter = 0;
+	uint64_t upscaled_pass_counter = 0;
+	uint32_t upscale_log2 = 0;
 	uint64_t flush_ns = 0; // time spent submitting passes (written by the thread that drives the renderer)
 	bool tmem_snapshot_valid = false;
 

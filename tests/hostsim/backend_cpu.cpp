@@ -28,6 +28,11 @@ struct rdpb_device
 	std::vector<PrimSetup> prims;
 	std::vector<Span> spans;
 	std::vector<uint32_t> fine, coarse;
+	// internal upscaling
+	uint32_t scale_log2 = 0;
+	std::vector<uint8_t> up_rdram, up_hidden, up_reference;
+	std::vector<Span> up_spans;
+	std::vector<uint32_t> up_fine, up_coarse;
 	rdpb_pass_counts counts = {};
 	std::vector<uint32_t> vi_stage[3];
 	std::vector<uint32_t> vi_out, vi_prev;
@@ -56,6 +61,23 @@ struct rdpb_device
 		b.hidden = hidden.data();
 		b.blend_lut = blend_lut.data();
 		b.counters = counters;
+		return b;
+	}
+
+	// Buffers of an upscaled pass: its own RDRAM domain, spans and masks; everything else is the native pass's.
+	PassBuffers upscaled_buffers(const FbInfo &fb)
+	{
+		PassBuffers b = buffers();
+		const size_t tiles = size_t(fb.tiles_x) * fb.tiles_y;
+		if (up_fine.size() < tiles * fb.mask_stride)
+			up_fine.resize(tiles * fb.mask_stride, 0);
+		if (up_coarse.size() < tiles * fb.coarse_stride)
+			up_coarse.resize(tiles * fb.coarse_stride, 0);
+		b.spans = up_spans.data();
+		b.fine_mask = up_fine.data();
+		b.coarse_mask = up_coarse.data();
+		b.rdram = up_rdram.data();
+		b.hidden = up_hidden.data();
 		return b;
 	}
 };
@@ -166,17 +188,18 @@ int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 	if (g_null_compute)
 		return 0;
 	const FbInfo fb = *static_cast<const FbInfo *>(fb_info);
-	PassBuffers b = dev->buffers();
+	const int sl = int(fb.scale_log2), S = 1 << sl;
+	PassBuffers b = sl ? dev->upscaled_buffers(fb) : dev->buffers();
 	auto or_fn = [](uint32_t *p, uint32_t v) { *p |= v; };
 	for (uint32_t i = 0; i < fb.num_prims; i++)
 	{
 		const PrimSetup &p = b.prims[i];
 		if (p.flags & SF_NO_PIXELS)
 			continue;
-		for (int y = p.line_lo; y <= p.line_hi + 1; y++)
+		for (int y = p.line_lo * S; y <= (p.line_hi + 1) * S + S - 1; y++)
 		{
 			int lo, hi;
-			pass_span_line(b, fb, p, y, lo, hi);
+			pass_span_line(b, fb, p, y, lo, hi, sl);
 			if (lo <= hi)
 				pass_bin_row(fb, i, y / int(kTileH), lo, hi, or_fn, b.fine_mask, b.coarse_mask);
 		}
@@ -200,10 +223,11 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 		        fb.num_prims, fb.fmt, sum->num_shaded_states, sum->rf_or, sum->rf_and, sum->bf_or, sum->bf_and, sum->texel_kinds,
 		        sum->modes_uniform, (unsigned long long)sum->comb_rgb, sum->comb_alpha, sum->blend_misc);
 	}
-	PassBuffers b = dev->buffers();
+	const int sl = int(fb.scale_log2);
+	PassBuffers b = sl ? dev->upscaled_buffers(fb) : dev->buffers();
 	// RDP_HOSTSIM_DEFERRED=1: eligible passes take the scalar statement of the deferred tile pipeline instead of
 	// the in-order walk (tests/test_hostsim_conformance.py runs the suites both ways).
-	const bool deferred = summary && getenv("RDP_HOSTSIM_DEFERRED") && deferrable_pass(*static_cast<const PassSummary *>(summary), fb);
+	const bool deferred = !sl && summary && getenv("RDP_HOSTSIM_DEFERRED") && deferrable_pass(*static_cast<const PassSummary *>(summary), fb);
 	dev->last_deferred = deferred;
 	if (deferred)
 		dev->deferred_passes++;
@@ -226,10 +250,10 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 						continue;
 					FbView view;
 					PixelState px;
-					pass_pixel_begin<SpecGeneric>(b, fb, view, px, x, y);
+					pass_pixel_begin<SpecGeneric>(b, fb, view, px, x, y, sl);
 					dev->counters[1] += deferred ? pass_pixel_walk_deferred<SpecGeneric>(b, fb, view, px, x, y, tile)
 					                             : pass_pixel_walk<SpecGeneric>(b, fb, view, px, x, y, tile);
-					pass_pixel_end(fb, view, px, x, y);
+					pass_pixel_end(fb, view, px, x, y, sl);
 				}
 			}
 			pass_tile_clear_masks(b, fb, tile);
@@ -241,6 +265,54 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 }
 
 int rdpb_pass_end(rdpb_device *) { return 0; }
+
+int rdpb_upscaling_init(rdpb_device *dev, uint32_t scale_log2)
+{
+	if (scale_log2 < 1 || scale_log2 > 3)
+		return -1;
+	dev->scale_log2 = scale_log2;
+	const size_t slices = size_t(1) << (2 * scale_log2);
+	dev->up_rdram.assign(slices * dev->rdram_size, 0);
+	dev->up_hidden.assign(slices * (dev->rdram_size >> 1), 3); // rdp_renderer.cpp:593
+	dev->up_reference.assign(dev->rdram_size, 0);
+	dev->up_spans.resize(size_t(kMaxSpansPerPass) << scale_log2);
+	return 0;
+}
+
+int rdpb_launch_upscale_sync(rdpb_device *dev, const void *fb_info, int stage)
+{
+	if (g_null_compute || !dev->scale_log2)
+		return 0;
+	const FbInfo fb = *static_cast<const FbInfo *>(fb_info);
+	UpscaleSync u;
+	u.rdram = dev->rdram.data();
+	u.hidden = dev->hidden.data();
+	u.reference = dev->up_reference.data();
+	u.up_rdram = dev->up_rdram.data();
+	u.up_hidden = dev->up_hidden.data();
+	u.rdram_size = dev->rdram_size;
+	u.num_slices = 1u << (2 * dev->scale_log2);
+	u.size_log2 = fb.fmt == FB_RGBA8888 ? 2u : ((fb.fmt == FB_RGBA5551 || fb.fmt == FB_IA88) ? 1u : 0u);
+	u.fb_index = fb.color_addr >> u.size_log2;
+	u.depth_index = fb.depth_addr >> 1;
+	u.num_pixels = fb.width * fb.height;
+	u.alias = fb.color_addr == fb.depth_addr;
+	for (uint32_t i = 0; i < u.num_pixels; i++)
+		upscale_sync_pixel(u, i, stage == RDPB_UPSCALE_SYNC_POST);
+	dev->launches++;
+	return 0;
+}
+
+int rdpb_upscaled_read(rdpb_device *dev, void *rdram_dst, void *hidden_dst)
+{
+	if (!dev->scale_log2)
+		return -1;
+	if (rdram_dst)
+		memcpy(rdram_dst, dev->up_rdram.data(), dev->up_rdram.size());
+	if (hidden_dst)
+		memcpy(hidden_dst, dev->up_hidden.data(), dev->up_hidden.size());
+	return 0;
+}
 
 int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *lines)
 {

@@ -43,13 +43,13 @@ def gpu_available() -> bool:
 class SideBySide:
     """backend: 'hostsim' (CPU build of the device code, tests only) or 'cuda' (the product library)."""
 
-    def __init__(self, backend: str, rdram_size: int = RDRAM_SIZE, hidden_size: int = HIDDEN_SIZE, with_oracle=True):
+    def __init__(self, backend: str, rdram_size: int = RDRAM_SIZE, hidden_size: int = HIDDEN_SIZE, with_oracle=True, flags: int = 0):
         self.rdram_size = rdram_size
         self.hidden_size = hidden_size
         self.oracle = angrylion.Oracle(rdram_size) if with_oracle else None
         self.rdram = np.zeros(rdram_size, dtype=np.uint8)
         lib = build_hostsim() if backend == "hostsim" else None
-        self.gpu = rdp.CommandProcessor(self.rdram, hidden_size, library=lib)
+        self.gpu = rdp.CommandProcessor(self.rdram, hidden_size, flags=flags, library=lib)
         # The oracle initialises hidden RDRAM to 3 like the processor does; tests overwrite both anyway.
         self.frames_oracle = []
         self.frames_gpu = []
