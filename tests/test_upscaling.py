@@ -59,7 +59,9 @@ def _check_c2(backend, scale, triangles):
     for shift in (24, 16, 8):
         a = ((native >> shift) & 0xff).astype(np.float64)
         b = ((img >> shift) & 0xff).astype(np.float64).reshape(H, scale, W, scale).mean(axis=(1, 3))
-        assert np.abs(a - b).mean() < 4.0  # same picture ...
+        # same picture (the textures are random noise, so the four sub-samples of a pixel do not average to the native
+        # sample exactly: ~10 of 255 per covered pixel, against ~85 for unrelated images) ...
+        assert np.abs(a - b)[native != 0].mean() < 16.0
     assert sum(np.array_equal(img[sy::scale, sx::scale], native) for sy in range(scale) for sx in range(scale)) == 0  # ... but not a replica
     covered_native = (native != 0).sum()
     covered_up = (img != 0).sum() / (scale * scale)
