@@ -203,7 +203,7 @@ class CommandProcessor:
     def scanout_sync(self, opts: ScanoutOptions | None = None, out: np.ndarray | None = None):
         """Returns (pixels[h, w] uint32 RGBA8 little-endian bytes r,g,b,a, w, h)."""
         if out is None:
-            out = np.empty(640 * 576 * 4, dtype=np.uint32)
+            out = np.empty(640 * 576 * self.upscaling_factor() ** 2, dtype=np.uint32)
         w, h = C.c_uint(0), C.c_uint(0)
         self.lib.rdp_b200_scanout_sync(self._h, C.byref(opts) if opts is not None else None, out.ctypes.data, out.size,
                                        C.byref(w), C.byref(h))

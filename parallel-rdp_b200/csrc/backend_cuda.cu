@@ -1031,6 +1031,14 @@ __global__ void __launch_bounds__(256) k_vi_scale(ViFrame f, ViBuffers b)
 		vi_scale_thread(f, b, x, y);
 }
 
+__global__ void __launch_bounds__(256) k_vi_downscale(const uint32_t *src, int src_width, uint32_t *dst, int dst_width, int dst_height)
+{
+	const int x = int(blockIdx.x * blockDim.x + threadIdx.x);
+	const int y = int(blockIdx.y * blockDim.y + threadIdx.y);
+	if (x < dst_width && y < dst_height)
+		vi_downscale_thread(src, src_width, dst, dst_width, x, y);
+}
+
 // ---- tile-kernel instantiations ------------------------------------------------------------------------------
 // Ordered from most to least specialised; a pass runs the first entry that covers all of its non-fill states
 // (rdp_spec.h).  The last entry is the fully dynamic uber-kernel.
@@ -1170,6 +1178,8 @@ struct rdpb_device
 	uint8_t *up_rdram = nullptr, *up_hidden = nullptr, *up_reference = nullptr;
 	Span *up_spans = nullptr;
 	uint32_t *up_fine = nullptr, *up_coarse = nullptr;
+	uint32_t *vi_down[2] = { nullptr, nullptr }; // down-sized results of an upscaled scan-out, per output slot
+	uint32_t *vi_result[2] = { nullptr, nullptr }; // what the last scan-out into each slot produced (full or down-sized)
 	uint32_t *d_fine = nullptr, *d_coarse = nullptr;
 	uint32_t *d_jobs = nullptr, *d_job_counter = nullptr;
 
@@ -1360,14 +1370,15 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 			dev->readback_in_flight[dev->vi_out_index] = false;
 		}
 		ViBuffers b;
-		b.rdram = dev->rdram;
-		b.hidden = dev->hidden;
+		const ViFrame &f = op.vi;
+		b.rdram = f.scale_log2 ? dev->up_rdram : dev->rdram;
+		b.hidden = f.scale_log2 ? dev->up_hidden : dev->hidden;
 		b.gamma_lut = dev->gamma_lut;
 		b.lines = op.lines;
 		b.filtered = dev->vi_filtered;
 		b.out = dev->vi_out[dev->vi_out_index];
 		b.prev = dev->vi_out[dev->vi_out_index ^ 1u];
-		const ViFrame &f = op.vi;
+		dev->vi_result[dev->vi_out_index] = b.out;
 		if (f.filt_width > 0 && f.filt_height > 0)
 		{
 			const dim3 block(32, 8);
@@ -1384,6 +1395,26 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 			k_vi_scale<<<grid, block, 0, dev->stream>>>(f, b);
 			prof_end(dev, s);
 			dev->launches++;
+		}
+		// Upscaled scan-out: halve the finished image downscale_steps times.  The full-size image stays where it is
+		// (the next field merges with it); the steps ping-pong between the filter stage (free by now) and the
+		// down-sized result buffer so that the last one lands in the latter.
+		if (f.scale_log2 && f.downscale_steps)
+		{
+			const uint32_t *src = b.out;
+			int w = f.out_width, h = f.out_height;
+			for (uint32_t i = 0; i < f.downscale_steps; i++)
+			{
+				uint32_t *dst = ((f.downscale_steps - i) & 1u) ? dev->vi_down[dev->vi_out_index] : dev->vi_filtered;
+				const dim3 block(32, 8);
+				const dim3 grid((w / 2 + 31) / 32, (h / 2 + 7) / 8);
+				k_vi_downscale<<<grid, block, 0, dev->stream>>>(src, w, dst, w / 2, h / 2);
+				dev->launches++;
+				src = dst;
+				w /= 2;
+				h /= 2;
+			}
+			dev->vi_result[dev->vi_out_index] = const_cast<uint32_t *>(src);
 		}
 		break;
 	}
@@ -1574,6 +1605,8 @@ void rdpb_device_destroy(rdpb_device *dev)
 	cudaFree(dev->up_spans);
 	cudaFree(dev->up_fine);
 	cudaFree(dev->up_coarse);
+	cudaFree(dev->vi_down[0]);
+	cudaFree(dev->vi_down[1]);
 	cudaFree(dev->d_fine);
 	cudaFree(dev->d_coarse);
 	cudaFree(dev->d_jobs);
@@ -1840,6 +1873,21 @@ int rdpb_upscaling_init(rdpb_device *dev, uint32_t scale_log2)
 	CK(cudaMemsetAsync(dev->up_reference, 0, dev->rdram_size, dev->stream));
 	CK(cudaMemsetAsync(dev->up_fine, 0, fine_bytes, dev->stream));
 	CK(cudaMemsetAsync(dev->up_coarse, 0, coarse_bytes, dev->stream));
+	// The scan-out stages grow with the image: filter stage, the two output images, and room for down-sized results.
+	CK(cudaStreamSynchronize(dev->stream));
+	const size_t stage_bytes = (size_t(kViStageWidth) * kViStageHeight * 2 * 4) << (2 * scale_log2);
+	const size_t out_bytes = (size_t(640) * 576 * 4) << (2 * scale_log2);
+	cudaFree(dev->vi_filtered);
+	cudaFree(dev->vi_out[0]);
+	cudaFree(dev->vi_out[1]);
+	CK(cudaMalloc(&dev->vi_filtered, stage_bytes));
+	for (int i = 0; i < 2; i++)
+	{
+		CK(cudaMalloc(&dev->vi_out[i], out_bytes));
+		CK(cudaMalloc(&dev->vi_down[i], out_bytes / 4));
+		CK(cudaMemsetAsync(dev->vi_out[i], 0, out_bytes, dev->stream));
+		dev->vi_result[i] = nullptr;
+	}
 	dev->scale_log2 = scale_log2;
 	return 0;
 }
@@ -1907,11 +1955,13 @@ int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *line
 	return issue(dev, op);
 }
 
-void *rdpb_vi_output_device_ptr(rdpb_device *dev) { return dev->vi_out[dev->vi_out_index]; }
+static uint32_t *vi_result_ptr(rdpb_device *dev, unsigned idx) { return dev->vi_result[idx] ? dev->vi_result[idx] : dev->vi_out[idx]; }
+
+void *rdpb_vi_output_device_ptr(rdpb_device *dev) { return vi_result_ptr(dev, dev->vi_out_index); }
 
 int rdpb_vi_read_output(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, int sync)
 {
-	return copy_common(dev, dst, dev->vi_out[dev->vi_out_index], size_t(width) * height * 4, cudaMemcpyDeviceToHost, sync);
+	return copy_common(dev, dst, vi_result_ptr(dev, dev->vi_out_index), size_t(width) * height * 4, cudaMemcpyDeviceToHost, sync);
 }
 
 static int signal_on(rdpb_device *dev, uint64_t value, cudaStream_t stream);
@@ -1925,7 +1975,7 @@ int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint
 	CK(cudaEventRecord(dev->vi_done, dev->stream));
 	CK(cudaStreamWaitEvent(dev->stream_down, dev->vi_done, 0));
 	if (width && height)
-		CK(cudaMemcpyAsync(dst, dev->vi_out[idx], size_t(width) * height * 4, cudaMemcpyDeviceToHost, dev->stream_down));
+		CK(cudaMemcpyAsync(dst, vi_result_ptr(dev, idx), size_t(width) * height * 4, cudaMemcpyDeviceToHost, dev->stream_down));
 	CK(cudaEventRecord(dev->readback_done[idx], dev->stream_down));
 	dev->readback_in_flight[idx] = true;
 	return signal_on(dev, fence_value, dev->stream_down);

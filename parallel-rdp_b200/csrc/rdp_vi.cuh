@@ -60,6 +60,12 @@ struct ViFrame
 	int32_t blend_count;
 	int32_t blend_rect[3][4]; // x0, y0, x1, y1
 	int32_t prev_width, prev_height; // 0 when there is no previous image
+
+	// Internal upscaling (video_interface.cpp:1299-1317, extract_vram.comp:61-66): the framebuffer is read from the
+	// upscaled domain's slices and every coordinate above is in upscaled pixels; the finished image can be halved
+	// `downscale_steps` times (video_interface.cpp:1001-1064).
+	uint32_t scale_log2;
+	uint32_t downscale_steps;
 };
 
 struct ViBuffers
@@ -98,10 +104,17 @@ RDP_HD ViColor vi_read_vram(const ViFrame &f, const ViBuffers &b, int x, int y)
 {
 	ViColor c;
 	const uint32_t type = f.status & VI_STATUS_TYPE_MASK;
+	// Upscaled pixel (x, y) is native pixel (x >> sl, y >> sl) of slice (y % S) * S + x % S.
+	const int sl = int(f.scale_log2);
+	const uint32_t slice = (uint32_t(y) & ((1u << sl) - 1u)) * (1u << sl) + (uint32_t(x) & ((1u << sl) - 1u));
+	x >>= sl;
+	y >>= sl;
+	const uint8_t *rdram = b.rdram + size_t(slice) * f.rdram_size;
+	const uint8_t *hidden = b.hidden + size_t(slice) * (f.rdram_size >> 1);
 	if (type == VI_STATUS_TYPE_RGBA8888)
 	{
 		uint32_t idx = uint32_t(y * int(f.fb_width) + x + int(f.fb_offset)) & ((f.rdram_size >> 2) - 1u);
-		const uint32_t w = reinterpret_cast<const uint32_t *>(b.rdram)[idx];
+		const uint32_t w = reinterpret_cast<const uint32_t *>(rdram)[idx];
 		c.r = int(w >> 24);
 		c.g = int((w >> 16) & 0xff);
 		c.b = int((w >> 8) & 0xff);
@@ -110,11 +123,11 @@ RDP_HD ViColor vi_read_vram(const ViFrame &f, const ViBuffers &b, int x, int y)
 	else if (type == VI_STATUS_TYPE_RGBA5551)
 	{
 		uint32_t idx = uint32_t(y * int(f.fb_width) + x + int(f.fb_offset)) & ((f.rdram_size >> 1) - 1u);
-		const uint32_t w = reinterpret_cast<const uint16_t *>(b.rdram)[idx ^ 1u];
+		const uint32_t w = reinterpret_cast<const uint16_t *>(rdram)[idx ^ 1u];
 		c.r = int((w >> 8) & 0xf8u);
 		c.g = int((w >> 3) & 0xf8u);
 		c.b = int((w << 2) & 0xf8u);
-		c.a = int(((w & 1u) << 2) | b.hidden[idx]);
+		c.a = int(((w & 1u) << 2) | hidden[idx]);
 	}
 	else
 		c.r = c.g = c.b = c.a = 0;
@@ -397,6 +410,20 @@ RDP_HD void vi_scale_thread(const ViFrame &f, const ViBuffers &b, int ox, int oy
 		}
 	}
 	b.out[size_t(oy) * size_t(f.out_width) + size_t(ox)] = result;
+}
+
+// One halving step of the finished upscaled image: each output pixel is the rounded mean of a 2x2 block (the
+// reference blits with a linear filter at exactly half size, video_interface.cpp:1054-1057).
+RDP_HD void vi_downscale_thread(const uint32_t *src, int src_width, uint32_t *dst, int dst_width, int x, int y)
+{
+	const uint32_t p00 = src[size_t(2 * y) * size_t(src_width) + size_t(2 * x)];
+	const uint32_t p10 = src[size_t(2 * y) * size_t(src_width) + size_t(2 * x + 1)];
+	const uint32_t p01 = src[size_t(2 * y + 1) * size_t(src_width) + size_t(2 * x)];
+	const uint32_t p11 = src[size_t(2 * y + 1) * size_t(src_width) + size_t(2 * x + 1)];
+	uint32_t out = 0;
+	for (int sh = 0; sh < 32; sh += 8)
+		out |= ((((p00 >> sh) & 0xffu) + ((p10 >> sh) & 0xffu) + ((p01 >> sh) & 0xffu) + ((p11 >> sh) & 0xffu) + 2u) >> 2) << sh;
+	dst[size_t(y) * size_t(dst_width) + size_t(x)] = out;
 }
 
 void build_blender_lut(uint8_t *lut);

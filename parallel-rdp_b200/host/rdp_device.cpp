@@ -61,7 +61,8 @@ CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, 
 		const uint32_t up = (flags & COMMAND_PROCESSOR_FLAG_UPSCALING_8X_BIT) ? 3u :
 		                    (flags & COMMAND_PROCESSOR_FLAG_UPSCALING_4X_BIT) ? 2u :
 		                    (flags & COMMAND_PROCESSOR_FLAG_UPSCALING_2X_BIT) ? 1u : 0u;
-		renderer.set_upscaling(up);
+		if (renderer.set_upscaling(up))
+			vi.set_upscaling_log2(renderer.get_upscaling_log2());
 	}
 	vi.init(device, rdram_size);
 

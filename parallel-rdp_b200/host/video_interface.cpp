@@ -294,8 +294,8 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 		if (options.persist_frame_on_invalid_input && (frame_count - last_valid_frame_count < 4) && have_prev_scanout)
 		{
 			result.device_rgba8 = rdpb_vi_output_device_ptr(device);
-			result.width = prev_width;
-			result.height = prev_height;
+			result.width = prev_result_width;
+			result.height = prev_result_height;
 		}
 		else
 			have_prev_scanout = false;
@@ -307,6 +307,46 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 	const bool divot = (regs.status & VI_CONTROL_DIVOT_ENABLE_BIT) != 0;
 	const bool serrate = (regs.status & VI_CONTROL_SERRATE_BIT) != 0 && !options.upscale_deinterlacing;
 
+	// Internal upscaling: everything measured in framebuffer or output pixels scales with the image
+	// (ref video_interface.cpp:1299-1317); the per-pixel steps (x_add, y_add) do not.
+	const int scale = 1 << scale_log2;
+	if (scale > 1)
+	{
+		// The framebuffer may hold pixels the RDP never rendered (CPU-drawn screens): bring the upscaled domain up to
+		// date over the range this scan-out can read (ref vram_fetch_stage, video_interface.cpp:412-420, 369-396).
+		{
+			const int pixel_size_log2 = (regs.status & VI_CONTROL_TYPE_MASK) == VI_CONTROL_TYPE_RGBA8888_BIT ? 2 : 1;
+			const int aa_width = regs.max_x + 2 + 4 + int(divot) * 2;
+			const int aa_height = regs.max_y + 1 + 4;
+			int offset = regs.vi_offset & ~((1 << pixel_size_log2) - 1);
+			offset += ((divot ? -3 : -2) + -2 * regs.vi_width) << pixel_size_log2;
+			FbInfo range = {};
+			range.color_addr = range.depth_addr = uint32_t(offset) & uint32_t(rdram_size - 1);
+			range.width = uint32_t(aa_height * regs.vi_width + aa_width);
+			range.height = 1;
+			range.fmt = pixel_size_log2 == 2 ? uint32_t(FB_RGBA8888) : uint32_t(FB_RGBA5551);
+			range.rdram_size = uint32_t(rdram_size);
+			rdpb_launch_upscale_sync(device, &range, RDPB_UPSCALE_SYNC_PRE);
+		}
+		regs.h_start *= scale;
+		regs.h_start_clamp *= scale;
+		regs.v_start *= scale;
+		regs.h_res *= scale;
+		regs.h_res_clamp *= scale;
+		regs.v_res *= scale;
+		regs.max_x = regs.max_x * scale + (scale - 1);
+		regs.max_y = regs.max_y * scale + (scale - 1);
+		for (auto &line : lines)
+		{
+			line.h_start *= scale;
+			line.h_start_clamp *= scale;
+			line.h_end_clamp *= scale;
+			line.x_start *= scale;
+			line.y_start *= scale;
+			line.y_base *= scale;
+		}
+	}
+
 	ViFrame f = {};
 	// NB: blank (0) / reserved (1) types were promoted to 5551 / 8888 above; the first blank frame after a
 	// valid one is still scanned out with that promoted type, exactly like the oracle does.
@@ -314,16 +354,17 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 	f.fb_width = uint32_t(regs.vi_width);
 	f.fb_offset = uint32_t(regs.vi_offset) >> ((regs.status & VI_CONTROL_TYPE_MASK) == VI_CONTROL_TYPE_RGBA8888_BIT ? 2 : 1);
 	f.rdram_size = uint32_t(rdram_size);
-	f.fetch_bug = (regs.init_y_add < 1024) ? 1u : 0u;
-	f.filt_width = std::min<int>(regs.max_x + 2, kViStageWidth);
-	f.filt_height = std::min<int>(regs.max_y + 2, kViStageHeight);
-	f.stage_stride = kViStageWidth;
-	f.layer_stride = kViStageWidth * kViStageHeight;
+	f.fetch_bug = (regs.init_y_add < 1024 && scale == 1) ? 1u : 0u; // ref need_fetch_bug_emulation, video_interface.cpp:398-403
+	f.scale_log2 = scale_log2;
+	f.filt_width = std::min<int>(regs.max_x + 2, int(kViStageWidth) * scale);
+	f.filt_height = std::min<int>(regs.max_y + 2, int(kViStageHeight) * scale);
+	f.stage_stride = kViStageWidth * uint32_t(scale);
+	f.layer_stride = f.stage_stride * kViStageHeight * uint32_t(scale);
 	(void)divot;
 
 	// Output geometry.
-	unsigned width = VI_SCANOUT_WIDTH;
-	unsigned height = (regs.is_pal ? VI_V_RES_PAL : VI_V_RES_NTSC) >> int(!serrate);
+	unsigned width = VI_SCANOUT_WIDTH * unsigned(scale);
+	unsigned height = ((regs.is_pal ? VI_V_RES_PAL : VI_V_RES_NTSC) >> int(!serrate)) * unsigned(scale);
 	unsigned crop_left, crop_right, crop_top, crop_bottom;
 	if (options.crop_rect.enable)
 	{
@@ -344,6 +385,10 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 		crop_left = crop_right = crop_x;
 		crop_top = crop_bottom = crop_y;
 	}
+	crop_left *= unsigned(scale);
+	crop_right *= unsigned(scale);
+	crop_top *= unsigned(scale);
+	crop_bottom *= unsigned(scale);
 	if (crop_left + crop_right < width && crop_top + crop_bottom < height)
 	{
 		width -= crop_left + crop_right;
@@ -358,6 +403,7 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 	f.crop_top = int(crop_top);
 	f.y_add = regs.init_y_add;
 	f.frame_count = frame_count;
+	f.info_y_shift = int(scale_log2);
 	if (serrate)
 	{
 		regs.v_start *= 2;
@@ -365,8 +411,10 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 		f.serrate_shift = 1;
 		f.serrate_mask = 1;
 		f.serrate_select = regs.v_current_line == 0 ? 1 : 0;
-		f.info_y_shift = 1;
+		f.info_y_shift++;
 	}
+	// Halving steps of the finished image (ref downscale_stage, video_interface.cpp:1001-1064): at most down to 1x.
+	f.downscale_steps = std::min<uint32_t>(std::min(8u, options.downscale_steps), scale_log2);
 	f.v_start = regs.v_start;
 
 	const int dx = -int(crop_left), dy = -int(crop_top);
@@ -413,11 +461,13 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 	have_prev_scanout = true;
 	prev_width = width;
 	prev_height = height;
+	prev_result_width = width >> f.downscale_steps;
+	prev_result_height = height >> f.downscale_steps;
 	frame_count++;
 
 	result.device_rgba8 = rdpb_vi_output_device_ptr(device);
-	result.width = width;
-	result.height = height;
+	result.width = width >> f.downscale_steps;
+	result.height = height >> f.downscale_steps;
 	return result;
 }
 }

@@ -148,6 +148,8 @@ public:
 	};
 
 	void init(rdpb_device *device, size_t rdram_size);
+	// Internal upscaling: scan out of the upscaled domain at (1 << log2) times the resolution (ref video_interface.cpp:1215-1317).
+	void set_upscaling_log2(uint32_t log2) { scale_log2 = log2; }
 	void set_vi_register(VIRegister reg, uint32_t value);
 	// Copies the register file for one scan-out and resets the per-scanline latches (as scanout() always did).
 	void capture_registers(RegisterFile &out);
@@ -162,13 +164,15 @@ public:
 private:
 	rdpb_device *device = nullptr;
 	size_t rdram_size = 0;
+	uint32_t scale_log2 = 0;
 	RegisterFile regfile;
 
 	uint32_t frame_count = 0;
 	uint32_t last_valid_frame_count = 0;
 	bool previous_frame_blank = false;
 	bool have_prev_scanout = false;
-	unsigned prev_width = 0, prev_height = 0;
+	unsigned prev_width = 0, prev_height = 0;               // full-size image the next field merges with
+	unsigned prev_result_width = 0, prev_result_height = 0; // what scanout() returned (after downscale steps)
 
 	rdpb::ViRegs decode_vi_registers(const RegisterFile &file, rdpb::ViLine *lines) const;
 	void clear_per_scanline_state();

@@ -36,6 +36,7 @@ struct rdpb_device
 	rdpb_pass_counts counts = {};
 	std::vector<uint32_t> vi_stage[3];
 	std::vector<uint32_t> vi_out, vi_prev;
+	const uint32_t *vi_result = nullptr; // what the last scan-out produced (vi_out, or a down-sized copy)
 	uint64_t launches = 0;
 	uint64_t deferred_passes = 0;
 	bool last_deferred = false;
@@ -319,18 +320,19 @@ int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *line
 	if (g_null_compute)
 		return 0;
 	const ViFrame f = *static_cast<const ViFrame *>(frame);
-	const size_t max_out = size_t(640) * 576;
+	const size_t scale2 = size_t(1) << (2 * dev->scale_log2);
+	const size_t max_out = size_t(640) * 576 * scale2;
 	if (dev->vi_out.size() != max_out)
 	{
 		dev->vi_out.assign(max_out, 0);
 		dev->vi_prev.assign(max_out, 0);
-		dev->vi_stage[0].assign(size_t(kViStageWidth) * kViStageHeight * 2, 0);
+		dev->vi_stage[0].assign(size_t(kViStageWidth) * kViStageHeight * 2 * scale2, 0);
 	}
 	std::swap(dev->vi_out, dev->vi_prev);
 
 	ViBuffers b;
-	b.rdram = dev->rdram.data();
-	b.hidden = dev->hidden.data();
+	b.rdram = f.scale_log2 ? dev->up_rdram.data() : dev->rdram.data();
+	b.hidden = f.scale_log2 ? dev->up_hidden.data() : dev->hidden.data();
 	b.gamma_lut = dev->gamma_lut.data();
 	b.lines = static_cast<const ViLine *>(lines);
 	b.filtered = dev->vi_stage[0].data();
@@ -345,14 +347,36 @@ int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *line
 		for (int x = 0; x < f.out_width; x++)
 			vi_scale_thread(f, b, x, y);
 	dev->launches += 2;
+
+	dev->vi_result = dev->vi_out.data();
+	if (f.scale_log2 && f.downscale_steps)
+	{
+		// Halve the finished image; the full-size one stays for the next field's merge.
+		std::vector<uint32_t> *bufs[2] = { &dev->vi_stage[1], &dev->vi_stage[2] };
+		const uint32_t *src = dev->vi_out.data();
+		int w = f.out_width, h = f.out_height;
+		for (uint32_t i = 0; i < f.downscale_steps; i++)
+		{
+			std::vector<uint32_t> &dst = *bufs[i & 1];
+			dst.assign(size_t(w / 2) * (h / 2), 0);
+			for (int y = 0; y < h / 2; y++)
+				for (int x = 0; x < w / 2; x++)
+					vi_downscale_thread(src, w, dst.data(), w / 2, x, y);
+			src = dst.data();
+			w /= 2;
+			h /= 2;
+			dev->launches++;
+		}
+		dev->vi_result = src;
+	}
 	return 0;
 }
 
-void *rdpb_vi_output_device_ptr(rdpb_device *dev) { return dev->vi_out.data(); }
+void *rdpb_vi_output_device_ptr(rdpb_device *dev) { return const_cast<uint32_t *>(dev->vi_result ? dev->vi_result : dev->vi_out.data()); }
 
 int rdpb_vi_read_output(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, int)
 {
-	memcpy(dst, dev->vi_out.data(), size_t(width) * height * 4);
+	memcpy(dst, dev->vi_result ? dev->vi_result : dev->vi_out.data(), size_t(width) * height * 4);
 	return 0;
 }
 

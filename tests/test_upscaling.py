@@ -168,3 +168,72 @@ def test_gpu_conformance_with_upscaling(name):
         finally:
             sbs.close()
     assert digests["cuda"] == digests["hostsim"]
+
+
+# --- scan-out of the upscaled domain (video_interface.cpp:1215-1426 with scaling_factor > 1) -------------------------
+def _scanout_c2(backend, scale, triangles, steps):
+    """One C2 frame, scanned out with `downscale_steps` = each of `steps`: list of (pixels, w, h), plus the oracle image."""
+    sbs = SideBySide(backend, rdram_size=wl.RDRAM_SIZE, hidden_size=wl.HIDDEN_SIZE, flags=FLAGS.get(scale, 0))
+    try:
+        _c2(sbs, triangles)
+        for k, v in wl.c2_vi_registers(0).items():
+            sbs.set_vi_register(rdp.VI_REG[k], v)
+        ref = sbs.oracle.update_screen()
+        outs = []
+        for n in steps:
+            opts = sbs.gpu.default_scanout_options()
+            opts.blend_previous_frame = 0
+            opts.upscale_deinterlacing = 0
+            opts.downscale_steps = n
+            opts.vi_gamma_dither = 0  # the dither noise is seeded by the frame counter: keep repeated scan-outs comparable
+            pix, w, h = sbs.gpu.scanout_sync(opts)
+            outs.append((pix.copy(), w, h))
+        return outs, ref
+    finally:
+        sbs.close()
+
+
+def _rgb_planes(img):
+    return [((img >> s) & 0xff).astype(np.float64) for s in (0, 8, 16)]
+
+
+def _check_scanout(backend, scale, triangles):
+    log2 = scale.bit_length() - 1
+    outs, ref = _scanout_c2(backend, scale, triangles, list(range(log2 + 2)))
+    (native_like, w0, h0) = outs[log2]  # halved all the way down: the native output size
+    assert (w0, h0) == (ref.shape[1], ref.shape[0])
+    for n, (pix, w, h) in enumerate(outs):
+        eff = min(n, log2)
+        assert (w, h) == (ref.shape[1] * scale >> eff, ref.shape[0] * scale >> eff)
+        assert pix.any()
+    # more steps than there is scale to undo changes nothing (video_interface.cpp:1009)
+    assert np.array_equal(outs[log2][0], outs[log2 + 1][0])
+    # each step is exactly the rounded 2x2 mean of the previous image
+    for n in range(log2):
+        big, small = outs[n][0], outs[n + 1][0]
+        for a, b in zip(_rgb_planes(big), _rgb_planes(small)):
+            box = np.floor((a.reshape(b.shape[0], 2, b.shape[1], 2).sum(axis=(1, 3)) + 2) / 4)
+            assert np.array_equal(box, b)
+    # and the fully halved image is the native scan-out up to what supersampling changes (edges, texture detail)
+    for a, b in zip(_rgb_planes(native_like), _rgb_planes(ref)):
+        assert np.abs(a - b)[ref != 0].mean() < 16.0
+    return hashlib.sha256(b"".join(o[0].tobytes() for o in outs)).hexdigest()
+
+
+@pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
+def test_hostsim_upscaled_scanout():
+    _check_scanout("hostsim", 2, 150)
+
+
+@pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
+def test_hostsim_downscale_steps_are_ignored_without_upscaling():
+    outs, ref = _scanout_c2("hostsim", 1, 150, [0, 2])
+    assert outs[0][1:] == outs[1][1:] == (ref.shape[1], ref.shape[0])
+    assert np.array_equal(outs[0][0], outs[1][0])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("scale", [2, 4])
+def test_gpu_upscaled_scanout_matches_scalar_statement(scale):
+    assert _check_scanout("cuda", scale, 800) == _check_scanout("hostsim", scale, 800)
