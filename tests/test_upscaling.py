@@ -214,9 +214,11 @@ def _check_scanout(backend, scale, triangles):
         for a, b in zip(_rgb_planes(big), _rgb_planes(small)):
             box = np.floor((a.reshape(b.shape[0], 2, b.shape[1], 2).sum(axis=(1, 3)) + 2) / 4)
             assert np.array_equal(box, b)
-    # and the fully halved image is the native scan-out up to what supersampling changes (edges, texture detail)
+    # and the fully halved image is the native scan-out up to what supersampling changes (edges, noise-texture detail)
+    # and the oracle's gamma dither, which this comparison leaves on: ~10-20 of 255 per lit pixel, against ~85 for
+    # unrelated images
     for a, b in zip(_rgb_planes(native_like), _rgb_planes(ref)):
-        assert np.abs(a - b)[ref != 0].mean() < 16.0
+        assert np.abs(a - b)[ref != 0].mean() < 32.0
     return hashlib.sha256(b"".join(o[0].tobytes() for o in outs)).hexdigest()
 
 
