@@ -1055,22 +1055,25 @@ struct TileVariant
 	TileKernel kernel;
 };
 
-template <class S, bool DEFERRED = false>
+template <class S, bool DEFERRED = false, bool UPSCALED = false>
 static TileVariant make_variant(const char *name)
 {
 	static_assert(!DEFERRED || (S::rf_may & kRfNotDeferrable) == 0u || S::rf_may == ~0u,
 	              "a deferred feature class must exclude the states the deferred pipeline cannot run");
 	return { name, S::rf_may, S::rf_must, S::bf_may, S::bf_must, S::fmt_mask, S::tk_mask, S::exact, S::comb_rgb, S::comb_alpha,
-		     S::blend_misc, DEFERRED, &k_tiles<S, DEFERRED> };
+		     S::blend_misc, DEFERRED, &k_tiles<S, DEFERRED, UPSCALED> };
 }
 
 #include "rdp_variants.inc"
 
-static_assert(sizeof(kTileVariants) / sizeof(kTileVariants[0]) <= 31, "grow rdpb_device::variant_blocks_per_sm (slot 31 is the upscaled kernel)");
+static_assert(sizeof(kTileVariants) / sizeof(kTileVariants[0]) <= 30, "grow rdpb_device::variant_blocks_per_sm (slots 30, 31 are the upscaled kernels)");
 
-// Upscaled passes: the dynamic in-order kernel with run-time scale (one instantiation serves 2x / 4x / 8x).
-static const TileVariant kUpscaledVariant = { "generic/upscaled", ~0u, 0u, ~0u, 0u, 0x1fu, ~0u, false, 0ull, 0u, 0u, false,
-	                                          &k_tiles<SpecGeneric, false, true> };
+// Upscaled passes: in-order kernels with a run-time scale (one instantiation serves 2x / 4x / 8x) -- the hot exact
+// state, then the dynamic kernel.  Matched like kTileVariants.
+static const TileVariant kUpscaledVariants[] = {
+	make_variant<variants::ZbOpaTexModulate2C, false, true>("zb-opa-tex-modulate-2c/rgba32/upscaled"),
+	make_variant<SpecGeneric, false, true>("generic/upscaled"),
+};
 
 // Not a tile kernel: fill-only passes of at most kFillPassMaxPrims primitives (launched per pixel, see k_fill_pass).
 static const TileVariant kFillPassVariant = { "fill-pass", 0u, 0u, 0u, 0u, 0x1fu, 0u, false, 0ull, 0u, 0u, false, &k_fill_pass };
@@ -1078,22 +1081,11 @@ static const TileVariant kFillPassVariant = { "fill-pass", 0u, 0u, 0u, 0u, 0x1fu
 // Environment switches (read per pass, so tests can flip them): RDP_B200_FORCE_GENERIC pins the in-order uber-kernel,
 // RDP_B200_NO_DEFERRED keeps every pass on the in-order kernels, RDP_B200_FORCE_DEFERRED sends every deferrable
 // pass through the fully dynamic deferred kernel (how the conformance suites exercise it).
-static const TileVariant *pick_tile_variant(const PassSummary *sum, const FbInfo &fb)
+static const TileVariant *match_tile_variant(const TileVariant *table, size_t n, const PassSummary *sum, uint32_t fmt, bool deferrable)
 {
-	if (fb.scale_log2)
-		return &kUpscaledVariant;
-	const uint32_t fmt = fb.fmt;
-	const size_t n = sizeof(kTileVariants) / sizeof(kTileVariants[0]);
-	if (!sum || getenv("RDP_B200_FORCE_GENERIC"))
-		return &kTileVariants[n - 1];
-	if (sum->num_shaded_states == 0 && fb.num_prims <= kFillPassMaxPrims && !getenv("RDP_B200_NO_FILL_PASS"))
-		return &kFillPassVariant;
-	const bool deferrable = deferrable_pass(*sum, fb) && sum->num_shaded_states != 0 && !getenv("RDP_B200_NO_DEFERRED");
-	if (deferrable && getenv("RDP_B200_FORCE_DEFERRED"))
-		return &kTileVariants[n - 2];
 	for (size_t i = 0; i < n; i++)
 	{
-		const TileVariant &v = kTileVariants[i];
+		const TileVariant &v = table[i];
 		if (!(v.fmt_mask & (1u << fmt)))
 			continue;
 		if (v.deferred && !deferrable)
@@ -1112,7 +1104,27 @@ static const TileVariant *pick_tile_variant(const PassSummary *sum, const FbInfo
 		}
 		return &v;
 	}
-	return &kTileVariants[n - 1];
+	return &table[n - 1];
+}
+
+static const TileVariant *pick_tile_variant(const PassSummary *sum, const FbInfo &fb)
+{
+	if (fb.scale_log2)
+	{
+		const size_t nu = sizeof(kUpscaledVariants) / sizeof(kUpscaledVariants[0]);
+		if (!sum || sum->num_shaded_states == 0 || getenv("RDP_B200_FORCE_GENERIC"))
+			return &kUpscaledVariants[nu - 1];
+		return match_tile_variant(kUpscaledVariants, nu, sum, fb.fmt, false);
+	}
+	const size_t n = sizeof(kTileVariants) / sizeof(kTileVariants[0]);
+	if (!sum || getenv("RDP_B200_FORCE_GENERIC"))
+		return &kTileVariants[n - 1];
+	if (sum->num_shaded_states == 0 && fb.num_prims <= kFillPassMaxPrims && !getenv("RDP_B200_NO_FILL_PASS"))
+		return &kFillPassVariant;
+	const bool deferrable = deferrable_pass(*sum, fb) && sum->num_shaded_states != 0 && !getenv("RDP_B200_NO_DEFERRED");
+	if (deferrable && getenv("RDP_B200_FORCE_DEFERRED"))
+		return &kTileVariants[n - 2];
+	return match_tile_variant(kTileVariants, n, sum, fb.fmt, deferrable);
 }
 
 // One GPU-side operation, as issued live or replayed from the log.
@@ -1325,7 +1337,8 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		}
 		const uint32_t tiles = op.fb.tiles_x * op.fb.tiles_y;
 		// Persistent grid: exactly as many blocks as can be resident (occupancy of this instantiation x SMs).
-		const size_t vi = op.variant == &kUpscaledVariant ? 31 : size_t(op.variant - kTileVariants);
+		const bool up = op.variant >= kUpscaledVariants && op.variant < kUpscaledVariants + sizeof(kUpscaledVariants) / sizeof(kUpscaledVariants[0]);
+		const size_t vi = up ? 30 + size_t(op.variant - kUpscaledVariants) : size_t(op.variant - kTileVariants);
 		if (!dev->variant_blocks_per_sm[vi])
 		{
 			int n = 0;
