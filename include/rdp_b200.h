@@ -96,6 +96,9 @@ void *rdp_b200_get_tmem(rdp_b200_processor *p);
 
 /* set_vi_register, rdp_device.cpp:970-975 */
 void rdp_b200_set_vi_register(rdp_b200_processor *p, uint32_t reg, uint32_t value);
+/* Extension: all 14 VI registers in one call, in register-number order (what a dump replayer or an emulator's
+ * vertical-interrupt handler has at hand); equivalent to 14 rdp_b200_set_vi_register calls. */
+void rdp_b200_set_vi_registers(rdp_b200_processor *p, const uint32_t values[14]);
 /* Per-scanline VI registers, rdp_device.cpp:977-995 */
 void rdp_b200_begin_vi_register_per_scanline(rdp_b200_processor *p, uint32_t flags);
 void rdp_b200_set_vi_register_for_scanline(rdp_b200_processor *p, uint32_t reg_bit, uint32_t value);

@@ -54,6 +54,7 @@ def _bind(lib):
         "rdp_b200_get_hidden_rdram_size": (SZ, [P]),
         "rdp_b200_get_tmem": (P, [P]),
         "rdp_b200_set_vi_register": (None, [P, U32, U32]),
+        "rdp_b200_set_vi_registers": (None, [P, P]),
         "rdp_b200_begin_vi_register_per_scanline": (None, [P, U32]),
         "rdp_b200_set_vi_register_for_scanline": (None, [P, U32, U32]),
         "rdp_b200_latch_vi_register_for_scanline": (None, [P, C.c_uint]),
@@ -194,6 +195,11 @@ class CommandProcessor:
     # --- VI -------------------------------------------------------------------------------------------------
     def set_vi_register(self, reg, value: int):
         self.lib.rdp_b200_set_vi_register(self._h, VI_REG[reg] if isinstance(reg, str) else int(reg), value & 0xffffffff)
+
+    def set_vi_registers(self, values: np.ndarray):
+        """All 14 registers at once (uint32[14], register-number order)."""
+        assert values.dtype == np.uint32 and values.size == 14
+        self.lib.rdp_b200_set_vi_registers(self._h, values.ctypes.data)
 
     def default_scanout_options(self) -> ScanoutOptions:
         o = ScanoutOptions()

@@ -91,6 +91,11 @@ void rdp_b200_set_vi_register(rdp_b200_processor *p, uint32_t reg, uint32_t valu
 	if (reg < uint32_t(VIRegister::Count))
 		p->impl.set_vi_register(VIRegister(reg), value);
 }
+void rdp_b200_set_vi_registers(rdp_b200_processor *p, const uint32_t values[14])
+{
+	for (uint32_t r = 0; r < 14; r++)
+		p->impl.set_vi_register(VIRegister(r), values[r]);
+}
 void rdp_b200_begin_vi_register_per_scanline(rdp_b200_processor *p, uint32_t flags) { p->impl.begin_vi_register_per_scanline(flags); }
 void rdp_b200_set_vi_register_for_scanline(rdp_b200_processor *p, uint32_t reg_bit, uint32_t value)
 {
