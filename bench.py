@@ -366,6 +366,14 @@ def run_ours(args):
     out_dims = ((640 * args.upscale) >> ds, (480 * args.upscale) >> ds)
 
     def e2e_run(S, count):
+        if os.environ.get("BENCH_E2E_NO_READBACK"):  # diagnostic only: scan out on the device, no image copy to the host
+            for i in range(count):
+                for s in range(S):
+                    st = streams[s]
+                    st.proc.enqueue_command_stream_borrowed(st.frames[i % st.n])
+                    st.proc.set_vi_registers(st.vi_block[i & 1])
+                    st.proc.scanout(st.opts)
+            return
         fences = [[] for _ in range(S)]
         for i in range(count):
             for s in range(S):
