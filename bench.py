@@ -349,8 +349,14 @@ def run_ours(args):
     alg_total, alg_per_frame = tile_kernel_algorithmic_bytes(tiles_processed, args.steps)
     peak, peak_src = measured_peaks()
     achieved = (alg_total / 1e9) / (tiles_ms / 1e3) if tiles_ms > 0 else 0.0
+    traffic = None
+    try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/)
+        t = json.load(open(os.path.join(ROOT, "profiles", "k_tiles_traffic.json")))
+        traffic = int(t["dram_bytes_read_per_launch"]) + int(t["dram_bytes_write_per_launch"])
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "hbm", "kernel": "k_tiles", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_total / tiles_launches),
                 "avg_launch_us": round(1e3 * tiles_ms / tiles_launches, 3),
                 "kernel_share_of_step": round(tiles_ms / profiled_ms, 4) if profiled_ms > 0 else None,
