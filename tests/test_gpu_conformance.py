@@ -82,3 +82,40 @@ def test_gpu_vi_matches_oracle(name):
     assert not errs, errs
     n = VI_GOLDEN["iterations"]
     assert digests[:n] == VI_GOLDEN["digests"][name]
+
+
+# --- the tile kernels' overflow paths --------------------------------------------------------------------------------
+# Random screen-sized triangles pile hundreds of primitives onto every tile: more than one 128-entry list per tile
+# (several walker runs, no mask staging), more than 256 fragments per 32-entry chunk (several batches in the deferred
+# walker), and -- above 8192 primitives -- the coarse-mask gather instead of the single-round one.
+STRESS = {
+    "deferred-3000": (cf.Variant(color=True, depth=True, primitive_count=3000, depth_compare=True, aa=True, randomize_rdram=True,
+                                 image_read_enable=True), "generic"),
+    "deferred-texture-2cycle-3000": (cf.Variant(color=True, depth=True, texture=True, texture_size=2,
+                                                cycle_type=1, perspective=True, primitive_count=3000, depth_compare=True, aa=True,
+                                                randomize_rdram=True, image_read_enable=True), "generic"),
+    "in-order-alpha-test-3000": (cf.Variant(color=True, depth=True, primitive_count=3000, depth_compare=True, aa=True, alpha_test=True,
+                                            randomize_rdram=True, image_read_enable=True), "generic"),
+    "coarse-gather-9000": (cf.Variant(color=True, depth=True, primitive_count=9000, depth_compare=True, aa=True, randomize_rdram=True,
+                                      image_read_enable=True), "generic"),
+}
+
+
+@pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", sorted(STRESS))
+@pytest.mark.parametrize("force_deferred", [False, True])
+def test_gpu_many_overlapping_primitives(name, force_deferred, monkeypatch):
+    if force_deferred:
+        monkeypatch.setenv("RDP_B200_FORCE_DEFERRED", "1")
+    v, _ = STRESS[name]
+    sbs = SideBySide("cuda")
+    try:
+        errs = cf.run_rasterization(sbs, v, 1)
+        passes = sbs.gpu.pass_count()
+        variant = sbs.gpu.last_tile_variant()
+    finally:
+        sbs.close()
+    assert not errs, errs
+    assert passes <= 4
+    if force_deferred and "alpha-test" not in name:
+        assert variant == "generic+deferred"
