@@ -196,6 +196,9 @@ class CommandProcessor:
     def set_vi_register(self, reg, value: int):
         self.lib.rdp_b200_set_vi_register(self._h, VI_REG[reg] if isinstance(reg, str) else int(reg), value & 0xffffffff)
 
+    def set_quirks(self, native_resolution_tex_rect: bool = True, native_texture_lod: bool = False):
+        self.lib.rdp_b200_set_quirks(self._h, int(native_resolution_tex_rect), int(native_texture_lod))
+
     def set_vi_registers(self, values: np.ndarray):
         """All 14 registers at once (uint32[14], register-number order)."""
         assert values.dtype == np.uint32 and values.size == 14

@@ -1,13 +1,18 @@
 // backend_cuda.cu -- the product backend: CUDA kernels for sm_100a and the C-ABI of include/rdp_b200_backend.h.
 //
-// Kernels (one per render-pass stage, launched in stream order; see rdp_pass.cuh for the per-thread bodies):
-//   k_tmem_update  2048 threads, one per TMEM word            (replaces shaders/tmem_update.comp)
-//   k_prim_setup   one thread per primitive                    (replaces CPU decode, rdp_device.cpp:268-419)
-//   k_span_bin     one warp per primitive, lanes = scanlines   (replaces span_setup.comp + tile_binning_combined.comp;
-//                  warp shuffles reduce each 8-line tile row's X range, lanes then atomicOr the tile masks)
-//   k_tiles        one 8x8 block per tile, one thread per pixel (replaces rasterizer.comp + depth_blend.comp, fused)
-//   k_vi_filter    VI AA / dither-reconstruction / divot straight from RDRAM (extract_vram.comp + vi_fetch + vi_divot)
-//   k_vi_scale     VI scale, gamma, field merge                (vi_scale.frag + vi_blend_fields.frag)
+// Kernels (launched in stream order; rdp_pass.cuh / rdp_blend.cuh / rdp_vi.cuh hold the per-thread bodies):
+//   k_front         TMEM upload replay (one thread per TMEM word) + primitive decode (one thread per primitive) +
+//                   span-job allocation, one launch             (replaces tmem_update.comp, rdp_device.cpp:268-419)
+//   k_span_bin      one warp per (primitive, 32-line chunk), lanes = scanlines: edge walk -> Span, warp shuffles reduce
+//                   each tile row's X range, lanes atomicOr the tile masks (span_setup.comp + tile_binning_combined.comp)
+//   k_tiles<S,D,U>  persistent warps, one 8x4 tile per warp at a time, one lane per pixel; S = static-state
+//                   specialisation, D = deferred pipeline (coverage/Z -> ordered depth -> compacted shading -> ordered
+//                   blend) or in-order walker, U = internal upscaling         (rasterizer.comp + depth_blend.comp)
+//   k_fill_pass     small fill-only passes (clears), per pixel, no tile machinery
+//   k_upscale_sync  PRE / POST synchronisation of the upscaled domain      (update_upscaled_domain_pre/post.comp)
+//   k_vi_filter     VI AA / dither-reconstruction / divot from a shared-memory copy of the framebuffer neighbourhood
+//                   (extract_vram.comp + vi_fetch.frag + vi_divot.frag)
+//   k_vi_scale      VI scale, gamma, field merge (vi_scale.frag + vi_blend_fields.frag); k_vi_downscale halves the image
 // Nothing here is a dense contraction, so no tensor-core path exists; the work is integer ALU + coalesced
 // RDRAM loads/stores.  There is no CPU fallback: creation fails when no CUDA device is usable.
 //
@@ -300,11 +305,12 @@ struct TileWalker
 					if (yy < line_lo || yy > line_hi)
 						continue;
 					const Span *sp = b.spans + ((hdr.x << sl) + uint32_t(yy - line_lo));
-					const uint2 sh = *reinterpret_cast<const uint2 *>(&sp->start_x);
+					const uint4 sh = *reinterpret_cast<const uint4 *>(&sp->start_x);
 					if ((sh.y >> 16) == 0u) // !valid
 						continue;
-					const int lo = max(int(int16_t(sh.x & 0xffffu)) - x0, 0);
-					const int hi = min(int(int16_t(sh.x >> 16)) - x0, int(kTileW) - 1);
+					// sh.w = touch range: start_x / end_x, widened for primitives an upscaled pass does not upscale
+					const int lo = max(int(int16_t(sh.w & 0xffffu)) - x0, 0);
+					const int hi = min(int(int16_t(sh.w >> 16)) - x0, int(kTileW) - 1);
 					if (lo > hi)
 						continue;
 					pixmask |= (((2u << hi) - 1u) & ~((1u << lo) - 1u)) << (r * int(kTileW));
@@ -340,7 +346,15 @@ struct TileWalker
 					PrimSetup p;
 					load_prim_for_shading(b.prims + prim, span_base, ids, lines, dzw, p);
 					const PassState &st = b.states[ids & 0xffffu];
-					if (process_pixel_span<S>(ctx, view, px, x, y, prim, p, sp, st))
+					// A primitive the upscaled pass does not upscale shades every sub-pixel as its native pixel's first
+					// one (shading.h:45-52); the span fetched above already is that line's.
+					int sx = x, sy = y;
+					if (sl != 0 && (p.flags & SF_DISABLE_UPSCALING))
+					{
+						sx &= ~((1 << sl) - 1);
+						sy &= ~((1 << sl) - 1);
+					}
+					if (process_pixel_span<S>(ctx, view, px, sx, sy, prim, p, sp, st))
 						shaded++;
 				}
 			}

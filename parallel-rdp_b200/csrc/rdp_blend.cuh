@@ -722,6 +722,13 @@ RDP_HD bool process_pixel_primitive(const ShadeContext &ctx, const FbView &fb, P
 	const Span &sp = ctx.spans[(p.span_base << sl) + uint32_t(y - line_lo)];
 	if (!sp.valid)
 		return false;
+	// Not upscaled: every sub-pixel is shaded as its native pixel's first sub-pixel (shading.h:45-52).  The span stored
+	// for line y already is the snapped line's (compute_span).
+	if (sl != 0 && (p.flags & SF_DISABLE_UPSCALING))
+	{
+		x &= ~((1 << sl) - 1);
+		y &= ~((1 << sl) - 1);
+	}
 	return process_pixel_span<S>(ctx, fb, px, x, y, prim, p, sp, ctx.states[p.state_id]);
 }
 

@@ -3,10 +3,13 @@
 //
 //   tmem_update : 2048 threads, one per TMEM word, replay the pass's texture loads and snapshot TMEM after each
 //   prim_setup  : one thread per primitive, decode raw command words -> PrimSetup
-//   span_bin    : one warp per primitive; lanes own scanlines, edge-walk them into Span records and OR the
-//                 primitive's bit into the mask of every 8x8 tile its spans touch (exact, span-derived binning)
-//   tiles       : one thread per pixel; load colour/depth once, walk the tile's primitive mask in order,
-//                 shade + blend in registers, store once if dirty
+//   span_bin    : one warp per (primitive, 32-line chunk); lanes own scanlines, edge-walk them into Span records and OR
+//                 the primitive's bit into the mask of every 8x4 tile its spans touch (exact, span-derived binning)
+//   tiles       : one lane per pixel; load colour/depth once, walk the tile's primitive mask in order,
+//                 shade + blend in registers, store once if dirty.  pass_pixel_walk is the in-order statement,
+//                 pass_pixel_walk_deferred the four-phase one (the CUDA walkers in backend_cuda.cu do the same work
+//                 warp-cooperatively)
+// plus the PRE / POST synchronisation of the upscaled domain when internal upscaling is on.
 //
 // Reference dispatch sequence being replaced: parallel-rdp/rdp_renderer.cpp:2223-2285.
 #pragma once
@@ -78,8 +81,8 @@ RDP_HD void pass_span_line(const PassBuffers &b, const FbInfo &fb, const PrimSet
 	b.spans[(p.span_base << sl) + uint32_t(y - line_lo)] = sp;
 	if (y <= line_hi && sp.valid && y >= 0 && y < int(fb.height))
 	{
-		bin_lo = imax(int(sp.start_x), 0);
-		bin_hi = imin(int(sp.end_x), int(fb.width) - 1);
+		bin_lo = imax(int(int16_t(sp.touch_range & 0xffffu)), 0);
+		bin_hi = imin(int(int16_t(sp.touch_range >> 16)), int(fb.width) - 1);
 	}
 }
 

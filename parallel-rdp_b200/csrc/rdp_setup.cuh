@@ -265,6 +265,8 @@ RDP_HD void decode_primitive(const uint32_t *w, const PassState &st, const PrimR
 
 	if (rec.line_hi < rec.line_lo)
 		flags |= SF_NO_PIXELS;
+	if (op == OP_FILL_RECT || op == OP_TEX_RECT_FLIP || (op == OP_TEX_RECT && (st.quirks & QUIRK_NATIVE_RESOLUTION_TEX_RECT)))
+		flags |= SF_DISABLE_UPSCALING;
 
 	p.flags = uint8_t(flags);
 	p.span_base = rec.span_base;
@@ -327,6 +329,10 @@ RDP_HD uint32_t step_snapped(int d, int dist, int sl)
 RDP_HD void compute_span(const PrimSetup &p, const PassState &st, int y, Span &out, int sl = 0)
 {
 	const int S = 1 << sl;
+	// A primitive that is not upscaled shows every upscaled line the span of its native line's first sub-line.
+	const bool native_only = sl != 0 && (p.flags & SF_DISABLE_UPSCALING) != 0;
+	if (native_only)
+		y &= ~(S - 1);
 	const bool flip = (p.flags & SF_FLIP) != 0;
 	const bool do_offset = (p.flags & SF_DO_OFFSET) != 0;
 	const bool skip_xfrac = (p.flags & SF_SKIP_XFRAC) != 0;
@@ -437,5 +443,13 @@ RDP_HD void compute_span(const PrimSetup &p, const PassState &st, int y, Span &o
 			valid = false;
 	out.valid = valid ? 1 : 0;
 	out.lodlength = int16_t(flip ? (end_x - out.base_x) : (out.base_x - start_x));
+	int touch_lo = start_x, touch_hi = end_x;
+	if (native_only)
+	{
+		// upscaled pixels x with (x & ~(S - 1)) in [start_x, end_x]
+		touch_lo = (start_x + (S - 1)) & ~(S - 1);
+		touch_hi = (end_x & ~(S - 1)) + (S - 1);
+	}
+	out.touch_range = uint32_t(uint16_t(int16_t(touch_lo))) | (uint32_t(uint16_t(int16_t(touch_hi))) << 16);
 }
 }

@@ -1072,12 +1072,15 @@ RDP_HD void shade_color(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 		divide_st(perspective, rs >> 16, rt >> 16, rw >> 16, s, t, persp_overflow);
 		if (uses_lod)
 		{
-			const int xs = int(uint32_t(rs) + uint32_t(direction * ms));
-			const int xt = int(uint32_t(rt) + uint32_t(direction * mt));
-			const int xw = int(uint32_t(rw) + uint32_t(direction * mw));
-			const int ys = int(uint32_t(rs) + uint32_t((p.dstzw_dy[0] & ~0x7fff) >> sl));
-			const int yt = int(uint32_t(rt) + uint32_t((p.dstzw_dy[1] & ~0x7fff) >> sl));
-			const int yw = int(uint32_t(rw) + uint32_t((p.dstzw_dy[3] & ~0x7fff) >> sl));
+			// native_texture_lod quirk: LOD as the native resolution would compute it (shading.h:193-196)
+			const int lod_dir = (sl != 0 && (st.quirks & QUIRK_NATIVE_TEXTURE_LOD)) ? (direction << sl) : direction;
+			const int xs = int(uint32_t(rs) + uint32_t(lod_dir * ms));
+			const int xt = int(uint32_t(rt) + uint32_t(lod_dir * mt));
+			const int xw = int(uint32_t(rw) + uint32_t(lod_dir * mw));
+			const int dy_mul = lod_dir < 0 ? -lod_dir : lod_dir; // |direction|: 1, or S under the native-LOD quirk (interpolation.h:104-107)
+			const int ys = int(uint32_t(rs) + uint32_t(dy_mul) * uint32_t((p.dstzw_dy[0] & ~0x7fff) >> sl));
+			const int yt = int(uint32_t(rt) + uint32_t(dy_mul) * uint32_t((p.dstzw_dy[1] & ~0x7fff) >> sl));
+			const int yw = int(uint32_t(rw) + uint32_t(dy_mul) * uint32_t((p.dstzw_dy[3] & ~0x7fff) >> sl));
 			divide_st(perspective, xs >> 16, xt >> 16, xw >> 16, s_dx, t_dx, persp_overflow);
 			divide_st(perspective, ys >> 16, yt >> 16, yw >> 16, s_dy, t_dy, persp_overflow);
 		}

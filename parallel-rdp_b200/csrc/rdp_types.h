@@ -154,6 +154,17 @@ enum SetupFlags : uint32_t
 	SF_KEEP_ODD = 1u << 4,
 	SF_FILL_COPY_RASTER = 1u << 5,
 	SF_NO_PIXELS = 1u << 6, // never rasterises (Y clipped away); kept so the primitive counter advances
+	// Internal upscaling renders this primitive at native resolution, replicated over each pixel's S*S sub-pixels: fill
+	// rectangles and flipped texture rectangles always, texture rectangles under the native_resolution_tex_rect quirk
+	// (ref rdp_device.cpp:730, 763, 806; shaders/shading.h:45-52).
+	SF_DISABLE_UPSCALING = 1u << 7,
+};
+
+// Quirks a state snapshot carries (ref rdp_device.hpp:76-109).
+enum QuirkFlags : uint32_t
+{
+	QUIRK_NATIVE_RESOLUTION_TEX_RECT = 1u << 0,
+	QUIRK_NATIVE_TEXTURE_LOD = 1u << 1,
 };
 
 enum TileFlags : uint32_t
@@ -193,7 +204,7 @@ struct alignas(16) PassState
 	int32_t prim_depth; // (z & 0x7fff) << 16
 
 	uint16_t sc_xlo, sc_ylo, sc_xhi, sc_yhi; // scissor, 10.2
-	uint32_t pad1;
+	uint32_t quirks; // QuirkFlags
 	TileDesc tiles[8];
 };
 
@@ -238,7 +249,10 @@ struct alignas(16) Span
 	int16_t lodlength;
 	uint16_t valid;
 	int32_t base_x; // integer X the attributes were latched at
-	uint32_t pad;
+	// Pixel range [lo, hi] (int16 | int16 << 16) this line can touch: what binning and the tile kernels' mask phase use.
+	// Equal to start_x / end_x except for SF_DISABLE_UPSCALING primitives in an upscaled pass, where it is the range of
+	// upscaled pixels whose native pixel's first sub-pixel lies in [start_x, end_x].
+	uint32_t touch_range;
 };
 static_assert(offsetof(Span, start_x) == 48, "Span header word must sit at byte 48");
 

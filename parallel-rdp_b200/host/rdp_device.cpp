@@ -63,6 +63,7 @@ CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, 
 		                    (flags & COMMAND_PROCESSOR_FLAG_UPSCALING_2X_BIT) ? 1u : 0u;
 		if (renderer.set_upscaling(up))
 			vi.set_upscaling_log2(renderer.get_upscaling_log2());
+		apply_quirks(); // the defaults: texture rectangles at native resolution, LOD at the rendered resolution
 	}
 	vi.init(device, rdram_size);
 
@@ -287,6 +288,7 @@ void CommandProcessor::enqueue_command_direct(unsigned num_words, const uint32_t
 	}
 	case OP_META_SET_QUIRKS:
 		quirks.u.words[0] = words[1];
+		apply_quirks();
 		break;
 	case OP_META_SCANOUT:
 		execute_scanout_request(reinterpret_cast<ScanoutRequest *>(uintptr_t(uint64_t(words[1]) | (uint64_t(words[2]) << 32))));
@@ -388,6 +390,12 @@ void CommandProcessor::enqueue_command_stream_borrowed(size_t num_words, const u
 		execute_borrowed_stream(num_words, words);
 	else
 		ring.enqueue_stream_borrowed(num_words, words);
+}
+
+void CommandProcessor::apply_quirks()
+{
+	renderer.set_quirks((quirks.u.options.native_resolution_tex_rect ? QUIRK_NATIVE_RESOLUTION_TEX_RECT : 0u) |
+	                    (quirks.u.options.native_texture_lod ? QUIRK_NATIVE_TEXTURE_LOD : 0u));
 }
 
 void CommandProcessor::set_quirks(const Quirks &q)

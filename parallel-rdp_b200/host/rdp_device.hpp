@@ -168,6 +168,7 @@ private:
 	uint64_t timeline_value = 0;
 	std::atomic<uint64_t> signalled_timeline{0};
 	Quirks quirks;
+	void apply_quirks();
 
 	void enqueue_command_inner(unsigned num_words, const uint32_t *words);
 	void drain_command_ring();

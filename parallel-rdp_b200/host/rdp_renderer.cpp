@@ -15,6 +15,15 @@ using namespace rdpb;
 
 namespace RDP
 {
+void Renderer::set_quirks(uint32_t quirk_flags)
+{
+	if (regs.quirks != quirk_flags)
+	{
+		regs.quirks = quirk_flags;
+		state_dirty = true;
+	}
+}
+
 bool Renderer::set_upscaling(uint32_t log2)
 {
 	if (log2 == 0)

@@ -83,6 +83,8 @@ public:
 	bool init(rdpb_device *device, size_t rdram_size);
 	// Internal upscaling factor 1 << log2 (0: off).  Allocates the upscaled domain in the backend.
 	bool set_upscaling(uint32_t log2);
+	// QuirkFlags (csrc/rdp_types.h); part of every state snapshot taken from now on.
+	void set_quirks(uint32_t quirk_flags);
 	uint32_t get_upscaling_log2() const { return upscale_log2; }
 	uint64_t get_upscaled_pass_count() const { return upscaled_pass_counter; }
 	void set_validation_interface(ValidationInterface *iface) { validation = iface; }

@@ -108,12 +108,9 @@ def test_hostsim_fill_rect_is_replicated_and_cpu_writes_propagate():
         for s in range(scale * scale):
             u16 = up[s][lo:hi].view(np.uint16).reshape(68, 160, 2)[:, :, ::-1].reshape(68, 320)
             uh = hidden[s][lo // 2:hi // 2].reshape(68, 320)
-            # ... and both are in every slice: the stripe by the PRE broadcast, the fill by rendering.  The rectangle's
-            # last column / row belong to the scaled edge (xl * S, as in span_setup.comp:167-169): only the slices on
-            # the near side of it are covered there, so they are left out of the comparison.
+            # ... and both are in every slice: the stripe by the PRE broadcast, the fill by rendering -- fill rectangles
+            # are never upscaled (rdp_device.cpp:730), every sub-pixel repeats its native pixel, edges included.
             keep = np.ones((68, 320), bool)
-            keep[:, 215] = False
-            keep[67, :] = False
             assert np.array_equal(u16[keep], n16[keep])
             # hidden bits travel with a colour word that changed or was rendered; untouched words keep the domain's
             # initial value (3, rdp_renderer.cpp:593)
@@ -239,3 +236,46 @@ def test_hostsim_downscale_steps_are_ignored_without_upscaling():
 @pytest.mark.parametrize("scale", [2, 4])
 def test_gpu_upscaled_scanout_matches_scalar_statement(scale):
     assert _check_scanout("cuda", scale, 800) == _check_scanout("hostsim", scale, 800)
+
+
+# --- quirks (rdp_device.hpp:76-109): which primitives an upscaled pass really upscales ---------------------------------
+def _tex_rect_slices(native_tex_rect: bool):
+    """A scaled texture rectangle over a cleared 320x240 RGBA16 target at 2x: the four slices of the colour image."""
+    scale = 2
+    sbs = SideBySide("hostsim", rdram_size=wl.RDRAM_SIZE, hidden_size=wl.HIDDEN_SIZE, flags=FLAGS[scale])
+    try:
+        sbs.clear_rdram()
+        sbs.gpu.set_quirks(native_tex_rect, False)
+        sbs.write_tmem(np.random.RandomState(5).randint(0, 256, 4096, dtype=np.uint8))
+        b = Builder()
+        b.set_color_image(0, 2, COLOR, 320)
+        b.set_scissor(0, 0, 320, 240)
+        b.om.cycle_type = rb.CYCLE_1
+        b.om.sample_quad = True
+        b.touch_other_modes()
+        b.flush_other_modes()
+        CC = rb.CC
+        b.set_combine(((CC.A_ZERO, CC.B_ZERO, CC.C_ZERO, CC.D_TEXEL0), (CC.AA_ZERO, CC.AA_ZERO, CC.AC_ZERO, CC.AA_TEXEL0)))
+        b.set_tile(0, rb.FMT_RGBA, rb.SIZE_16, 64, 0, mask_s=5, mask_t=5)
+        b.set_tile_size(0, 0, 0, 32, 32)
+        b.tex_rect(0, 20, 12, 150, 90, 0, 0, 150, 170)  # s/t steps that are not whole texels: the filter has work to do
+        b.sync_full()
+        sbs.run(b.take())
+        sbs.gpu.idle()
+        assert not sbs.compare_rdram()
+        assert sbs.gpu.upscaled_pass_count() == 1
+        up, _ = sbs.gpu.read_upscaled_rdram()
+        lo, hi = COLOR, COLOR + 320 * 110 * 2
+        return [up[s][lo:hi].view(np.uint16).reshape(110, 320).copy() for s in range(scale * scale)]
+    finally:
+        sbs.close()
+
+
+@pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
+def test_hostsim_native_resolution_tex_rect_quirk():
+    on = _tex_rect_slices(True)    # the default: texture rectangles are not upscaled -> every sub-pixel repeats its pixel
+    assert on[0].any()
+    assert all(np.array_equal(on[0], s) for s in on[1:])
+    off = _tex_rect_slices(False)  # upscaled like a triangle: the sub-pixels sample the texture at their own positions
+    assert off[0].any()
+    assert not all(np.array_equal(off[0], s) for s in off[1:])
