@@ -38,6 +38,15 @@
 
 using namespace rdpb;
 
+// Every processor owns three CUDA streams (compute, upload, read-back).  With the driver's default of 8 hardware work
+// queues, eight processors on one GPU make unrelated streams share a queue and wait on each other; ask for more
+// before the context exists.  (Read at context creation: a host that initialises CUDA before loading this library
+// has to export CUDA_DEVICE_MAX_CONNECTIONS itself -- see INTEGRATION.md.)
+__attribute__((constructor)) static void rdpb_request_work_queues()
+{
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+}
+
 namespace
 {
 constexpr unsigned kStagingSlots = 4;
@@ -1212,7 +1221,12 @@ struct rdpb_device
 	uint32_t *vi_filtered = nullptr;
 	uint32_t *vi_out[2] = {};
 	unsigned vi_out_index = 0;
-	ViLine *d_vi_lines = nullptr;
+	// Per-line scan-out parameters on the device: a few sets, each remembered on the host, so a scan-out whose lines
+	// equal a resident set (the two fields of an interlaced mode alternate) uploads nothing.
+	static constexpr unsigned kViLineSets = 4;
+	ViLine *d_vi_lines = nullptr; // kViLineSets * kViMaxLines
+	std::vector<ViLine> vi_line_shadow[kViLineSets];
+	unsigned vi_line_next = 0;
 	uint8_t *vi_host_staging = nullptr;
 	cudaEvent_t vi_lines_done[2] = {};
 	bool vi_lines_in_flight[2] = {};
@@ -1278,6 +1292,10 @@ struct rdpb_device
 	}
 };
 
+// Entry points run on the caller's thread or the command thread; each selects the device once instead of paying a
+// driver call per entry (eight streams' threads share the driver's locks).
+static void use_device(const rdpb_device *dev);
+
 static bool check(rdpb_device *dev, cudaError_t err, const char *what)
 {
 	if (err == cudaSuccess)
@@ -1291,6 +1309,16 @@ static bool check(rdpb_device *dev, cudaError_t err, const char *what)
 }
 
 #define CK(call) do { if (!check(dev, (call), #call)) return -1; } while (0)
+
+static void use_device(const rdpb_device *dev)
+{
+	static thread_local int current = -1;
+	if (current != dev->ordinal)
+	{
+		cudaSetDevice(dev->ordinal);
+		current = dev->ordinal;
+	}
+}
 
 // ---- profiling helpers ---------------------------------------------------------------------------------------
 static int prof_begin(rdpb_device *dev, int kind)
@@ -1456,8 +1484,10 @@ static int submit(rdpb_device *dev, GpuOp &op)
 {
 	if (dev->pass_upload_pending)
 	{
-		// First kernel of the pass: everything uploaded so far for it (stream_up) must have landed.
-		if (!check(dev, cudaStreamWaitEvent(dev->stream, dev->staging_done[dev->staging_index], 0), "cudaStreamWaitEvent"))
+		// First kernel of the pass: everything uploaded so far for it (stream_up) must have landed.  The same event
+		// gates the reuse of the pass's host staging slot.
+		if (!check(dev, cudaEventRecord(dev->staging_done[dev->staging_index], dev->stream_up), "cudaEventRecord") ||
+		    !check(dev, cudaStreamWaitEvent(dev->stream, dev->staging_done[dev->staging_index], 0), "cudaStreamWaitEvent"))
 			return -1;
 		dev->pass_upload_pending = false;
 	}
@@ -1559,7 +1589,7 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	const size_t max_out = size_t(640) * 576 * 4;
 	need(cudaMalloc(&dev->vi_out[0], max_out), "cudaMalloc vi out");
 	need(cudaMalloc(&dev->vi_out[1], max_out), "cudaMalloc vi out");
-	need(cudaMalloc(&dev->d_vi_lines, sizeof(ViLine) * kViMaxLines), "cudaMalloc vi lines");
+	need(cudaMalloc(&dev->d_vi_lines, sizeof(ViLine) * kViMaxLines * rdpb_device::kViLineSets), "cudaMalloc vi lines");
 	need(cudaHostAlloc(&dev->vi_host_staging, sizeof(ViLine) * kViMaxLines * 2, cudaHostAllocDefault), "cudaHostAlloc vi staging");
 	for (auto &e : dev->vi_lines_done)
 		need(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
@@ -1610,7 +1640,7 @@ void rdpb_device_destroy(rdpb_device *dev)
 {
 	if (!dev)
 		return;
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	cudaDeviceSynchronize();
 	cudaFree(dev->rdram);
 	cudaFree(dev->hidden);
@@ -1682,7 +1712,7 @@ const char *rdpb_last_error(rdpb_device *dev) { return dev->error.c_str(); }
 
 int rdpb_register_host_memory(rdpb_device *dev, void *ptr, size_t size)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	cudaError_t e = cudaHostRegister(ptr, size, cudaHostRegisterDefault);
 	if (e != cudaSuccess)
 	{
@@ -1694,7 +1724,7 @@ int rdpb_register_host_memory(rdpb_device *dev, void *ptr, size_t size)
 
 int rdpb_unregister_host_memory(rdpb_device *dev, void *ptr)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	cudaHostUnregister(ptr);
 	cudaGetLastError();
 	return 0;
@@ -1702,7 +1732,7 @@ int rdpb_unregister_host_memory(rdpb_device *dev, void *ptr)
 
 static int copy_common(rdpb_device *dev, void *dst, const void *src, size_t size, cudaMemcpyKind kind, int sync)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	CK(cudaMemcpyAsync(dst, src, size, kind, dev->stream));
 	if (sync)
 		CK(cudaStreamSynchronize(dev->stream));
@@ -1727,7 +1757,7 @@ int rdpb_hidden_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size
 }
 int rdpb_hidden_fill(rdpb_device *dev, uint8_t value)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	CK(cudaMemsetAsync(dev->hidden, value, dev->hidden_size, dev->stream));
 	return 0;
 }
@@ -1737,7 +1767,7 @@ void *rdpb_hidden_device_ptr(rdpb_device *dev) { return dev->hidden; }
 
 int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	dev->staging_index = (dev->staging_index + 1) % kStagingSlots;
 	const unsigned i = dev->staging_index;
 	if (dev->staging_in_flight[i])
@@ -1755,7 +1785,7 @@ int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
 
 int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	const unsigned i = dev->staging_index;
 	const uint8_t *base = dev->staging[i];
 
@@ -1798,7 +1828,7 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 
 	if (block_bytes)
 		CK(cudaMemcpyAsync(block, block_host, block_bytes, cudaMemcpyHostToDevice, dev->stream_up));
-	CK(cudaEventRecord(dev->staging_done[i], dev->stream_up));
+	// staging_done[i] is recorded once, behind the last copy of the pass (first kernel submission, or pass end).
 	dev->staging_in_flight[i] = true;
 	dev->pass_upload_pending = true;
 
@@ -1811,7 +1841,7 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 
 int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_words, uint32_t dst_word_offset)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	if (!num_words)
 		return 0;
 	if (size_t(dst_word_offset) + num_words > kMaxPassWords)
@@ -1820,15 +1850,13 @@ int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_w
 		return -1;
 	}
 	CK(cudaMemcpyAsync(const_cast<uint32_t *>(dev->cur_words) + dst_word_offset, src, size_t(num_words) * 4, cudaMemcpyHostToDevice, dev->stream_up));
-	// Staged runs live in the current staging slot: its reuse must wait for this copy too.
-	CK(cudaEventRecord(dev->staging_done[dev->staging_index], dev->stream_up));
 	dev->pass_upload_pending = true;
 	return 0;
 }
 
 int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	if (!update_tmem && !num_prims)
 		return 0;
 	GpuOp op = {};
@@ -1841,7 +1869,7 @@ int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, u
 
 int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	GpuOp op = {};
 	op.kind = GOP_SPAN;
 	op.fb = *static_cast<const FbInfo *>(fb_info);
@@ -1854,7 +1882,7 @@ const char *rdpb_last_tile_variant(rdpb_device *dev) { return dev->last_variant 
 
 int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	GpuOp op = {};
 	op.kind = GOP_TILES;
 	op.fb = *static_cast<const FbInfo *>(fb_info);
@@ -1873,8 +1901,14 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 
 int rdpb_pass_end(rdpb_device *dev)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	const unsigned i = dev->staging_index;
+	if (dev->pass_upload_pending)
+	{
+		// Nothing was launched for this pass: its copies still need their completion event for the slot's reuse.
+		CK(cudaEventRecord(dev->staging_done[i], dev->stream_up));
+		dev->pass_upload_pending = false;
+	}
 	CK(cudaEventRecord(dev->kernels_done[i], dev->stream));
 	dev->kernels_in_flight[i] = true;
 	return 0;
@@ -1882,7 +1916,7 @@ int rdpb_pass_end(rdpb_device *dev)
 
 int rdpb_upscaling_init(rdpb_device *dev, uint32_t scale_log2)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	if (scale_log2 < 1 || scale_log2 > 3 || dev->scale_log2)
 		return -1;
 	const size_t slices = size_t(1) << (2 * scale_log2);
@@ -1921,7 +1955,7 @@ int rdpb_upscaling_init(rdpb_device *dev, uint32_t scale_log2)
 
 int rdpb_launch_upscale_sync(rdpb_device *dev, const void *fb_info, int stage)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	if (!dev->scale_log2)
 		return 0;
 	GpuOp op = {};
@@ -1933,7 +1967,7 @@ int rdpb_launch_upscale_sync(rdpb_device *dev, const void *fb_info, int stage)
 
 int rdpb_upscaled_read(rdpb_device *dev, void *rdram_dst, void *hidden_dst)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	if (!dev->scale_log2)
 		return -1;
 	const size_t slices = size_t(1) << (2 * dev->scale_log2);
@@ -1947,7 +1981,7 @@ int rdpb_upscaled_read(rdpb_device *dev, void *rdram_dst, void *hidden_dst)
 
 int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *lines)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	GpuOp op = {};
 	op.kind = GOP_VI;
 	op.vi = *static_cast<const ViFrame *>(frame);
@@ -1963,18 +1997,41 @@ int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *line
 		}
 	}
 
-	// Per-line parameters go through a small pinned staging block (re-used once the previous copy has landed).
-	const unsigned slot = dev->vi_out_index & 1u;
-	if (dev->vi_lines_in_flight[slot])
+	bool resident = false;
+	if (!dev->recording)
 	{
-		CK(cudaEventSynchronize(dev->vi_lines_done[slot]));
-		dev->vi_lines_in_flight[slot] = false;
+		for (unsigned k = 0; k < rdpb_device::kViLineSets && !resident; k++)
+		{
+			if (dev->vi_line_shadow[k].size() == kViMaxLines && memcmp(dev->vi_line_shadow[k].data(), lines, sizeof(ViLine) * kViMaxLines) == 0)
+			{
+				d_lines = dev->d_vi_lines + size_t(k) * kViMaxLines;
+				resident = true;
+			}
+		}
+		if (!resident)
+		{
+			const unsigned k = dev->vi_line_next;
+			dev->vi_line_next = (k + 1) % rdpb_device::kViLineSets;
+			dev->vi_line_shadow[k].assign(static_cast<const ViLine *>(lines), static_cast<const ViLine *>(lines) + kViMaxLines);
+			d_lines = dev->d_vi_lines + size_t(k) * kViMaxLines;
+		}
 	}
-	ViLine *h_lines = reinterpret_cast<ViLine *>(dev->vi_host_staging) + size_t(slot) * kViMaxLines;
-	memcpy(h_lines, lines, sizeof(ViLine) * kViMaxLines);
-	CK(cudaMemcpyAsync(d_lines, h_lines, sizeof(ViLine) * kViMaxLines, cudaMemcpyHostToDevice, dev->stream));
-	CK(cudaEventRecord(dev->vi_lines_done[slot], dev->stream));
-	dev->vi_lines_in_flight[slot] = true;
+	if (!resident)
+	{
+		// Per-line parameters go through a small pinned staging block (re-used once the previous copy has landed).  The
+		// copy is ordered on the compute stream behind every scan-out that still reads the set being replaced.
+		const unsigned slot = dev->vi_out_index & 1u;
+		if (dev->vi_lines_in_flight[slot])
+		{
+			CK(cudaEventSynchronize(dev->vi_lines_done[slot]));
+			dev->vi_lines_in_flight[slot] = false;
+		}
+		ViLine *h_lines = reinterpret_cast<ViLine *>(dev->vi_host_staging) + size_t(slot) * kViMaxLines;
+		memcpy(h_lines, lines, sizeof(ViLine) * kViMaxLines);
+		CK(cudaMemcpyAsync(d_lines, h_lines, sizeof(ViLine) * kViMaxLines, cudaMemcpyHostToDevice, dev->stream));
+		CK(cudaEventRecord(dev->vi_lines_done[slot], dev->stream));
+		dev->vi_lines_in_flight[slot] = true;
+	}
 
 	op.lines = d_lines;
 	if (dev->recording)
@@ -1997,7 +2054,7 @@ static int signal_on(rdpb_device *dev, uint64_t value, cudaStream_t stream);
 // waiting for `fence_value` means the pixels are in `dst`.  The compute stream is never blocked by the copy.
 int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, uint64_t fence_value)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	const unsigned idx = dev->vi_out_index;
 	CK(cudaEventRecord(dev->vi_done, dev->stream));
 	CK(cudaStreamWaitEvent(dev->stream_down, dev->vi_done, 0));
@@ -2015,7 +2072,7 @@ int rdpb_signal(rdpb_device *dev, uint64_t value)
 
 static int signal_on(rdpb_device *dev, uint64_t value, cudaStream_t stream)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	std::lock_guard<std::mutex> holder{dev->timeline_lock};
 	cudaEvent_t ev;
 	if (!dev->free_events.empty())
@@ -2032,7 +2089,7 @@ static int signal_on(rdpb_device *dev, uint64_t value, cudaStream_t stream)
 
 int rdpb_wait(rdpb_device *dev, uint64_t value)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	cudaEvent_t ev = nullptr;
 	{
 		// Points are recorded in stream order, so everything queued before `value` completes no later than it.
@@ -2057,7 +2114,7 @@ int rdpb_wait(rdpb_device *dev, uint64_t value)
 
 int rdpb_sync(rdpb_device *dev)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	CK(cudaStreamSynchronize(dev->stream_up));
 	CK(cudaStreamSynchronize(dev->stream));
 	CK(cudaStreamSynchronize(dev->stream_down));
@@ -2070,7 +2127,7 @@ uint64_t rdpb_launch_count(rdpb_device *dev) { return dev->launches; }
 // ---- measurement plumbing ------------------------------------------------------------------------------------
 int rdpb_profile_enable(rdpb_device *dev, int on, uint32_t max_launches)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	CK(cudaStreamSynchronize(dev->stream));
 	while (on && dev->prof_pool.size() < max_launches)
 	{
@@ -2086,7 +2143,7 @@ int rdpb_profile_enable(rdpb_device *dev, int on, uint32_t max_launches)
 
 int rdpb_profile_read(rdpb_device *dev, int kind, uint32_t *launches, double *total_ms)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	CK(cudaStreamSynchronize(dev->stream));
 	uint32_t n = 0;
 	double total = 0.0;
@@ -2106,7 +2163,7 @@ int rdpb_profile_read(rdpb_device *dev, int kind, uint32_t *launches, double *to
 
 int rdpb_counters_read(rdpb_device *dev, uint64_t *out8, int reset)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	uint64_t all[kCounterWords];
 	CK(cudaMemcpyAsync(all, dev->d_counters, sizeof(all), cudaMemcpyDeviceToHost, dev->stream));
 	CK(cudaStreamSynchronize(dev->stream));
@@ -2124,7 +2181,7 @@ int rdpb_counters_read(rdpb_device *dev, uint64_t *out8, int reset)
 
 int rdpb_record_begin(rdpb_device *dev, size_t arena_bytes)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	CK(cudaStreamSynchronize(dev->stream));
 	if (dev->arena_size < arena_bytes)
 	{
@@ -2152,7 +2209,7 @@ int rdpb_record_mark(rdpb_device *dev)
 
 int rdpb_record_end(rdpb_device *dev)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	dev->recording = false;
 	if (dev->marks.empty() || dev->marks.back() != dev->log.size())
 		dev->marks.push_back(uint32_t(dev->log.size()));
@@ -2167,7 +2224,7 @@ uint32_t rdpb_record_steps(rdpb_device *dev)
 
 int rdpb_replay_step(rdpb_device *dev, uint32_t step)
 {
-	cudaSetDevice(dev->ordinal);
+	use_device(dev);
 	if (dev->recording || step + 1 >= dev->marks.size())
 		return -1;
 	for (uint32_t i = dev->marks[step]; i < dev->marks[step + 1]; i++)
