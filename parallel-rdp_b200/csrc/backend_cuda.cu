@@ -1008,12 +1008,20 @@ __global__ void __launch_bounds__(256) k_vi_filter(ViFrame f, ViBuffers b)
 {
 	__shared__ uint32_t s_vram[10][40];
 	__shared__ uint32_t s_fetch[8][34];
+	// Pixels with partial coverage take the AA half of the fetch filter.  They are few (polygon edges) but scattered:
+	// left in place, nearly every warp would walk that code for a handful of lanes.  They are queued here and the
+	// block's threads take them from the queue, densely.
+	__shared__ uint16_t s_partial[8 * 34];
+	__shared__ uint32_t s_partial_count;
 	const int tx = int(threadIdx.x), ty = int(threadIdx.y);
 	const int bx = int(blockIdx.x) * 32, by = int(blockIdx.y) * 8;
 	const int x = bx + tx, y = by + ty;
 	const bool bug = blockIdx.z != 0;
 	const int tid = ty * 32 + tx;
+	const bool divot = (f.status & VI_STATUS_DIVOT) != 0;
 
+	if (tid == 0)
+		s_partial_count = 0;
 	for (int i = tid; i < 380; i += 256)
 	{
 		const int ry = i / 38, rx = i - ry * 38;
@@ -1022,17 +1030,32 @@ __global__ void __launch_bounds__(256) k_vi_filter(ViFrame f, ViBuffers b)
 	__syncthreads();
 	const ViSharedReader read = { s_vram, bx - 3, by - 1 };
 
-	ViColor c = vi_fetch_core(f, read, x, y, bug);
-	if (f.status & VI_STATUS_DIVOT)
+	// Fetch items: the block's own pixels (column 1..32 of s_fetch) and, for the divot, one halo column on each side.
+	// Full-coverage items are finished on the spot, the others queued.
+	for (int item = tid; item < (divot ? 256 + 16 : 256); item += 256)
 	{
-		// Fetch results fit 8 bits per channel (the dither filter cannot leave [0, 255]), so packing is lossless.
-		s_fetch[ty][tx + 1] = vi_pack(c);
-		if (tid < 16)
-		{
-			const int row = tid >> 1, right = tid & 1;
-			s_fetch[row][right ? 33 : 0] = vi_pack(vi_fetch_core(f, read, right ? bx + 32 : bx - 1, by + row, bug));
-		}
-		__syncthreads();
+		const int row = item < 256 ? (item >> 5) : ((item - 256) >> 1);
+		const int col = item < 256 ? (item & 31) + 1 : (((item - 256) & 1) ? 33 : 0);
+		const int fx = bx + col - 1, fy = by + row;
+		const ViColor mid = read(fx, fy);
+		if (mid.a != 7)
+			s_partial[atomicAdd(&s_partial_count, 1u)] = uint16_t(row * 34 + col);
+		else
+			s_fetch[row][col] = vi_pack(vi_fetch_full(f, read, fx, fy, bug, mid));
+	}
+	__syncthreads();
+	for (uint32_t i = uint32_t(tid); i < s_partial_count; i += 256u)
+	{
+		const int row = int(s_partial[i]) / 34, col = int(s_partial[i]) - row * 34;
+		const int fx = bx + col - 1, fy = by + row;
+		s_fetch[row][col] = vi_pack(vi_fetch_partial(f, read, fx, fy, bug, read(fx, fy)));
+	}
+	__syncthreads();
+
+	// Fetch results fit 8 bits per channel (the dither filter cannot leave [0, 255]), so packing is lossless.
+	ViColor c = vi_unpack(s_fetch[ty][tx + 1]);
+	if (divot)
+	{
 		const ViColor l = vi_unpack(s_fetch[ty][tx]);
 		const ViColor r = vi_unpack(s_fetch[ty][tx + 2]);
 		if ((l.a & c.a & r.a) != 7)

@@ -154,55 +154,60 @@ RDP_HD int vi_clamp1(int v) { return iclamp(v, -1, 1); }
 
 // vi_fetch.frag: AA filter (partial coverage) or dither reconstruction (full coverage) at framebuffer pixel (x, y).
 // `bug` selects the variant the oracle produces when it re-reads a line ("fetch bug").
-// `read(x, y)` yields the decoded framebuffer pixel: straight from RDRAM (vi_fetch_pixel below), or from a block's
-// shared-memory copy of its neighbourhood in the CUDA filter kernel, where every pixel is then decoded once
-// instead of once per consumer.
+//
+// The two halves of vi_fetch.frag, split so that the CUDA filter kernel can run the (rare, expensive) partial-coverage
+// half over a compacted list of pixels instead of making every warp that contains one such pixel walk through it.
+//
+// Partial coverage (mid.a != 7): the AA filter.
 template <class Reader>
-RDP_HD ViColor vi_fetch_core(const ViFrame &f, const Reader &read, int x, int y, bool bug)
+RDP_HD ViColor vi_fetch_partial(const ViFrame &f, const Reader &read, int x, int y, bool bug, const ViColor &mid)
 {
-	const ViColor mid = read(x, y);
 	ViColor out = mid;
-
-	if (mid.a != 7)
+	int lo[3] = { mid.r, mid.g, mid.b }, hi[3] = { mid.r, mid.g, mid.b };
+	int lo2[3] = { mid.r, mid.g, mid.b }, hi2[3] = { mid.r, mid.g, mid.b };
+	const ViColor to_left = read(x - 2, y);
+	const ViColor to_right = read(x + 2, y);
+	vi_track_neighbor(read(x - 1, y - 1), lo, hi, lo2, hi2);
+	vi_track_neighbor(read(x + 1, y - 1), lo, hi, lo2, hi2);
+	vi_track_neighbor(to_left, lo, hi, lo2, hi2);
+	vi_track_neighbor(to_right, lo, hi, lo2, hi2);
+	if (!bug)
 	{
-		int lo[3] = { mid.r, mid.g, mid.b }, hi[3] = { mid.r, mid.g, mid.b };
-		int lo2[3] = { mid.r, mid.g, mid.b }, hi2[3] = { mid.r, mid.g, mid.b };
-		const ViColor to_left = read(x - 2, y);
-		const ViColor to_right = read(x + 2, y);
-		vi_track_neighbor(read(x - 1, y - 1), lo, hi, lo2, hi2);
-		vi_track_neighbor(read(x + 1, y - 1), lo, hi, lo2, hi2);
+		vi_track_neighbor(read(x - 1, y + 1), lo, hi, lo2, hi2);
+		vi_track_neighbor(read(x + 1, y + 1), lo, hi, lo2, hi2);
+	}
+	else
+	{
+		// The lower row is not read; left/right are seen twice instead.
 		vi_track_neighbor(to_left, lo, hi, lo2, hi2);
 		vi_track_neighbor(to_right, lo, hi, lo2, hi2);
-		if (!bug)
-		{
-			vi_track_neighbor(read(x - 1, y + 1), lo, hi, lo2, hi2);
-			vi_track_neighbor(read(x + 1, y + 1), lo, hi, lo2, hi2);
-		}
-		else
-		{
-			// The lower row is not read; left/right are seen twice instead.
-			vi_track_neighbor(to_left, lo, hi, lo2, hi2);
-			vi_track_neighbor(to_right, lo, hi, lo2, hi2);
-		}
-		const int m[3] = { mid.r, mid.g, mid.b };
-		int res[3];
-		for (int i = 0; i < 3; i++)
-		{
-			if (f.fetch_bug)
-			{
-				// Only compiled in when the bug layer exists (FETCH_BUG define of the reference shader).
-				if (m[i] == lo[i]) lo2[i] = lo[i];
-				if (m[i] == hi[i]) hi2[i] = hi[i];
-			}
-			const uint32_t offset = uint32_t(lo2[i] + hi2[i] - (m[i] << 1));
-			const uint32_t coeff = uint32_t(7 - mid.a);
-			res[i] = int((uint32_t(m[i]) + ((offset * coeff + 4u) >> 3)) & 0xffu);
-		}
-		out.r = res[0];
-		out.g = res[1];
-		out.b = res[2];
 	}
-	else if (f.status & VI_STATUS_DITHER_FILTER)
+	const int m[3] = { mid.r, mid.g, mid.b };
+	int res[3];
+	for (int i = 0; i < 3; i++)
+	{
+		if (f.fetch_bug)
+		{
+			// Only compiled in when the bug layer exists (FETCH_BUG define of the reference shader).
+			if (m[i] == lo[i]) lo2[i] = lo[i];
+			if (m[i] == hi[i]) hi2[i] = hi[i];
+		}
+		const uint32_t offset = uint32_t(lo2[i] + hi2[i] - (m[i] << 1));
+		const uint32_t coeff = uint32_t(7 - mid.a);
+		res[i] = int((uint32_t(m[i]) + ((offset * coeff + 4u) >> 3)) & 0xffu);
+	}
+	out.r = res[0];
+	out.g = res[1];
+	out.b = res[2];
+	return out;
+}
+
+// Full coverage: dither reconstruction (when enabled), else the pixel as it is.
+template <class Reader>
+RDP_HD ViColor vi_fetch_full(const ViFrame &f, const Reader &read, int x, int y, bool bug, const ViColor &mid)
+{
+	ViColor out = mid;
+	if (f.status & VI_STATUS_DITHER_FILTER)
 	{
 		const int base[3] = { mid.r >> 3, mid.g >> 3, mid.b >> 3 };
 		int acc[3] = { 0, 0, 0 };
@@ -242,9 +247,19 @@ RDP_HD ViColor vi_fetch_core(const ViFrame &f, const Reader &read, int x, int y,
 		out.r = mid.r + acc[0];
 		out.g = mid.g + acc[1];
 		out.b = mid.b + acc[2];
+	
 	}
-	out.a = mid.a;
 	return out;
+}
+
+// `read(x, y)` yields the decoded framebuffer pixel: straight from RDRAM (vi_fetch_pixel below), or from a block's
+// shared-memory copy of its neighbourhood in the CUDA filter kernel, where every pixel is then decoded once
+// instead of once per consumer.
+template <class Reader>
+RDP_HD ViColor vi_fetch_core(const ViFrame &f, const Reader &read, int x, int y, bool bug)
+{
+	const ViColor mid = read(x, y);
+	return mid.a != 7 ? vi_fetch_partial(f, read, x, y, bug, mid) : vi_fetch_full(f, read, x, y, bug, mid);
 }
 
 struct ViVramReader
