@@ -8,7 +8,7 @@ timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; echo "reference rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 20 --warmup 3 --small --no-parity --no-cpu-baseline --streams 1 > gpurun_out/${tag}_ncu2.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on --launch-skip 14 -c 7 -f -o gpurun_out/${tag}_all \
+timeout 600 ncu --set full --clock-control none --import-source on --launch-skip 16 -c 8 -f -o gpurun_out/${tag}_all \
   python bench.py --steps 2 --warmup 1 --small --no-parity --no-cpu-baseline --streams 1 > gpurun_out/${tag}_ncu.log 2>&1
 echo "ncu rc=$?"
 python - <<PY
