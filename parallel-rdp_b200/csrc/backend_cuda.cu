@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(kFrontThreads) k_front(PassBuffers b, uint32_t
 
 // One warp per span job (primitive, 32-line chunk); lane = scanline.  Each 4-lane group is one tile row: the
 // group shuffle-reduces the row's X range, then its lanes split the row's tiles and OR the primitive's bit in.
+template <bool UPSCALED>
 __global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
 {
 	const uint32_t job_index = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
 	// With internal upscaling (fb.scale_log2) the job's 32 native lines are 32 * S lines of the upscaled image,
 	// walked in S rounds of 32; the upscaled tile kernel's tile counter is reset here, in stream order after the
 	// native tile kernel that left it exhausted.
-	const int sl = int(fb.scale_log2);
-	if (sl && blockIdx.x == 0 && threadIdx.x == 0)
+	const int sl = UPSCALED ? int(fb.scale_log2) : 0; // a literal 0 in the native instantiation: no loop, no shifts
+	if (UPSCALED && blockIdx.x == 0 && threadIdx.x == 0)
 		b.job_counter[1] = 0;
 	const int first = int(p.line_lo) & ~int(kTileH - 1);
 	const int sub = lane & int(kTileH - 1);
@@ -1383,7 +1384,10 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	{
 		const uint32_t warps_per_block = 4;
 		const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN);
-		k_span_bin<<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
+		if (op.fb.scale_log2)
+			k_span_bin<true><<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
+		else
+			k_span_bin<false><<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
 		prof_end(dev, s);
 		dev->launches++;
 		break;

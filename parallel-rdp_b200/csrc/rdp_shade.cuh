@@ -108,7 +108,7 @@ RDP_HD int clamp_depth(int z)
 // ---------------------------------------------------------------------------------------------
 // Coverage: coverage.h:31-44.  Bit layout: two samples per sub-scanline, offsets {0,4},{2,6},{0,4},{2,6}.
 // ---------------------------------------------------------------------------------------------
-RDP_HD int compute_coverage(const Span &s, int x)
+RDP_HD int compute_coverage_scalar(const Span &s, int x)
 {
 	const int base = (x << 3) & 0xffff;
 	int cov = 0;
@@ -123,6 +123,32 @@ RDP_HD int compute_coverage(const Span &s, int x)
 			cov |= 2 << (2 * line);
 	}
 	return cov;
+}
+
+// The same eight comparisons two sub-scanlines at a time, in the 16-bit halves of a word.  Sample positions stay
+// below 0x7fff for x < 4095, and the edges are either valid x.3 values below 0x8000 or the invalid-line sentinels
+// (left 0xffff, right 0), which masking bit 15 off turns into "never reached" / "never below" -- so
+// (P | 0x8000) - E cannot borrow across the halves and its bit 15 says P >= E.  With 8x internal upscaling edges
+// reach beyond 0x7fff (scissor 4095 * 2 * 8): `wide` keeps those passes on the scalar form.
+RDP_HD int compute_coverage(const Span &s, int x, bool wide = false)
+{
+	if (wide || uint32_t(x) >= 4095u)
+		return compute_coverage_scalar(s, x); // (also the wrapped positions of a negative x)
+	const uint32_t H = 0x80008000u;
+	const uint32_t base = uint32_t(x) << 3;
+	const uint32_t p0 = (base | ((base + 2u) << 16)) | H; // samples {0, 2} of an even / odd sub-scanline pair
+	const uint32_t p1 = ((base + 4u) | ((base + 6u) << 16)) | H; // samples {4, 6}
+	uint32_t cov = 0;
+	for (int pair = 0; pair < 2; pair++)
+	{
+		const uint32_t l = (uint32_t(s.xl[2 * pair]) | (uint32_t(s.xl[2 * pair + 1]) << 16)) & ~H;
+		const uint32_t r = (uint32_t(s.xr[2 * pair]) | (uint32_t(s.xr[2 * pair + 1]) << 16)) & ~H;
+		const uint32_t c0 = (p0 - l) & ~(p0 - r) & H; // bit 15: first line of the pair, bit 31: second
+		const uint32_t c1 = (p1 - l) & ~(p1 - r) & H;
+		const uint32_t m = (c0 >> 15) | (c1 >> 14);   // bits 0, 1: first line; bits 16, 17: second
+		cov |= ((m | (m >> 14)) & 0xfu) << (4 * pair);
+	}
+	return int(cov);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1158,9 +1184,9 @@ RDP_HD void shade_color(const ShadeContext &ctx, int x, int y, uint32_t prim_ind
 
 // Coverage half: the 8-bit sub-sample mask of pixel x on this span, 0 when the primitive does not shade it
 // (no sample covered, or -- without AA -- the first sample not covered).
-RDP_HD int shade_coverage(const Span &sp, int x, uint32_t rf)
+RDP_HD int shade_coverage(const Span &sp, int x, uint32_t rf, int scale_log2 = 0)
 {
-	const int coverage = compute_coverage(sp, x);
+	const int coverage = compute_coverage(sp, x, scale_log2 > 2);
 	if (!(rf & RF_AA) && (coverage & 1) == 0)
 		return 0;
 	return coverage;
@@ -1211,7 +1237,7 @@ RDP_HD int shade_pixel(const ShadeContext &ctx, int x, int y, uint32_t prim_inde
 		return 1;
 	}
 
-	const int coverage = shade_coverage(sp, x, rf);
+	const int coverage = shade_coverage(sp, x, rf, ctx.scale_log2);
 	if (coverage == 0)
 		return 0;
 	int coverage_count = pop_count(uint32_t(coverage));
