@@ -906,36 +906,32 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 // the span kernel filled as usual.
 constexpr uint32_t kFillPassMaxPrims = 8;
 
+constexpr int kFillPixelsPerThread = 4;
+
 __global__ void __launch_bounds__(256) k_fill_pass(PassBuffers b, FbInfo fb)
 {
 	__shared__ uint32_t s_count[2];
 	if (threadIdx.x < 2)
 		s_count[threadIdx.x] = 0;
 	__syncthreads();
-	// A 256-thread block covers 64 x 8 pixels = 8 x 2 tiles, two pixels (x, x + 32) per thread: 640 x 480 is 600 blocks,
-	// one resident wave on 148 SMs.
+	// A 256-thread block covers 128 x 8 pixels = 16 x 2 tiles; a thread owns the pixels x0 + 32 k of its row (k < 4),
+	// so the per-row part of the work (primitive header, span range, fill colour) is done once for four pixels.
 	const int y = int(blockIdx.y * 8u + (threadIdx.x >> 5));
+	const int x0 = int(blockIdx.x * (32u * kFillPixelsPerThread) + (threadIdx.x & 31u));
 	const uint32_t tile_row = uint32_t(y) / kTileH;
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
 		b.job_counter[0] = 0;
 
-	FbView view;
-	view.rdram = b.rdram;
-	view.hidden = b.hidden;
-	view.blend_lut = b.blend_lut;
-	view.fmt = fb.fmt;
-	view.rdram_size = fb.rdram_size;
-	view.alias = fb.color_addr == fb.depth_addr;
-	const uint32_t shift = view.fmt == FB_RGBA8888 ? 2u : ((view.fmt == FB_RGBA5551 || view.fmt == FB_IA88) ? 1u : 0u);
-
 	uint32_t tiles_done = 0, shaded = 0;
-#pragma unroll
-	for (int half = 0; half < 2; half++)
+	// Clear the bin masks of the block's tiles (the span kernel filled them as for any pass): the first lanes of the
+	// warp on each tile row take one tile each.
+	constexpr uint32_t kTilesPerBlockRow = 32u * kFillPixelsPerThread / kTileW;
+	if ((y & int(kTileH - 1)) == 0 && tile_row < fb.tiles_y && (threadIdx.x & 31u) < kTilesPerBlockRow)
 	{
-		const int x = int(blockIdx.x * 64u + uint32_t(half) * 32u + (threadIdx.x & 31u));
-		if ((x & int(kTileW - 1)) == 0 && (y & int(kTileH - 1)) == 0 && uint32_t(x) / kTileW < fb.tiles_x && tile_row < fb.tiles_y)
+		const uint32_t tile_x = blockIdx.x * kTilesPerBlockRow + (threadIdx.x & 31u);
+		if (tile_x < fb.tiles_x)
 		{
-			const size_t tile = size_t(tile_row) * fb.tiles_x + uint32_t(x) / kTileW;
+			const size_t tile = size_t(tile_row) * fb.tiles_x + tile_x;
 			uint32_t any = 0;
 			for (uint32_t i = 0; i < fb.mask_stride; i++)
 			{
@@ -944,31 +940,81 @@ __global__ void __launch_bounds__(256) k_fill_pass(PassBuffers b, FbInfo fb)
 			}
 			for (uint32_t i = 0; i < fb.coarse_stride; i++)
 				b.coarse_mask[tile * fb.coarse_stride + i] = 0u;
-			tiles_done += any ? 1u : 0u;
+			tiles_done = any ? 1u : 0u;
+		}
+	}
+
+	if (y < int(fb.height))
+	{
+		// Last fill colour that reached each of the thread's pixels, in submission order.
+		uint32_t color[kFillPixelsPerThread];
+		uint32_t covered = 0;
+		for (uint32_t i = 0; i < fb.num_prims; i++)
+		{
+			const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(&b.prims[i].span_base));
+			const int line_lo = int(int16_t(hdr.z & 0xffffu)), line_hi = int(int16_t(hdr.z >> 16));
+			if (y < line_lo || y > line_hi)
+				continue;
+			const Span *sp = b.spans + (hdr.x + uint32_t(y - line_lo));
+			const uint2 sh = __ldg(reinterpret_cast<const uint2 *>(&sp->start_x));
+			if ((sh.y >> 16) == 0u)
+				continue;
+			const int lo = int(int16_t(sh.x & 0xffffu)), hi = int(int16_t(sh.x >> 16));
+			const uint32_t fill = b.states[hdr.y & 0xffffu].fill_color;
+#pragma unroll
+			for (int k = 0; k < kFillPixelsPerThread; k++)
+			{
+				const int x = x0 + 32 * k;
+				if (x >= lo && x <= hi && x < int(fb.width))
+				{
+					color[k] = fill;
+					covered |= 1u << k;
+					shaded++;
+				}
+			}
 		}
 
-		if (x < int(fb.width) && y < int(fb.height))
+		const uint32_t row = fb.width * uint32_t(y);
+#pragma unroll
+		for (int k = 0; k < kFillPixelsPerThread; k++)
 		{
-			PixelState px;
-			px.r = px.g = px.b = px.a = 0;
-			px.depth = px.dz = 0;
-			px.color_dirty = px.depth_dirty = false;
-			px.color_index = (fb.color_addr >> shift) + fb.width * uint32_t(y) + uint32_t(x);
-
-			for (uint32_t i = 0; i < fb.num_prims; i++)
+			if (!((covered >> k) & 1u))
+				continue;
+			const uint32_t pix = row + uint32_t(x0 + 32 * k);
+			const uint32_t col = color[k];
+			if (fb.fmt == FB_RGBA5551 || fb.fmt == FB_IA88)
 			{
-				const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(&b.prims[i].span_base));
-				const int line_lo = int(int16_t(hdr.z & 0xffffu)), line_hi = int(int16_t(hdr.z >> 16));
-				if (y < line_lo || y > line_hi)
-					continue;
-				const Span *sp = b.spans + (hdr.x + uint32_t(y - line_lo));
-				const uint2 sh = *reinterpret_cast<const uint2 *>(&sp->start_x);
-				if ((sh.y >> 16) == 0u || x < int(int16_t(sh.x & 0xffffu)) || x > int(int16_t(sh.x >> 16)))
-					continue;
-				fill_pixel(view, px, b.states[hdr.y & 0xffffu].fill_color);
-				shaded++;
+				// The fill pipe stores the half of the fill colour the pixel's parity selects, as it is, and the
+				// coverage its low bit stands for (fill_pixel + store_color, rdp_blend.cuh, written out).
+				const uint32_t index = ((fb.color_addr >> 1) + pix) & ((fb.rdram_size >> 1) - 1u);
+				const uint32_t v = (index & 1u) ? (col & 0xffffu) : (col >> 16);
+				rdram16(b.rdram)[index ^ 1u] = uint16_t(v);
+				b.hidden[index] = uint8_t((v & 1u) * 3u);
 			}
-			store_color(view, px, px.color_index);
+			else if (fb.fmt == FB_RGBA8888)
+			{
+				const uint32_t index = ((fb.color_addr >> 2) + pix) & ((fb.rdram_size >> 2) - 1u);
+				rdram32(b.rdram)[index] = col;
+				*reinterpret_cast<uint16_t *>(b.hidden + 2u * index) = uint16_t((((col >> 16) & 1u) * 3u) | (((col & 1u) * 3u) << 8));
+			}
+			else
+			{
+				// 8-bit targets (and the 4-bit one, which the fill pipe leaves alone) take the general route.
+				FbView view;
+				view.rdram = b.rdram;
+				view.hidden = b.hidden;
+				view.blend_lut = b.blend_lut;
+				view.fmt = fb.fmt;
+				view.rdram_size = fb.rdram_size;
+				view.alias = fb.color_addr == fb.depth_addr;
+				PixelState px;
+				px.r = px.g = px.b = px.a = 0;
+				px.depth = px.dz = 0;
+				px.color_dirty = px.depth_dirty = false;
+				px.color_index = fb.color_addr + pix;
+				fill_pixel(view, px, col);
+				store_color(view, px, px.color_index);
+			}
 		}
 	}
 
@@ -1398,7 +1444,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		if (op.variant == &kFillPassVariant)
 		{
 			// Pixel grid, rounded up to whole tiles so that every tile's masks are cleared.
-			const dim3 grid((op.fb.tiles_x * kTileW + 63u) / 64u, (op.fb.tiles_y + 1u) / 2u);
+			const dim3 grid((op.fb.tiles_x * kTileW + 32u * kFillPixelsPerThread - 1u) / (32u * kFillPixelsPerThread), (op.fb.tiles_y + 1u) / 2u);
 			k_fill_pass<<<grid, 256, 0, dev->stream>>>(dev->buffers(op), op.fb);
 			prof_end(dev, s);
 			dev->launches++;
