@@ -60,10 +60,64 @@ struct StagingLayout
 	static constexpr size_t total = uploads_off + size_t(kMaxUploadsPerPass) * sizeof(TmemUpload);
 };
 
-// Front end of a pass, one launch: the first `tmem_blocks` blocks replay the pass's texture loads (one thread per
-// TMEM word), the remaining blocks decode one primitive per thread and allocate its span jobs.
+// Front end of a pass, one launch: the first `tmem_blocks` blocks replay the pass's texture loads, the remaining
+// blocks decode one primitive per thread and allocate its span jobs.
+//
+// Texture-load replay: what an upload writes to a TMEM word does not depend on what the word held (the gather of
+// rdp_tmem.cuh is a pure function of the upload and the word index), only the order of the writes matters.  A block
+// owns 32 TMEM words; its eight warps evaluate eight uploads of the pass at a time -- eight RDRAM round trips in
+// flight instead of one after the other -- and the first warp then applies the results in upload order, writing a
+// snapshot after each.
 constexpr uint32_t kFrontThreads = 256;
-constexpr uint32_t kTmemBlocks = kTmemBytes / 2 / kFrontThreads;
+constexpr uint32_t kTmemWordsPerBlock = 32;
+constexpr uint32_t kTmemUploadLanes = kFrontThreads / kTmemWordsPerBlock;
+constexpr uint32_t kTmemBlocks = kTmemBytes / 2 / kTmemWordsPerBlock;
+
+__device__ __forceinline__ void front_tmem_replay(const PassBuffers &b, uint32_t num_uploads, uint32_t rdram_size)
+{
+	__shared__ uint32_t s_gather[kTmemUploadLanes][kTmemWordsPerBlock]; // bit 31: the upload writes the word; low 16 bits: value
+	const uint32_t w = threadIdx.x & (kTmemWordsPerBlock - 1u), lane_u = threadIdx.x / kTmemWordsPerBlock;
+	const int slot = int(blockIdx.x * kTmemWordsPerBlock + w);
+	uint16_t *live = reinterpret_cast<uint16_t *>(b.tmem);
+	uint16_t *inst = reinterpret_cast<uint16_t *>(b.tmem_instances);
+	RdramView rdram;
+	rdram.data = b.rdram;
+	rdram.mask = rdram_size - 1u;
+
+	uint32_t value = 0;
+	if (lane_u == 0)
+	{
+		value = live[slot];
+		inst[slot] = uint16_t(value);
+	}
+	for (uint32_t base = 0; base < num_uploads; base += kTmemUploadLanes)
+	{
+		const uint32_t u = base + lane_u;
+		uint32_t g = 0;
+		if (u < num_uploads)
+		{
+			uint32_t v = 0xffff0000u; // tmem_apply_upload only touches the low 16 bits, and only on a hit
+			tmem_apply_upload(b.uploads[u], rdram, slot, v);
+			g = (v >> 16) == 0u ? (0x80000000u | v) : 0u;
+		}
+		s_gather[lane_u][w] = g;
+		__syncthreads();
+		if (lane_u == 0)
+		{
+			const uint32_t n = min(kTmemUploadLanes, num_uploads - base);
+			for (uint32_t k = 0; k < n; k++)
+			{
+				const uint32_t r = s_gather[k][w];
+				if (r & 0x80000000u)
+					value = r & 0xffffu;
+				inst[size_t(base + k + 1u) * (kTmemBytes / 2) + slot] = uint16_t(value);
+			}
+		}
+		__syncthreads();
+	}
+	if (lane_u == 0)
+		live[slot] = uint16_t(value);
+}
 
 __global__ void __launch_bounds__(kFrontThreads) k_front(PassBuffers b, uint32_t tmem_blocks, uint32_t num_uploads,
                                                          uint32_t rdram_size, uint32_t num_prims)
@@ -73,7 +127,7 @@ __global__ void __launch_bounds__(kFrontThreads) k_front(PassBuffers b, uint32_t
 		b.job_counter[1] = 0;
 	if (blockIdx.x < tmem_blocks)
 	{
-		pass_tmem_word(b, num_uploads, rdram_size, int(blockIdx.x * kFrontThreads + threadIdx.x));
+		front_tmem_replay(b, num_uploads, rdram_size);
 		return;
 	}
 
@@ -81,8 +135,30 @@ __global__ void __launch_bounds__(kFrontThreads) k_front(PassBuffers b, uint32_t
 	uint32_t njobs = 0;
 	if (i < num_prims)
 	{
-		pass_setup_prim(b, i);
+		// The decode reads its command words one dependent group after another; with ~1 warp per SM in this launch
+		// nothing hides those round trips.  Fetch the whole command first -- every load independent -- and decode
+		// from the local copy.
 		const PrimRecord rec = b.records[i];
+		const uint32_t *w = b.words + rec.word_offset;
+		const uint2 *w2 = reinterpret_cast<const uint2 *>(w); // commands are 64-bit units: word_offset is even
+		uint32_t local_words[44];
+		const uint2 head = __ldg(w2);
+		const uint32_t op = (head.x >> 24) & 63u;
+		// Triangles: 8 edge words + 16 shade + 16 texture + 4 depth (bits 2, 1, 0 of the opcode); rectangles 2 or 4.
+		const uint32_t len = op >= OP_TRI_FILL && op <= OP_TRI_SHADE_TEX_Z ? 8u + ((op & 4u) ? 16u : 0u) + ((op & 2u) ? 16u : 0u) + ((op & 1u) ? 4u : 0u)
+		                                                                      : (op == OP_FILL_RECT ? 2u : 4u);
+		local_words[0] = head.x;
+		local_words[1] = head.y;
+#pragma unroll
+		for (uint32_t k = 1; k < 22; k++)
+		{
+			uint2 v = make_uint2(0u, 0u);
+			if (2u * k < len)
+				v = __ldg(w2 + k);
+			local_words[2 * k] = v.x;
+			local_words[2 * k + 1] = v.y;
+		}
+		decode_primitive(local_words, b.states[rec.state_id], rec, b.prims[i]);
 		njobs = span_job_count(rec.line_lo, rec.line_hi);
 	}
 
