@@ -109,6 +109,10 @@ int rdpb_launch_upscale_sync(rdpb_device *dev, const void *native_fb_info, int s
 /* Blocking read-back of the whole upscaled domain: S*S images of rdram_size bytes, S*S images of rdram_size / 2 bytes. */
 int rdpb_upscaled_read(rdpb_device *dev, void *rdram_dst, void *hidden_dst);
 
+/* The scan-out runs on its own stream; this makes the compute stream (rdpb_stream) wait for the one in flight, for
+ * callers that consume rdpb_vi_output_device_ptr() in compute-stream order. */
+int rdpb_vi_join(rdpb_device *dev);
+
 /* Instrumentation: number of kernels launched since creation. */
 uint64_t rdpb_launch_count(rdpb_device *dev);
 

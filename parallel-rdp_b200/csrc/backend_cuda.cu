@@ -1346,6 +1346,12 @@ struct rdpb_device
 	cudaStream_t stream_up = nullptr, stream_down = nullptr;
 	bool side_streams_owned = true;
 	cudaEvent_t vi_done = nullptr;
+	// The scan-out runs on its own stream, behind everything rendered so far, so that the next frame's passes need
+	// not queue up behind it: only an operation that writes RDRAM the scan-out may still be reading waits for it.
+	cudaStream_t stream_vi = nullptr;
+	cudaEvent_t vi_fork = nullptr;   // compute stream -> scan-out stream: everything the scan-out must see
+	bool vi_busy = false;            // a scan-out was launched and the compute stream has not waited for it since
+	uint32_t vi_lo = 0, vi_hi = 0;   // RDRAM bytes it reads (lo >= hi: unknown)
 	cudaEvent_t readback_done[2] = {};
 	bool readback_in_flight[2] = {};
 	unsigned staging_index = 0;
@@ -1466,21 +1472,50 @@ static void use_device(const rdpb_device *dev)
 	}
 }
 
+// ---- scan-out stream ----
+// Make the compute stream wait for the scan-out in flight (if any).
+static int join_vi(rdpb_device *dev)
+{
+	if (dev->vi_busy)
+	{
+		CK(cudaStreamWaitEvent(dev->stream, dev->vi_done, 0));
+		dev->vi_busy = false;
+	}
+	return 0;
+}
+
+// Does a pass rendering into `fb` write RDRAM the scan-out in flight may still read?  (Hidden RDRAM follows RDRAM one
+// byte per 16-bit word, so the same test covers it; the upscaled domain's slices are addressed like native RDRAM.)
+static bool writes_scanout_range(const rdpb_device *dev, const FbInfo &fb)
+{
+	if (!dev->vi_busy)
+		return false;
+	if (dev->vi_lo >= dev->vi_hi)
+		return true;
+	const uint64_t pixels = uint64_t(fb.width >> fb.scale_log2) * (fb.height >> fb.scale_log2);
+	const uint32_t bpp = fb.fmt == FB_RGBA8888 ? 4u : ((fb.fmt == FB_RGBA5551 || fb.fmt == FB_IA88) ? 2u : 1u);
+	const uint64_t c_lo = fb.color_addr, c_hi = c_lo + pixels * bpp;
+	const uint64_t d_lo = fb.depth_addr, d_hi = d_lo + pixels * 2u;
+	if (c_hi > fb.rdram_size || d_hi > fb.rdram_size)
+		return true; // wraps around the end of RDRAM
+	return (c_lo < dev->vi_hi && dev->vi_lo < c_hi) || (d_lo < dev->vi_hi && dev->vi_lo < d_hi);
+}
+
 // ---- profiling helpers ---------------------------------------------------------------------------------------
-static int prof_begin(rdpb_device *dev, int kind)
+static int prof_begin(rdpb_device *dev, int kind, cudaStream_t stream = nullptr)
 {
 	if (!dev->profiling || dev->prof_used >= dev->prof_pool.size())
 		return -1;
 	const int slot = int(dev->prof_used++);
 	dev->prof_pool[slot].kind = kind;
-	cudaEventRecord(dev->prof_pool[slot].a, dev->stream);
+	cudaEventRecord(dev->prof_pool[slot].a, stream ? stream : dev->stream);
 	return slot;
 }
 
-static void prof_end(rdpb_device *dev, int slot)
+static void prof_end(rdpb_device *dev, int slot, cudaStream_t stream = nullptr)
 {
 	if (slot >= 0)
-		cudaEventRecord(dev->prof_pool[slot].b, dev->stream);
+		cudaEventRecord(dev->prof_pool[slot].b, stream ? stream : dev->stream);
 }
 
 // ---- the one place kernels are launched from -----------------------------------------------------------------
@@ -1516,6 +1551,9 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	}
 	case GOP_TILES:
 	{
+		// The first kernels of a pass (set-up, spans) never write RDRAM; this one does.
+		if (writes_scanout_range(dev, op.fb) && join_vi(dev) != 0)
+			return -1;
 		const int s = prof_begin(dev, op.variant == &kFillPassVariant ? RDPB_KERNEL_FILL_PASS : RDPB_KERNEL_TILES);
 		if (op.variant == &kFillPassVariant)
 		{
@@ -1546,6 +1584,8 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	}
 	case GOP_UPSCALE_SYNC:
 	{
+		if (writes_scanout_range(dev, op.fb) && join_vi(dev) != 0)
+			return -1;
 		UpscaleSync u;
 		u.rdram = dev->rdram;
 		u.hidden = dev->hidden;
@@ -1565,11 +1605,20 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	}
 	case GOP_VI:
 	{
+		// Fork: the scan-out stream picks up behind everything the compute stream has been given so far.  (A second
+		// scan-out before the compute stream ever waited for the first simply queues behind it on that stream.)
+		cudaStream_t vs = dev->stream_vi;
+		if (vs != dev->stream)
+		{
+			if (!check(dev, cudaEventRecord(dev->vi_fork, dev->stream), "cudaEventRecord") ||
+			    !check(dev, cudaStreamWaitEvent(vs, dev->vi_fork, 0), "cudaStreamWaitEvent"))
+				return -1;
+		}
 		dev->vi_out_index ^= 1u;
 		if (dev->readback_in_flight[dev->vi_out_index])
 		{
 			// The image about to be overwritten may still be on its way to the host.
-			if (!check(dev, cudaStreamWaitEvent(dev->stream, dev->readback_done[dev->vi_out_index], 0), "cudaStreamWaitEvent"))
+			if (!check(dev, cudaStreamWaitEvent(vs, dev->readback_done[dev->vi_out_index], 0), "cudaStreamWaitEvent"))
 				return -1;
 			dev->readback_in_flight[dev->vi_out_index] = false;
 		}
@@ -1587,17 +1636,17 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		{
 			const dim3 block(32, 8);
 			const dim3 grid((f.filt_width + 31) / 32, (f.filt_height + 7) / 8, f.fetch_bug ? 2 : 1);
-			const int s = prof_begin(dev, RDPB_KERNEL_VI_FILTER);
-			k_vi_filter<<<grid, block, 0, dev->stream>>>(f, b);
-			prof_end(dev, s);
+			const int s = prof_begin(dev, RDPB_KERNEL_VI_FILTER, vs);
+			k_vi_filter<<<grid, block, 0, vs>>>(f, b);
+			prof_end(dev, s, vs);
 			dev->launches++;
 		}
 		{
 			const dim3 block(32, 8);
 			const dim3 grid((f.out_width + 31) / 32, (f.out_height + 7) / 8);
-			const int s = prof_begin(dev, RDPB_KERNEL_VI_SCALE);
-			k_vi_scale<<<grid, block, 0, dev->stream>>>(f, b);
-			prof_end(dev, s);
+			const int s = prof_begin(dev, RDPB_KERNEL_VI_SCALE, vs);
+			k_vi_scale<<<grid, block, 0, vs>>>(f, b);
+			prof_end(dev, s, vs);
 			dev->launches++;
 		}
 		// Upscaled scan-out: halve the finished image downscale_steps times.  The full-size image stays where it is
@@ -1612,7 +1661,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 				uint32_t *dst = ((f.downscale_steps - i) & 1u) ? dev->vi_down[dev->vi_out_index] : dev->vi_filtered;
 				const dim3 block(32, 8);
 				const dim3 grid((w / 2 + 31) / 32, (h / 2 + 7) / 8);
-				k_vi_downscale<<<grid, block, 0, dev->stream>>>(src, w, dst, w / 2, h / 2);
+				k_vi_downscale<<<grid, block, 0, vs>>>(src, w, dst, w / 2, h / 2);
 				dev->launches++;
 				src = dst;
 				w /= 2;
@@ -1620,6 +1669,11 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 			}
 			dev->vi_result[dev->vi_out_index] = const_cast<uint32_t *>(src);
 		}
+		if (!check(dev, cudaEventRecord(dev->vi_done, vs), "cudaEventRecord"))
+			return -1;
+		dev->vi_busy = vs != dev->stream;
+		dev->vi_lo = f.vram_lo;
+		dev->vi_hi = f.vram_hi;
 		break;
 	}
 	default:
@@ -1707,6 +1761,11 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		need(cudaStreamCreateWithFlags(&dev->stream_down, cudaStreamNonBlocking), "cudaStreamCreate down");
 	}
 	need(cudaEventCreateWithFlags(&dev->vi_done, cudaEventDisableTiming), "cudaEventCreate");
+	need(cudaEventCreateWithFlags(&dev->vi_fork, cudaEventDisableTiming), "cudaEventCreate");
+	if (dev->stream_up == dev->stream)
+		dev->stream_vi = dev->stream; // RDP_B200_SINGLE_STREAM: everything in one queue
+	else
+		need(cudaStreamCreateWithFlags(&dev->stream_vi, cudaStreamNonBlocking), "cudaStreamCreate vi");
 	for (auto &e : dev->readback_done)
 		need(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
 	need(cudaMalloc(&dev->rdram, rdram_size), "cudaMalloc rdram");
@@ -1845,6 +1904,10 @@ void rdpb_device_destroy(rdpb_device *dev)
 	}
 	if (dev->vi_done)
 		cudaEventDestroy(dev->vi_done);
+	if (dev->vi_fork)
+		cudaEventDestroy(dev->vi_fork);
+	if (dev->stream_vi && dev->stream_vi != dev->stream)
+		cudaStreamDestroy(dev->stream_vi);
 	for (auto &e : dev->readback_done)
 		if (e)
 			cudaEventDestroy(e);
@@ -1882,6 +1945,9 @@ int rdpb_unregister_host_memory(rdpb_device *dev, void *ptr)
 static int copy_common(rdpb_device *dev, void *dst, const void *src, size_t size, cudaMemcpyKind kind, int sync)
 {
 	use_device(dev);
+	// Slow-path copies (RDRAM / hidden RDRAM up and down, synchronous image reads): order them behind the scan-out too.
+	if (join_vi(dev) != 0)
+		return -1;
 	CK(cudaMemcpyAsync(dst, src, size, kind, dev->stream));
 	if (sync)
 		CK(cudaStreamSynchronize(dev->stream));
@@ -1907,6 +1973,8 @@ int rdpb_hidden_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size
 int rdpb_hidden_fill(rdpb_device *dev, uint8_t value)
 {
 	use_device(dev);
+	if (join_vi(dev) != 0)
+		return -1;
 	CK(cudaMemsetAsync(dev->hidden, value, dev->hidden_size, dev->stream));
 	return 0;
 }
@@ -2177,8 +2245,8 @@ int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *line
 		}
 		ViLine *h_lines = reinterpret_cast<ViLine *>(dev->vi_host_staging) + size_t(slot) * kViMaxLines;
 		memcpy(h_lines, lines, sizeof(ViLine) * kViMaxLines);
-		CK(cudaMemcpyAsync(d_lines, h_lines, sizeof(ViLine) * kViMaxLines, cudaMemcpyHostToDevice, dev->stream));
-		CK(cudaEventRecord(dev->vi_lines_done[slot], dev->stream));
+		CK(cudaMemcpyAsync(d_lines, h_lines, sizeof(ViLine) * kViMaxLines, cudaMemcpyHostToDevice, dev->stream_vi));
+		CK(cudaEventRecord(dev->vi_lines_done[slot], dev->stream_vi));
 		dev->vi_lines_in_flight[slot] = true;
 	}
 
@@ -2186,6 +2254,12 @@ int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *line
 	if (dev->recording)
 		dev->log.push_back(op);
 	return issue(dev, op);
+}
+
+int rdpb_vi_join(rdpb_device *dev)
+{
+	use_device(dev);
+	return join_vi(dev);
 }
 
 static uint32_t *vi_result_ptr(rdpb_device *dev, unsigned idx) { return dev->vi_result[idx] ? dev->vi_result[idx] : dev->vi_out[idx]; }
@@ -2205,8 +2279,7 @@ int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint
 {
 	use_device(dev);
 	const unsigned idx = dev->vi_out_index;
-	CK(cudaEventRecord(dev->vi_done, dev->stream));
-	CK(cudaStreamWaitEvent(dev->stream_down, dev->vi_done, 0));
+	CK(cudaStreamWaitEvent(dev->stream_down, dev->vi_done, 0)); // recorded behind the scan-out on its stream
 	if (width && height)
 		CK(cudaMemcpyAsync(dst, vi_result_ptr(dev, idx), size_t(width) * height * 4, cudaMemcpyDeviceToHost, dev->stream_down));
 	CK(cudaEventRecord(dev->readback_done[idx], dev->stream_down));
@@ -2266,7 +2339,9 @@ int rdpb_sync(rdpb_device *dev)
 	use_device(dev);
 	CK(cudaStreamSynchronize(dev->stream_up));
 	CK(cudaStreamSynchronize(dev->stream));
+	CK(cudaStreamSynchronize(dev->stream_vi));
 	CK(cudaStreamSynchronize(dev->stream_down));
+	dev->vi_busy = false;
 	return 0;
 }
 
@@ -2391,6 +2466,10 @@ int rdpb_replay_interleaved(rdpb_device *const *devs, uint32_t num_devs, uint32_
 			if (!steps || rdpb_replay_step(devs[d], s % steps) != 0)
 				return -1;
 		}
+	// The caller times on the compute streams: the last scan-outs belong inside that bracket.
+	for (uint32_t d = 0; d < num_devs; d++)
+		if (rdpb_vi_join(devs[d]) != 0)
+			return -1;
 	return 0;
 }
 }

@@ -66,6 +66,11 @@ struct ViFrame
 	// `downscale_steps` times (video_interface.cpp:1001-1064).
 	uint32_t scale_log2;
 	uint32_t downscale_steps;
+
+	// RDRAM byte range [vram_lo, vram_hi) the filter can read (native addresses; video_interface.cpp:369-396).  The
+	// backend runs the scan-out on its own stream and holds back only render passes that write into this range.
+	// lo >= hi: unknown, every pass waits.
+	uint32_t vram_lo, vram_hi;
 };
 
 struct ViBuffers

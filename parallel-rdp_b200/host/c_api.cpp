@@ -116,6 +116,9 @@ const void *rdp_b200_scanout(rdp_b200_processor *p, const rdp_b200_scanout_optio
 	ScanoutImage img = p->impl.scanout(convert_options(opts));
 	*width = img.width;
 	*height = img.height;
+	// The contract of this entry point: the pointer is good in rdp_b200_cuda_stream() order.
+	if (p->impl.get_backend_device())
+		rdpb_vi_join(p->impl.get_backend_device());
 	return img.device_rgba8;
 }
 

@@ -310,24 +310,36 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 	// Internal upscaling: everything measured in framebuffer or output pixels scales with the image
 	// (ref video_interface.cpp:1299-1317); the per-pixel steps (x_add, y_add) do not.
 	const int scale = 1 << scale_log2;
-	if (scale > 1)
+	// RDRAM range this scan-out can read (ref scanout_memory_range, video_interface.cpp:369-396): a 2-pixel border for
+	// the AA / dither filters plus one more column for the divot.
+	uint32_t vram_lo = 0, vram_hi = 0;
 	{
-		// The framebuffer may hold pixels the RDP never rendered (CPU-drawn screens): bring the upscaled domain up to
-		// date over the range this scan-out can read (ref vram_fetch_stage, video_interface.cpp:412-420, 369-396).
+		const int pixel_size_log2 = (regs.status & VI_CONTROL_TYPE_MASK) == VI_CONTROL_TYPE_RGBA8888_BIT ? 2 : 1;
+		const int aa_width = regs.max_x + 2 + 4 + int(divot) * 2;
+		const int aa_height = regs.max_y + 1 + 4;
+		int64_t offset = regs.vi_offset & ~((1 << pixel_size_log2) - 1);
+		offset += int64_t((divot ? -3 : -2) + -2 * regs.vi_width) << pixel_size_log2;
+		const int64_t length = (int64_t(aa_height) * regs.vi_width + aa_width) << pixel_size_log2;
+		if (offset >= 0 && length > 0 && offset + length <= int64_t(rdram_size))
 		{
-			const int pixel_size_log2 = (regs.status & VI_CONTROL_TYPE_MASK) == VI_CONTROL_TYPE_RGBA8888_BIT ? 2 : 1;
-			const int aa_width = regs.max_x + 2 + 4 + int(divot) * 2;
-			const int aa_height = regs.max_y + 1 + 4;
-			int offset = regs.vi_offset & ~((1 << pixel_size_log2) - 1);
-			offset += ((divot ? -3 : -2) + -2 * regs.vi_width) << pixel_size_log2;
+			vram_lo = uint32_t(offset);
+			vram_hi = uint32_t(offset + length);
+		}
+		if (scale > 1)
+		{
+			// The framebuffer may hold pixels the RDP never rendered (CPU-drawn screens): bring the upscaled domain up
+			// to date over that range (ref vram_fetch_stage, video_interface.cpp:412-420).
 			FbInfo range = {};
 			range.color_addr = range.depth_addr = uint32_t(offset) & uint32_t(rdram_size - 1);
-			range.width = uint32_t(aa_height * regs.vi_width + aa_width);
+			range.width = uint32_t(length >> pixel_size_log2);
 			range.height = 1;
 			range.fmt = pixel_size_log2 == 2 ? uint32_t(FB_RGBA8888) : uint32_t(FB_RGBA5551);
 			range.rdram_size = uint32_t(rdram_size);
 			rdpb_launch_upscale_sync(device, &range, RDPB_UPSCALE_SYNC_PRE);
 		}
+	}
+	if (scale > 1)
+	{
 		regs.h_start *= scale;
 		regs.h_start_clamp *= scale;
 		regs.v_start *= scale;
@@ -356,6 +368,8 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 	f.rdram_size = uint32_t(rdram_size);
 	f.fetch_bug = (regs.init_y_add < 1024 && scale == 1) ? 1u : 0u; // ref need_fetch_bug_emulation, video_interface.cpp:398-403
 	f.scale_log2 = scale_log2;
+	f.vram_lo = vram_lo;
+	f.vram_hi = vram_hi;
 	f.filt_width = std::min<int>(regs.max_x + 2, int(kViStageWidth) * scale);
 	f.filt_height = std::min<int>(regs.max_y + 2, int(kViStageHeight) * scale);
 	f.stage_stride = kViStageWidth * uint32_t(scale);

@@ -384,6 +384,7 @@ int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint
 {
 	return rdpb_vi_read_output(dev, dst, width, height, 1);
 }
+int rdpb_vi_join(rdpb_device *) { return 0; }
 int rdpb_signal(rdpb_device *, uint64_t) { return 0; }
 int rdpb_wait(rdpb_device *, uint64_t) { return 0; }
 int rdpb_sync(rdpb_device *) { return 0; }
