@@ -208,8 +208,11 @@ def run_ours(args):
     n_full = max(8, int(np.ceil(1.12 * L2_BYTES / frame_bytes)))
     n_full = min(n_full, max(args.steps, 8)) if args.small else n_full
     n_extra = max(8, n_full // 4)
-    base_seed = 1000 + 16 * rank if world > 1 else 2
-    streams = [Stream(rdp, lib, torch, local_rank, base_seed + s, n_full if s == 0 else n_extra, args.triangles, E2E_DEPTH,
+    # N > 1: the farm's round-robin deal (harness/farm.py, tests/test_farm_distributed.py) -- rank r owns the stream ids k
+    # with k mod world == r; stream k is seeded 1000 + k.  N = 1 keeps the C2 definition's seed 2 for stream 0.
+    def stream_seed(s):
+        return 1000 + (s * world + rank) if world > 1 else 2 + s
+    streams = [Stream(rdp, lib, torch, local_rank, stream_seed(s), n_full if s == 0 else n_extra, args.triangles, E2E_DEPTH,
                       args.upscale, args.downscale_steps)
                for s in range(s_max)]
     s0 = streams[0]
