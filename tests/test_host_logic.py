@@ -148,3 +148,32 @@ def test_scanout_async_matches_sync(monkeypatch):
     assert len(a) == len(b) == 3
     for x, y in zip(a, b):
         assert x.shape == y.shape and x.any() and np.array_equal(x, y)
+
+
+def test_bulk_vi_register_write_equals_fourteen_single_writes():
+    """rdp_b200_set_vi_registers (extension) against rdp_b200_set_vi_register: same scan-out."""
+    import numpy as np
+    from harness import workloads as wl
+    from sidebyside import SideBySide, rdp
+
+    images = []
+    for bulk in (False, True):
+        sbs = SideBySide("hostsim", rdram_size=wl.RDRAM_SIZE, hidden_size=wl.HIDDEN_SIZE, with_oracle=False)
+        try:
+            sbs.randomize_rdram(np.random.RandomState(7))
+            regs = wl.c2_vi_registers(1)
+            if bulk:
+                block = np.zeros(14, np.uint32)
+                for k, v in regs.items():
+                    block[rdp.VI_REG[k]] = v & 0xffffffff
+                sbs.gpu.set_vi_registers(block)
+            else:
+                for k, v in regs.items():
+                    sbs.gpu.set_vi_register(k, v)
+            opts = sbs.gpu.default_scanout_options()
+            opts.upscale_deinterlacing = 0
+            pix, w, h = sbs.gpu.scanout_sync(opts)
+            images.append(pix.copy())
+        finally:
+            sbs.close()
+    assert images[0].size and np.array_equal(images[0], images[1])
