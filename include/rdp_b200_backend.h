@@ -72,8 +72,11 @@ int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out);
  * one rdpb_pass_upload_words() call per contiguous run (`src` is staging memory or caller-owned "borrowed" memory). */
 int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *counts);
 int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_words, uint32_t dst_word_offset);
-/* Front end of a pass in one launch: replay `num_uploads` texture loads into TMEM snapshots (when update_tmem),
- * decode `num_prims` primitives from their raw command words and allocate their span jobs. */
+/* Front end of a pass in one launch: replay `num_uploads` texture loads into TMEM snapshots (when update_tmem & 1),
+ * decode `num_prims` primitives from their raw command words and allocate their span jobs.  update_tmem & 2: the
+ * pass's texture loads may read memory the previous pass renders to -- the CUDA backend runs set-up work ahead of the
+ * previous pass's tile kernel unless told so.  update_tmem & 4: the pass samples TMEM (the CUDA backend keeps two sets
+ * of TMEM snapshots and refreshes the one this pass uses when it is out of date even if bit 0 is clear). */
 int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims);
 int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo */);
 /* `summary` (rdpb::PassSummary) describes what the pass's states have in common; the backend uses it to pick a

@@ -1304,12 +1304,15 @@ enum OpKind
 	GOP_TILES = RDPB_KERNEL_TILES,
 	GOP_VI = RDPB_KERNEL_VI_FILTER, // issues filter + scale
 	GOP_UPSCALE_SYNC = 100,         // PRE / POST synchronisation of the upscaled domain (count = stage)
+	GOP_PASS_END = 101,             // stream bookkeeping at the end of a pass (no kernel)
 };
 
 struct GpuOp
 {
 	int kind;
 	uint32_t count, count2, flag;
+	uint32_t parity; // scratch set of the pass the operation belongs to
+	uint32_t hazard; // GOP_FRONT: the pass's texture loads may read what the previous pass renders
 	const TileVariant *variant;
 	FbInfo fb;
 	ViFrame vi;
@@ -1330,7 +1333,7 @@ struct rdpb_device
 
 	uint8_t *rdram = nullptr, *hidden = nullptr;
 	uint8_t *tmem_host = nullptr, *tmem_dev = nullptr; // same mapped pinned allocation
-	uint8_t *tmem_instances = nullptr;
+	uint8_t *tmem_instances = nullptr; // two sets (pass parity), kTmemBytes * (kMaxUploadsPerPass + 1) each
 	uint8_t *blend_lut = nullptr, *gamma_lut = nullptr;
 	unsigned long long *d_counters = nullptr;
 
@@ -1358,8 +1361,23 @@ struct rdpb_device
 
 	uint32_t *d_words[kStagingSlots] = {};  // device-side input slots, one per staging slot
 	uint8_t *d_inputs[kStagingSlots] = {};  // records | states | texture-load descriptors
-	PrimSetup *d_prims = nullptr;
-	Span *d_spans = nullptr;
+	// Per-pass scratch exists twice, indexed by the pass's parity: the set-up and span kernels of pass p + 1 run on
+	// their own stream while the tile kernel of pass p is still reading pass p's set.
+	static constexpr size_t kTmemSetBytes = size_t(kTmemBytes) * (kMaxUploadsPerPass + 1);
+	static constexpr size_t kFineWords = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 32);
+	static constexpr size_t kCoarseWords = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 1024);
+	PrimSetup *d_prims = nullptr; // [2][kMaxPrimsPerPass]
+	Span *d_spans = nullptr;      // [2][kMaxSpansPerPass]
+	uint32_t cur_parity = 0;                  // parity of the pass being submitted
+	cudaStream_t stream_front = nullptr;      // k_front + native k_span_bin of every pass, in submission order
+	cudaEvent_t span_done[2] = {};            // stream_front: the pass's set-up + spans are complete
+	cudaEvent_t scratch_free[2] = {};         // compute stream: the last pass that used this scratch set is done with it
+	bool front_pending[2] = {};               // span_done[q] recorded and the compute stream has not waited for it yet
+	cudaEvent_t host_write_done = nullptr;    // compute stream: last host -> RDRAM copy (texture loads read RDRAM)
+	bool host_write_pending = false;
+	// Snapshot 0 of a set is TMEM as it was when the set was last refreshed; live TMEM moves on with every pass that
+	// loads textures (and with host pokes, which arrive as a refresh request without uploads).
+	uint64_t tmem_epoch = 1, snapshot_epoch[2] = {};
 	// internal upscaling: S*S slices of RDRAM / hidden RDRAM, the native-sized shadow, the upscaled pass's spans + masks
 	uint32_t scale_log2 = 0;
 	uint8_t *up_rdram = nullptr, *up_hidden = nullptr, *up_reference = nullptr;
@@ -1367,8 +1385,8 @@ struct rdpb_device
 	uint32_t *up_fine = nullptr, *up_coarse = nullptr;
 	uint32_t *vi_down[2] = { nullptr, nullptr }; // down-sized results of an upscaled scan-out, per output slot
 	uint32_t *vi_result[2] = { nullptr, nullptr }; // what the last scan-out into each slot produced (full or down-sized)
-	uint32_t *d_fine = nullptr, *d_coarse = nullptr;
-	uint32_t *d_jobs = nullptr, *d_job_counter = nullptr;
+	uint32_t *d_fine = nullptr, *d_coarse = nullptr;      // [2][...]
+	uint32_t *d_jobs = nullptr, *d_job_counter = nullptr; // [2][kMaxJobsPerPass], [2][64]
 
 	uint32_t *vi_filtered = nullptr;
 	uint32_t *vi_out[2] = {};
@@ -1419,14 +1437,15 @@ struct rdpb_device
 		b.records = op.records;
 		b.states = op.states;
 		b.uploads = op.uploads;
-		b.prims = d_prims;
-		b.spans = d_spans;
-		b.fine_mask = d_fine;
-		b.coarse_mask = d_coarse;
-		b.jobs = d_jobs;
-		b.job_counter = d_job_counter;
+		const size_t q = op.parity & 1u;
+		b.prims = d_prims + q * kMaxPrimsPerPass;
+		b.spans = d_spans + q * size_t(kMaxSpansPerPass);
+		b.fine_mask = d_fine + q * kFineWords;
+		b.coarse_mask = d_coarse + q * kCoarseWords;
+		b.jobs = d_jobs + q * size_t(kMaxJobsPerPass);
+		b.job_counter = d_job_counter + q * 64u;
 		b.tmem = tmem_dev;
-		b.tmem_instances = tmem_instances;
+		b.tmem_instances = tmem_instances + q * kTmemSetBytes;
 		b.rdram = rdram;
 		b.hidden = hidden;
 		b.blend_lut = blend_lut;
@@ -1484,6 +1503,17 @@ static int join_vi(rdpb_device *dev)
 	return 0;
 }
 
+// Make the compute stream wait for the set-up + span kernels of the pass using scratch set q.
+static int join_front(rdpb_device *dev, uint32_t q)
+{
+	if (dev->front_pending[q])
+	{
+		CK(cudaStreamWaitEvent(dev->stream, dev->span_done[q], 0));
+		dev->front_pending[q] = false;
+	}
+	return 0;
+}
+
 // Does a pass rendering into `fb` write RDRAM the scan-out in flight may still read?  (Hidden RDRAM follows RDRAM one
 // byte per 16-bit word, so the same test covers it; the upscaled domain's slices are addressed like native RDRAM.)
 static bool writes_scanout_range(const rdpb_device *dev, const FbInfo &fb)
@@ -1530,22 +1560,60 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		const uint32_t setup_blocks = (op.count + kFrontThreads - 1) / kFrontThreads;
 		if (tmem_blocks + setup_blocks == 0)
 			break;
-		const int s = prof_begin(dev, RDPB_KERNEL_FRONT);
-		k_front<<<tmem_blocks + setup_blocks, kFrontThreads, 0, dev->stream>>>(dev->buffers(op), tmem_blocks, op.count2,
-		                                                                     dev->rdram_size, op.count);
-		prof_end(dev, s);
+		// Set-up runs on the front stream, ahead of the compute stream: it waits for the scratch set's previous user
+		// (two passes back), for host writes into RDRAM (texture sources), and -- only when the host saw that this
+		// pass's texture loads may read the previous pass's render target -- for the previous pass.
+		cudaStream_t fs = dev->stream_front;
+		const uint32_t q = op.parity & 1u;
+		if (fs != dev->stream)
+		{
+			if (!check(dev, cudaStreamWaitEvent(fs, dev->scratch_free[q], 0), "cudaStreamWaitEvent"))
+				return -1;
+			if (op.hazard && !check(dev, cudaStreamWaitEvent(fs, dev->scratch_free[q ^ 1u], 0), "cudaStreamWaitEvent"))
+				return -1;
+			if (dev->host_write_pending)
+			{
+				if (!check(dev, cudaStreamWaitEvent(fs, dev->host_write_done, 0), "cudaStreamWaitEvent"))
+					return -1;
+				dev->host_write_pending = false;
+			}
+		}
+		const int s = prof_begin(dev, RDPB_KERNEL_FRONT, fs);
+		k_front<<<tmem_blocks + setup_blocks, kFrontThreads, 0, fs>>>(dev->buffers(op), tmem_blocks, op.count2, dev->rdram_size, op.count);
+		prof_end(dev, s, fs);
 		dev->launches++;
+		if (fs != dev->stream)
+		{
+			if (!check(dev, cudaEventRecord(dev->span_done[q], fs), "cudaEventRecord"))
+				return -1;
+			dev->front_pending[q] = true;
+		}
 		break;
 	}
 	case GOP_SPAN:
 	{
 		const uint32_t warps_per_block = 4;
-		const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN);
 		if (op.fb.scale_log2)
+		{
+			// The upscaled pass follows the native tile kernel on the compute stream (which has waited for the set-up).
+			const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN);
 			k_span_bin<true><<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
+			prof_end(dev, s);
+		}
 		else
-			k_span_bin<false><<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
-		prof_end(dev, s);
+		{
+			cudaStream_t fs = dev->stream_front;
+			const uint32_t q = op.parity & 1u;
+			const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN, fs);
+			k_span_bin<false><<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, fs>>>(dev->buffers(op), op.fb);
+			prof_end(dev, s, fs);
+			if (fs != dev->stream)
+			{
+				if (!check(dev, cudaEventRecord(dev->span_done[q], fs), "cudaEventRecord"))
+					return -1;
+				dev->front_pending[q] = true;
+			}
+		}
 		dev->launches++;
 		break;
 	}
@@ -1553,6 +1621,8 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	{
 		// The first kernels of a pass (set-up, spans) never write RDRAM; this one does.
 		if (writes_scanout_range(dev, op.fb) && join_vi(dev) != 0)
+			return -1;
+		if (join_front(dev, op.parity & 1u) != 0)
 			return -1;
 		const int s = prof_begin(dev, op.variant == &kFillPassVariant ? RDPB_KERNEL_FILL_PASS : RDPB_KERNEL_TILES);
 		if (op.variant == &kFillPassVariant)
@@ -1581,6 +1651,17 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		prof_end(dev, s);
 		dev->launches++;
 		break;
+	}
+	case GOP_PASS_END:
+	{
+		// A pass that launched set-up work but nothing on the compute stream (texture loads only) still has to be
+		// ordered before whatever the compute stream does next; then the scratch set is free for the pass after next.
+		const uint32_t q = op.parity & 1u;
+		if (join_front(dev, q) != 0)
+			return -1;
+		if (dev->stream_front != dev->stream && !check(dev, cudaEventRecord(dev->scratch_free[q], dev->stream), "cudaEventRecord"))
+			return -1;
+		return 0;
 	}
 	case GOP_UPSCALE_SYNC:
 	{
@@ -1685,12 +1766,15 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 
 static int submit(rdpb_device *dev, GpuOp &op)
 {
+	op.parity = dev->cur_parity;
 	if (dev->pass_upload_pending)
 	{
 		// First kernel of the pass: everything uploaded so far for it (stream_up) must have landed.  The same event
-		// gates the reuse of the pass's host staging slot.
+		// gates the reuse of the pass's host staging slot.  A pass starts on the front stream (set-up); the compute
+		// stream inherits the dependency when it waits for the set-up.
+		cudaStream_t first = (op.kind == GOP_FRONT || (op.kind == GOP_SPAN && !op.fb.scale_log2)) ? dev->stream_front : dev->stream;
 		if (!check(dev, cudaEventRecord(dev->staging_done[dev->staging_index], dev->stream_up), "cudaEventRecord") ||
-		    !check(dev, cudaStreamWaitEvent(dev->stream, dev->staging_done[dev->staging_index], 0), "cudaStreamWaitEvent"))
+		    !check(dev, cudaStreamWaitEvent(first, dev->staging_done[dev->staging_index], 0), "cudaStreamWaitEvent"))
 			return -1;
 		dev->pass_upload_pending = false;
 	}
@@ -1763,9 +1847,18 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	need(cudaEventCreateWithFlags(&dev->vi_done, cudaEventDisableTiming), "cudaEventCreate");
 	need(cudaEventCreateWithFlags(&dev->vi_fork, cudaEventDisableTiming), "cudaEventCreate");
 	if (dev->stream_up == dev->stream)
-		dev->stream_vi = dev->stream; // RDP_B200_SINGLE_STREAM: everything in one queue
+		dev->stream_vi = dev->stream_front = dev->stream; // RDP_B200_SINGLE_STREAM: everything in one queue
 	else
+	{
 		need(cudaStreamCreateWithFlags(&dev->stream_vi, cudaStreamNonBlocking), "cudaStreamCreate vi");
+		need(cudaStreamCreateWithFlags(&dev->stream_front, cudaStreamNonBlocking), "cudaStreamCreate front");
+	}
+	for (int q = 0; q < 2; q++)
+	{
+		need(cudaEventCreateWithFlags(&dev->span_done[q], cudaEventDisableTiming), "cudaEventCreate");
+		need(cudaEventCreateWithFlags(&dev->scratch_free[q], cudaEventDisableTiming), "cudaEventCreate");
+	}
+	need(cudaEventCreateWithFlags(&dev->host_write_done, cudaEventDisableTiming), "cudaEventCreate");
 	for (auto &e : dev->readback_done)
 		need(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
 	need(cudaMalloc(&dev->rdram, rdram_size), "cudaMalloc rdram");
@@ -1773,7 +1866,7 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	need(cudaHostAlloc(&dev->tmem_host, kTmemBytes, cudaHostAllocMapped), "cudaHostAlloc tmem");
 	if (ok)
 		need(cudaHostGetDevicePointer(&dev->tmem_dev, dev->tmem_host, 0), "cudaHostGetDevicePointer tmem");
-	need(cudaMalloc(&dev->tmem_instances, size_t(kTmemBytes) * (kMaxUploadsPerPass + 1)), "cudaMalloc tmem instances");
+	need(cudaMalloc(&dev->tmem_instances, 2 * rdpb_device::kTmemSetBytes), "cudaMalloc tmem instances");
 	need(cudaMalloc(&dev->blend_lut, 0x8000), "cudaMalloc blend lut");
 	need(cudaMalloc(&dev->gamma_lut, 256 + 256 * 64), "cudaMalloc gamma lut");
 	need(cudaMalloc(&dev->d_counters, kCounterWords * sizeof(unsigned long long)), "cudaMalloc counters");
@@ -1785,14 +1878,14 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		                                       size_t(kMaxUploadsPerPass) * sizeof(TmemUpload) + 1024),
 		     "cudaMalloc pass inputs");
 	}
-	need(cudaMalloc(&dev->d_prims, size_t(kMaxPrimsPerPass) * sizeof(PrimSetup)), "cudaMalloc prims");
-	need(cudaMalloc(&dev->d_spans, size_t(kMaxSpansPerPass) * sizeof(Span)), "cudaMalloc spans");
-	const size_t fine_bytes = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 32) * 4;
-	const size_t coarse_bytes = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 1024) * 4;
+	need(cudaMalloc(&dev->d_prims, 2 * size_t(kMaxPrimsPerPass) * sizeof(PrimSetup)), "cudaMalloc prims");
+	need(cudaMalloc(&dev->d_spans, 2 * size_t(kMaxSpansPerPass) * sizeof(Span)), "cudaMalloc spans");
+	const size_t fine_bytes = 2 * rdpb_device::kFineWords * 4;
+	const size_t coarse_bytes = 2 * rdpb_device::kCoarseWords * 4;
 	need(cudaMalloc(&dev->d_fine, fine_bytes), "cudaMalloc fine masks");
 	need(cudaMalloc(&dev->d_coarse, coarse_bytes), "cudaMalloc coarse masks");
-	need(cudaMalloc(&dev->d_jobs, size_t(kMaxJobsPerPass) * 4), "cudaMalloc span jobs");
-	need(cudaMalloc(&dev->d_job_counter, 256), "cudaMalloc job counter");
+	need(cudaMalloc(&dev->d_jobs, 2 * size_t(kMaxJobsPerPass) * 4), "cudaMalloc span jobs");
+	need(cudaMalloc(&dev->d_job_counter, 2 * 256), "cudaMalloc job counter");
 	need(cudaMalloc(&dev->vi_filtered, size_t(kViStageWidth) * kViStageHeight * 2 * 4), "cudaMalloc vi filtered");
 	const size_t max_out = size_t(640) * 576 * 4;
 	need(cudaMalloc(&dev->vi_out[0], max_out), "cudaMalloc vi out");
@@ -1814,11 +1907,11 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		need(cudaMemsetAsync(dev->hidden, 0, hidden_size, dev->stream), "memset hidden");
 		need(cudaMemsetAsync(dev->d_fine, 0, fine_bytes, dev->stream), "memset fine");
 		need(cudaMemsetAsync(dev->d_coarse, 0, coarse_bytes, dev->stream), "memset coarse");
-		need(cudaMemsetAsync(dev->d_job_counter, 0, 256, dev->stream), "memset job counter");
+		need(cudaMemsetAsync(dev->d_job_counter, 0, 2 * 256, dev->stream), "memset job counter");
 		need(cudaMemsetAsync(dev->d_counters, 0, kCounterWords * sizeof(unsigned long long), dev->stream), "memset counters");
 		need(cudaMemsetAsync(dev->vi_out[0], 0, max_out, dev->stream), "memset vi out");
 		need(cudaMemsetAsync(dev->vi_out[1], 0, max_out, dev->stream), "memset vi out");
-		need(cudaMemsetAsync(dev->tmem_instances, 0, size_t(kTmemBytes) * (kMaxUploadsPerPass + 1), dev->stream), "memset tmem instances");
+		need(cudaMemsetAsync(dev->tmem_instances, 0, 2 * rdpb_device::kTmemSetBytes, dev->stream), "memset tmem instances");
 		memset(dev->tmem_host, 0, kTmemBytes);
 
 		static uint8_t lut[0x8000]; // large enough for both tables (32768 >= 256 + 256 * 64)
@@ -1908,6 +2001,17 @@ void rdpb_device_destroy(rdpb_device *dev)
 		cudaEventDestroy(dev->vi_fork);
 	if (dev->stream_vi && dev->stream_vi != dev->stream)
 		cudaStreamDestroy(dev->stream_vi);
+	if (dev->stream_front && dev->stream_front != dev->stream)
+		cudaStreamDestroy(dev->stream_front);
+	for (int q = 0; q < 2; q++)
+	{
+		if (dev->span_done[q])
+			cudaEventDestroy(dev->span_done[q]);
+		if (dev->scratch_free[q])
+			cudaEventDestroy(dev->scratch_free[q]);
+	}
+	if (dev->host_write_done)
+		cudaEventDestroy(dev->host_write_done);
 	for (auto &e : dev->readback_done)
 		if (e)
 			cudaEventDestroy(e);
@@ -1949,6 +2053,12 @@ static int copy_common(rdpb_device *dev, void *dst, const void *src, size_t size
 	if (join_vi(dev) != 0)
 		return -1;
 	CK(cudaMemcpyAsync(dst, src, size, kind, dev->stream));
+	if (kind == cudaMemcpyHostToDevice && dev->stream_front != dev->stream)
+	{
+		// Texture loads (front stream) read RDRAM: they have to see this copy.
+		CK(cudaEventRecord(dev->host_write_done, dev->stream));
+		dev->host_write_pending = true;
+	}
 	if (sync)
 		CK(cudaStreamSynchronize(dev->stream));
 	return 0;
@@ -1985,6 +2095,7 @@ void *rdpb_hidden_device_ptr(rdpb_device *dev) { return dev->hidden; }
 int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
 {
 	use_device(dev);
+	dev->cur_parity ^= 1u;
 	dev->staging_index = (dev->staging_index + 1) % kStagingSlots;
 	const unsigned i = dev->staging_index;
 	if (dev->staging_in_flight[i])
@@ -2074,13 +2185,26 @@ int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_w
 int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims)
 {
 	use_device(dev);
-	if (!update_tmem && !num_prims)
+	// The host keeps one "snapshot 0 is current" flag; there are two snapshot sets here.  Refresh this pass's set when
+	// asked to, or when the pass samples TMEM and the set was last refreshed in an earlier TMEM epoch.
+	const uint32_t q = dev->cur_parity & 1u;
+	bool refresh = (update_tmem & 1) != 0;
+	if (refresh)
+		dev->tmem_epoch++; // asked without uploads: the host changed live TMEM; with uploads: harmless
+	else if ((update_tmem & 4) && dev->snapshot_epoch[q] != dev->tmem_epoch)
+		refresh = true;
+	if (refresh)
+		dev->snapshot_epoch[q] = dev->tmem_epoch;
+	if (num_uploads)
+		dev->tmem_epoch++; // live TMEM after this pass is no longer what any snapshot 0 holds
+	if (!refresh && !num_prims)
 		return 0;
 	GpuOp op = {};
 	op.kind = GOP_FRONT;
 	op.count = num_prims;
 	op.count2 = num_uploads;
-	op.flag = update_tmem ? 1u : 0u;
+	op.flag = refresh ? 1u : 0u;
+	op.hazard = (update_tmem & 2) ? 1u : 0u;
 	return submit(dev, op);
 }
 
@@ -2126,6 +2250,13 @@ int rdpb_pass_end(rdpb_device *dev)
 		CK(cudaEventRecord(dev->staging_done[i], dev->stream_up));
 		dev->pass_upload_pending = false;
 	}
+	GpuOp op = {};
+	op.kind = GOP_PASS_END;
+	op.parity = dev->cur_parity;
+	if (dev->recording)
+		dev->log.push_back(op);
+	if (issue(dev, op) != 0)
+		return -1;
 	CK(cudaEventRecord(dev->kernels_done[i], dev->stream));
 	dev->kernels_in_flight[i] = true;
 	return 0;
@@ -2338,6 +2469,7 @@ int rdpb_sync(rdpb_device *dev)
 {
 	use_device(dev);
 	CK(cudaStreamSynchronize(dev->stream_up));
+	CK(cudaStreamSynchronize(dev->stream_front));
 	CK(cudaStreamSynchronize(dev->stream));
 	CK(cudaStreamSynchronize(dev->stream_vi));
 	CK(cudaStreamSynchronize(dev->stream_down));

@@ -439,7 +439,8 @@ void Renderer::flush_queues()
 	const bool update_tmem = num_uploads != 0 || (need_render && pass_reads_tmem && !tmem_snapshot_valid);
 	if (update_tmem)
 		tmem_snapshot_valid = num_uploads == 0;
-	rdpb_launch_front(device, update_tmem ? 1 : 0, num_uploads, need_render ? num_prims : 0);
+	rdpb_launch_front(device, (update_tmem ? 1 : 0) | (uploads_may_read_previous_pass ? 2 : 0) | ((need_render && pass_reads_tmem) ? 4 : 0),
+	                  num_uploads, need_render ? num_prims : 0);
 
 	if (need_render)
 	{
@@ -483,11 +484,20 @@ void Renderer::flush_queues()
 
 		const uint32_t pixels = info.width * info.height;
 		const uint32_t bpp = fb.fmt == FBFormat::RGBA8888 ? 4 : ((fb.fmt == FBFormat::RGBA5551 || fb.fmt == FBFormat::IA88) ? 2 : 1);
+		// What this pass renders to: the next pass's texture loads are checked against it (load_tile).
+		rendered_ranges[0][0] = fb.addr;
+		rendered_ranges[0][1] = fb.addr + pixels * bpp;
+		rendered_ranges[1][0] = fb.depth_addr;
+		rendered_ranges[1][1] = fb.depth_addr + pixels * 2;
+		rendered_ranges_valid = true;
 		note_gpu_write(fb.addr, pixels * bpp);
 		if (fb.depth_write_pending)
 			note_gpu_write(fb.depth_addr, pixels * 2);
 	}
 
+	if (!need_render)
+		rendered_ranges_valid = false; // nothing rendered: nothing for the next pass's loads to collide with
+	uploads_may_read_previous_pass = false;
 	rdpb_pass_end(device);
 	pass_counter++;
 	flush_ns += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - flush_t0).count());
@@ -538,6 +548,20 @@ void Renderer::load_tile(uint32_t tile, const LoadTileInfo &info)
 
 	if (tmem_upload_needs_flush(info.tex_addr))
 		flush_queues();
+	// The set-up of this pass may run before the previous pass's tile kernel has finished (CUDA backend): say so if
+	// this load could read what that pass renders.  Generous bound on the bytes a load can touch: every row up to thi
+	// at the image's pitch, or 16 KiB for block / TLUT loads, plus slack.
+	if (rendered_ranges_valid && !uploads_may_read_previous_pass)
+	{
+		const uint64_t row_bytes = (uint64_t(info.tex_width) << unsigned(info.size)) >> 1;
+		const uint64_t lo = info.tex_addr & uint32_t(rdram_size - 1);
+		const uint64_t hi = lo + (uint64_t(info.thi >> 2) + 2) * row_bytes + 16384 + 4096;
+		if (hi > rdram_size)
+			uploads_may_read_previous_pass = true;
+		for (int r = 0; r < 2; r++)
+			if (lo < rendered_ranges[r][1] && rendered_ranges[r][0] < hi)
+				uploads_may_read_previous_pass = true;
+	}
 
 	// No-op loads.
 	if (info.mode != UploadMode::Block)

@@ -156,6 +156,11 @@ private:
 	uint32_t base_primitive_index = 0;
 	uint64_t pass_counter = 0;
 	uint64_t upscaled_pass_counter = 0;
+	// Byte ranges [lo, hi) the previous pass renders to (colour, depth), and whether a texture load of the pass being
+	// recorded may read from them (rdpb_launch_front's ordering hint).
+	uint64_t rendered_ranges[2][2] = {};
+	bool rendered_ranges_valid = false;
+	bool uploads_may_read_previous_pass = false;
 	uint32_t upscale_log2 = 0;
 	uint64_t flush_ns = 0; // time spent submitting passes (written by the thread that drives the renderer)
 	bool tmem_snapshot_valid = false;

@@ -172,6 +172,7 @@ int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_w
 
 int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims)
 {
+	update_tmem &= 1; // bit 1 is a stream-ordering hint for the CUDA backend
 	if (g_null_compute)
 		return 0;
 	PassBuffers b = dev->buffers();
