@@ -196,6 +196,21 @@ class CommandProcessor:
     def set_vi_register(self, reg, value: int):
         self.lib.rdp_b200_set_vi_register(self._h, VI_REG[reg] if isinstance(reg, str) else int(reg), value & 0xffffffff)
 
+    # Raster effects (ref rdp_device.hpp:186-196): HStart / XScale latched per VI line between begin and end.
+    PER_SCANLINE_HSTART, PER_SCANLINE_XSCALE = 1, 2
+
+    def begin_vi_register_per_scanline(self, flags: int = 3):
+        self.lib.rdp_b200_begin_vi_register_per_scanline(self._h, flags)
+
+    def set_vi_register_for_scanline(self, reg_bit: int, value: int):
+        self.lib.rdp_b200_set_vi_register_for_scanline(self._h, reg_bit, value & 0xffffffff)
+
+    def latch_vi_register_for_scanline(self, vi_line: int):
+        self.lib.rdp_b200_latch_vi_register_for_scanline(self._h, vi_line)
+
+    def end_vi_register_per_scanline(self):
+        self.lib.rdp_b200_end_vi_register_per_scanline(self._h)
+
     def set_quirks(self, native_resolution_tex_rect: bool = True, native_texture_lod: bool = False):
         self.lib.rdp_b200_set_quirks(self._h, int(native_resolution_tex_rect), int(native_texture_lod))
 
