@@ -497,6 +497,7 @@ struct alignas(16) DeferWarp
 	uint32_t pixmask[32], base[32], prim[32], span_base[32], ids[32], lines[32], dzw[32]; // per list entry of the chunk
 	uint16_t list[kTileListCapacity];
 };
+static_assert(kDeferCapacity >= 32u * kGatherWords, "the next tile's mask words are staged in DeferWarp::desc (NextTilePrefetch::stage_masks)");
 
 // Per-warp shared memory of the tile kernel: just the primitive list for the in-order walker.
 template <class S, bool DEFERRED>
