@@ -142,6 +142,11 @@ uint64_t rdp_b200_upscaled_pass_count(rdp_b200_processor *p);
 /* Idles, then copies the upscaled domain to the host: S*S images of get_rdram_size() bytes into rdram_dst and S*S
  * images of get_rdram_size() / 2 bytes into hidden_dst (either may be NULL).  Returns 0, -1 when upscaling is off. */
 int rdp_b200_read_upscaled_rdram(rdp_b200_processor *p, void *rdram_dst, void *hidden_dst);
+/* RDP_B200_FLAG_SUPER_SAMPLED_READ_BACK (with an upscaling flag; refused without one, ref rdp_renderer.cpp:60-61):
+ * passes are rendered in the upscaled domain only, and every native pixel the pass stored to takes the rounded average
+ * of its S*S samples (16 / 32-bit colour; the first sample for 8-bit colour and for depth) in native RDRAM, hidden
+ * RDRAM left alone (ref rdp_renderer.cpp:2296-2334, update_upscaled_domain_resolve.comp).
+ * RDP_B200_FLAG_SUPER_SAMPLED_DITHER adds the reference's 4x4 ordered dither when averaging 5/5/5/1 colours. */
 
 /* ---- RDPDUMP2 command-stream dumps (replaces the reference's rdp_dump.cpp:29-185 DumpPlayer and
  * parallel-rdp/rdp_dump_write.cpp:34-151 RDPDumpWriter; same file format, files are interchangeable) ------------- */

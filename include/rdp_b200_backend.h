@@ -107,7 +107,12 @@ void *rdpb_stream(rdpb_device *dev);                 /* cudaStream_t for interop
  * rdpb_launch_upscale_sync(PRE / POST), then again through rdpb_launch_span_bin / rdpb_launch_tiles with an FbInfo whose
  * scale_log2 is set and whose width / height / tile counts are in upscaled pixels. */
 int rdpb_upscaling_init(rdpb_device *dev, uint32_t scale_log2);
-enum { RDPB_UPSCALE_SYNC_PRE = 0, RDPB_UPSCALE_SYNC_POST = 1 };
+/* Super-sampled read-back (replaces update_upscaled_domain_resolve.comp + clear_super_sampled_write_mask.comp,
+ * rdp_renderer.cpp:2037-2060, 2296-2334): the pass is submitted upscaled only, with FbInfo::write_mask set, as
+ * PRE, span_bin + tiles (upscaled), RESOLVE; RESOLVE averages the samples of every native pixel the pass stored to
+ * into native RDRAM and clears the write mask for the next pass.  RESOLVE_DITHER adds the ordered dither for 16-bit
+ * colour images. */
+enum { RDPB_UPSCALE_SYNC_PRE = 0, RDPB_UPSCALE_SYNC_POST = 1, RDPB_UPSCALE_SYNC_RESOLVE = 2, RDPB_UPSCALE_SYNC_RESOLVE_DITHER = 3 };
 int rdpb_launch_upscale_sync(rdpb_device *dev, const void *native_fb_info, int stage);
 /* Blocking read-back of the whole upscaled domain: S*S images of rdram_size bytes, S*S images of rdram_size / 2 bytes. */
 int rdpb_upscaled_read(rdpb_device *dev, void *rdram_dst, void *hidden_dst);

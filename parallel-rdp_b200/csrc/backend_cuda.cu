@@ -10,6 +10,7 @@
 //                   blend) or in-order walker, U = internal upscaling         (rasterizer.comp + depth_blend.comp)
 //   k_fill_pass     small fill-only passes (clears), per pixel, no tile machinery
 //   k_upscale_sync  PRE / POST synchronisation of the upscaled domain      (update_upscaled_domain_pre/post.comp)
+//   k_upscale_resolve  super-sampled read-back: samples averaged into RDRAM (update_upscaled_domain_resolve.comp)
 //   k_vi_filter     VI AA / dither-reconstruction / divot from a shared-memory copy of the framebuffer neighbourhood
 //                   (extract_vram.comp + vi_fetch.frag + vi_divot.frag)
 //   k_vi_scale      VI scale, gamma, field merge (vi_scale.frag + vi_blend_fields.frag); k_vi_downscale halves the image
@@ -961,6 +962,13 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 		shaded_total += walk.shaded;
 
 		pass_pixel_end(fb, view, px, walk.x, walk.y, sl);
+		if (UPSCALED)
+		{
+			// Super-sampled read-back: note which native pixels were stored to.
+			uint32_t *word = nullptr;
+			if (const uint32_t bits = pass_pixel_write_mask(b, fb, px, walk.x, walk.y, sl, word))
+				atomicOr(word, bits);
+		}
 	}
 
 	// One atomic per warp keeps the metrics essentially free.
@@ -1114,6 +1122,13 @@ __global__ void __launch_bounds__(256) k_fill_pass(PassBuffers b, FbInfo fb)
 __global__ void __launch_bounds__(256) k_upscale_sync(UpscaleSync u, int post)
 {
 	upscale_sync_pixel(u, blockIdx.x * blockDim.x + threadIdx.x, post != 0);
+}
+
+// Super-sampled read-back: resolve of the upscaled domain into native RDRAM (rdp_pass.cuh, upscale_resolve_pixel),
+// one thread per native pixel in 32x8 blocks.
+__global__ void __launch_bounds__(256) k_upscale_resolve(UpscaleSync u)
+{
+	upscale_resolve_pixel(u, blockIdx.x * 32u + threadIdx.x, blockIdx.y * 8u + threadIdx.y);
 }
 
 // VI filter: a 32x8 block first decodes its framebuffer neighbourhood (38 x 10 pixels: the AA / dither filters
@@ -1596,7 +1611,10 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		const uint32_t warps_per_block = 4;
 		if (op.fb.scale_log2)
 		{
-			// The upscaled pass follows the native tile kernel on the compute stream (which has waited for the set-up).
+			// The upscaled pass follows the native tile kernel on the compute stream (which has waited for the set-up);
+			// with super-sampled read-back there is no native tile kernel, so wait here.
+			if (join_front(dev, op.parity & 1u) != 0)
+				return -1;
 			const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN);
 			k_span_bin<true><<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
 			prof_end(dev, s);
@@ -1681,7 +1699,18 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		u.depth_index = op.fb.depth_addr >> 1;
 		u.num_pixels = op.fb.width * op.fb.height;
 		u.alias = op.fb.color_addr == op.fb.depth_addr;
-		k_upscale_sync<<<(u.num_pixels + 255u) / 256u, 256, 0, dev->stream>>>(u, int(op.count));
+		u.width = op.fb.width;
+		u.dither = op.count == RDPB_UPSCALE_SYNC_RESOLVE_DITHER;
+		if (op.count == RDPB_UPSCALE_SYNC_RESOLVE || op.count == RDPB_UPSCALE_SYNC_RESOLVE_DITHER)
+		{
+			k_upscale_resolve<<<dim3((op.fb.width + 31u) / 32u, (op.fb.height + 7u) / 8u), dim3(32, 8), 0, dev->stream>>>(u);
+			// The next pass starts from a clean write mask (ref clear_super_sampled_write_mask.comp).
+			const size_t words = size_t((op.fb.width + 3u) / 4u) * ((op.fb.height + 3u) / 4u);
+			if (!check(dev, cudaMemsetAsync(dev->up_rdram + size_t(u.num_slices) * u.rdram_size, 0, words * 4u, dev->stream), "cudaMemsetAsync"))
+				return -1;
+		}
+		else
+			k_upscale_sync<<<(u.num_pixels + 255u) / 256u, 256, 0, dev->stream>>>(u, int(op.count));
 		dev->launches++;
 		break;
 	}
@@ -2272,13 +2301,13 @@ int rdpb_upscaling_init(rdpb_device *dev, uint32_t scale_log2)
 	const size_t hidden_stride = dev->rdram_size >> 1;
 	const size_t fine_bytes = (size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 32) * 4) << (2 * scale_log2);
 	const size_t coarse_bytes = (size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 1024) * 4) << (2 * scale_log2);
-	CK(cudaMalloc(&dev->up_rdram, slices * dev->rdram_size));
+	CK(cudaMalloc(&dev->up_rdram, slices * dev->rdram_size + size_t(kWriteMaskWords) * 4)); // + the super-sampled write mask
 	CK(cudaMalloc(&dev->up_hidden, slices * hidden_stride));
 	CK(cudaMalloc(&dev->up_reference, dev->rdram_size));
 	CK(cudaMalloc(&dev->up_spans, (size_t(kMaxSpansPerPass) << scale_log2) * sizeof(Span)));
 	CK(cudaMalloc(&dev->up_fine, fine_bytes));
 	CK(cudaMalloc(&dev->up_coarse, coarse_bytes));
-	CK(cudaMemsetAsync(dev->up_rdram, 0, slices * dev->rdram_size, dev->stream));
+	CK(cudaMemsetAsync(dev->up_rdram, 0, slices * dev->rdram_size + size_t(kWriteMaskWords) * 4, dev->stream));
 	CK(cudaMemsetAsync(dev->up_hidden, 3, slices * hidden_stride, dev->stream)); // ref rdp_renderer.cpp:593
 	CK(cudaMemsetAsync(dev->up_reference, 0, dev->rdram_size, dev->stream));
 	CK(cudaMemsetAsync(dev->up_fine, 0, fine_bytes, dev->stream));

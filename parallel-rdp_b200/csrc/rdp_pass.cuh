@@ -142,6 +142,20 @@ RDP_HD void pass_pixel_end(const FbInfo &fb, const FbView &view, PixelState &px,
 	store_depth(view, px, (fb.depth_addr >> 1) + pix);
 }
 
+// Super-sampled read-back: which native pixel this upscaled pixel stored to.  Returns the bits to OR into *word
+// (bit 0 colour, bit 1 depth, at the native pixel's place in its 4x4 block; 0: nothing stored).  The mask words sit
+// behind the last RDRAM slice (ref memory_interfacing.h:305-337, finish_tile :340-362).
+RDP_HD uint32_t pass_pixel_write_mask(const PassBuffers &b, const FbInfo &fb, const PixelState &px, int x, int y, int sl, uint32_t *&word)
+{
+	if (!fb.write_mask || x >= int(fb.width) || y >= int(fb.height))
+		return 0u;
+	const uint32_t bits = (px.color_dirty ? 1u : 0u) | (px.depth_dirty ? 2u : 0u);
+	const uint32_t nx = uint32_t(x) >> sl, ny = uint32_t(y) >> sl;
+	const uint32_t blocks_x = ((fb.width >> sl) + 3u) >> 2;
+	word = reinterpret_cast<uint32_t *>(b.rdram + (size_t(fb.rdram_size) << (2 * sl))) + (ny >> 2) * blocks_x + (nx >> 2);
+	return bits << (2u * ((nx & 3u) + 4u * (ny & 3u)));
+}
+
 // Returns the number of primitives that shaded this pixel.
 template <class S>
 RDP_HD uint32_t pass_pixel_walk(const PassBuffers &b, const FbInfo &fb, const FbView &view, PixelState &px, int x, int y,
@@ -301,6 +315,8 @@ struct UpscaleSync
 	uint32_t num_pixels;
 	uint32_t size_log2;  // colour pixel size: 0, 1, 2
 	uint32_t alias;      // colour and depth share an address
+	uint32_t width;      // native framebuffer width (resolve only)
+	uint32_t dither;     // resolve only: ordered dither when averaging 5/5/5/1 colours
 };
 
 RDP_HD void upscale_sync_word(const UpscaleSync &u, uint32_t index, uint32_t size_log2, bool post)
@@ -350,6 +366,89 @@ RDP_HD void upscale_sync_pixel(const UpscaleSync &u, uint32_t i, bool post)
 	upscale_sync_word(u, u.fb_index + i, u.size_log2, post);
 	if (!u.alias)
 		upscale_sync_word(u, u.depth_index + i, 1u, post);
+}
+
+// Super-sampled read-back (ref shaders/update_upscaled_domain_resolve.comp:94-277, rdp_renderer.cpp:2325-2334): after
+// an upscaled-only pass, every native pixel one of whose S*S samples was stored to takes the rounded average of its
+// samples' colour channels (16 / 32-bit images; an 8-bit image takes the first sample, as does depth, which cannot be
+// filtered), in native RDRAM and in the shadow.  Hidden RDRAM is not resolved.  One thread per native pixel.
+RDP_HD void upscale_resolve_pixel(const UpscaleSync &u, uint32_t x, uint32_t y)
+{
+	if (x >= u.width)
+		return;
+	const uint32_t i = y * u.width + x;
+	if (i >= u.num_pixels)
+		return;
+	const uint32_t *mask = reinterpret_cast<const uint32_t *>(u.up_rdram + size_t(u.num_slices) * u.rdram_size);
+	const uint32_t bits = mask[(y >> 2) * ((u.width + 3u) >> 2) + (x >> 2)] >> (2u * ((x & 3u) + 4u * (y & 3u)));
+	const uint32_t n = u.num_slices;
+	if (bits & 1u)
+	{
+		if (u.size_log2 == 0u)
+		{
+			const uint32_t at = ((u.fb_index + i) & (u.rdram_size - 1u)) ^ 3u;
+			const uint8_t v = u.up_rdram[at]; // the reference sums the first sample S*S times
+			u.rdram[at] = v;
+			u.reference[at] = v;
+		}
+		else if (u.size_log2 == 1u)
+		{
+			const uint32_t at = ((u.fb_index + i) & ((u.rdram_size >> 1) - 1u)) ^ 1u;
+			uint32_t r = 0, g = 0, b = 0, a = 0;
+			for (uint32_t s = 0; s < n; s++)
+			{
+				const uint32_t w = reinterpret_cast<const uint16_t *>(u.up_rdram + size_t(s) * u.rdram_size)[at];
+				r += (w >> 11) & 31u;
+				g += (w >> 6) & 31u;
+				b += (w >> 1) & 31u;
+				a += w & 1u;
+			}
+			if (u.dither)
+			{
+				// 4x4 ordered pattern, 3 fractional bits below a 5-bit channel.
+				// (rows 0 4 1 5 / 4 0 5 1 / 3 7 2 6 / 7 3 6 2, one nibble per entry)
+				const uint32_t d = uint32_t((0x2637627315045140ull >> (4u * ((y & 3u) * 4u + (x & 3u)))) & 15u) * n;
+				r = (8u * r + d) / (8u * n);
+				g = (8u * g + d) / (8u * n);
+				b = (8u * b + d) / (8u * n);
+				a = (8u * a + d) / (8u * n);
+			}
+			else
+			{
+				r = (r + (n >> 1)) / n;
+				g = (g + (n >> 1)) / n;
+				b = (b + (n >> 1)) / n;
+				a = (a + (n >> 1)) / n;
+			}
+			const uint16_t v = uint16_t((r << 11) | (g << 6) | (b << 1) | a);
+			reinterpret_cast<uint16_t *>(u.rdram)[at] = v;
+			reinterpret_cast<uint16_t *>(u.reference)[at] = v;
+		}
+		else
+		{
+			const uint32_t at = (u.fb_index + i) & ((u.rdram_size >> 2) - 1u);
+			uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+			for (uint32_t s = 0; s < n; s++)
+			{
+				const uint32_t w = reinterpret_cast<const uint32_t *>(u.up_rdram + size_t(s) * u.rdram_size)[at];
+				c3 += w >> 24;
+				c2 += (w >> 16) & 255u;
+				c1 += (w >> 8) & 255u;
+				c0 += w & 255u;
+			}
+			const uint32_t h = n >> 1;
+			const uint32_t v = (((c3 + h) / n) << 24) | (((c2 + h) / n) << 16) | (((c1 + h) / n) << 8) | ((c0 + h) / n);
+			reinterpret_cast<uint32_t *>(u.rdram)[at] = v;
+			reinterpret_cast<uint32_t *>(u.reference)[at] = v;
+		}
+	}
+	if (!u.alias && (bits & 2u))
+	{
+		const uint32_t at = ((u.depth_index + i) & ((u.rdram_size >> 1) - 1u)) ^ 1u;
+		const uint16_t v = reinterpret_cast<const uint16_t *>(u.up_rdram)[at];
+		reinterpret_cast<uint16_t *>(u.rdram)[at] = v;
+		reinterpret_cast<uint16_t *>(u.reference)[at] = v;
+	}
 }
 
 // Zero the mask words of one tile after its pixels are done, so the next pass starts from clean masks.

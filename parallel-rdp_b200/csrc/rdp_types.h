@@ -289,7 +289,10 @@ struct FbInfo
 	// upscaled pixels, the pass reads and writes the upscaled RDRAM domain (S*S slices) and its own span / mask buffers;
 	// addresses, primitive records and scanline ranges stay native (ref rdp_renderer.cpp:1865-1868, 2138-2141).
 	uint32_t scale_log2;
-	uint32_t pad[2];
+	// Super-sampled read-back: the upscaled pass also records which native pixels it stored to (2 bits per native
+	// pixel, 4x4 pixels per word, behind the last RDRAM slice; ref memory_interfacing.h:305-337).
+	uint32_t write_mask;
+	uint32_t pad;
 };
 
 // Which passes are worth rendering upscaled: the reference's heuristic (rdp_renderer.cpp:3000-3012: only 16/32-bit
@@ -299,6 +302,14 @@ RDP_HD bool pass_wants_upscaling(const FbInfo &fb, uint32_t scale_log2)
 {
 	return (fb.fmt == FB_RGBA5551 || fb.fmt == FB_RGBA8888) && fb.width >= 256u && (fb.width << scale_log2) < 8192u;
 }
+// With super-sampled read-back every pass is rendered upscaled only (rdp_renderer.cpp:2955, 2990-2991); what remains
+// is our own range limit.
+RDP_HD bool pass_can_super_sample(const FbInfo &fb, uint32_t scale_log2)
+{
+	return (fb.width << scale_log2) < 8192u;
+}
+// Words of the super-sampled write mask (2 bits per native pixel of the largest framebuffer, rdp_renderer.cpp:581-582).
+enum : uint32_t { kWriteMaskWords = 2u * 1024u * 1024u / 32u };
 
 // A span job is one (primitive, 32-scanline chunk): one warp of the span/bin kernel.  Chunks start at the
 // primitive's first tile row so that every 4-lane group of a warp owns exactly one tile row.

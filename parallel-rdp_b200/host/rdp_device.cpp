@@ -26,9 +26,6 @@ CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, 
 		return;
 	}
 
-	if (flags & (COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_READ_BACK_BIT | COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_DITHER_BIT))
-		fprintf(stderr, "[rdp-b200] Super-sampled read-back is not implemented; native RDRAM keeps the native-resolution result.\n");
-
 	device = rdpb_device_create(config.cuda_device, uint32_t(rdram_size), uint32_t(hidden_rdram_size));
 	if (!device)
 	{
@@ -63,6 +60,13 @@ CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, 
 		                    (flags & COMMAND_PROCESSOR_FLAG_UPSCALING_2X_BIT) ? 1u : 0u;
 		if (renderer.set_upscaling(up))
 			vi.set_upscaling_log2(renderer.get_upscaling_log2());
+		// Super-sampled read-back (ref rdp_device.cpp:202-205, rdp_renderer.cpp:60-61: refused without upscaling).
+		if (!renderer.set_super_sampled_readback((flags & COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_READ_BACK_BIT) != 0,
+		                                         (flags & COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_DITHER_BIT) != 0))
+		{
+			fprintf(stderr, "[rdp-b200] Super-sampled read-back needs internal upscaling (2x / 4x / 8x).\n");
+			is_supported = false;
+		}
 		apply_quirks(); // the defaults: texture rectangles at native resolution, LOD at the rendered resolution
 	}
 	vi.init(device, rdram_size);

@@ -37,6 +37,16 @@ bool Renderer::set_upscaling(uint32_t log2)
 	return true;
 }
 
+bool Renderer::set_super_sampled_readback(bool enable, bool dither)
+{
+	// ref rdp_renderer.cpp:60-61: super-sampling a 1x render is refused.
+	if (enable && upscale_log2 == 0)
+		return false;
+	super_sampled_readback = enable;
+	super_sampled_dither = enable && dither;
+	return true;
+}
+
 bool Renderer::init(rdpb_device *device_, size_t rdram_size_)
 {
 	device = device_;
@@ -463,22 +473,32 @@ void Renderer::flush_queues()
 		// always -- RDRAM stays bit-exact -- and then once more into the upscaled domain.  Around the native tile launch
 		// the upscaled domain picks up whatever changed in native RDRAM behind its back (PRE) and the shadow copy
 		// takes the pass's own output (POST).
-		const bool upscale = upscale_log2 != 0 && pass_wants_upscaling(info, upscale_log2);
-		rdpb_launch_span_bin(device, &info);
+		// With super-sampled read-back (ref rdp_renderer.cpp:2296-2334, 2955-2980) there is no native pass at all: PRE,
+		// the upscaled pass recording which native pixels it stored to, then the resolve that averages those pixels'
+		// samples into native RDRAM (and the shadow).
+		const bool ssaa = super_sampled_readback && upscale_log2 != 0 && pass_can_super_sample(info, upscale_log2);
+		const bool upscale = ssaa || (upscale_log2 != 0 && pass_wants_upscaling(info, upscale_log2));
+		if (!ssaa)
+			rdpb_launch_span_bin(device, &info);
 		if (upscale)
 			rdpb_launch_upscale_sync(device, &info, RDPB_UPSCALE_SYNC_PRE);
-		rdpb_launch_tiles(device, &info, &summary);
+		if (!ssaa)
+			rdpb_launch_tiles(device, &info, &summary);
 		if (upscale)
 		{
-			rdpb_launch_upscale_sync(device, &info, RDPB_UPSCALE_SYNC_POST);
+			if (!ssaa)
+				rdpb_launch_upscale_sync(device, &info, RDPB_UPSCALE_SYNC_POST);
 			FbInfo up = info;
 			up.scale_log2 = upscale_log2;
+			up.write_mask = ssaa ? 1u : 0u;
 			up.width = info.width << upscale_log2;
 			up.height = info.height << upscale_log2;
 			up.tiles_x = (up.width + kTileW - 1) / kTileW;
 			up.tiles_y = (up.height + kTileH - 1) / kTileH;
 			rdpb_launch_span_bin(device, &up);
 			rdpb_launch_tiles(device, &up, &summary);
+			if (ssaa)
+				rdpb_launch_upscale_sync(device, &info, super_sampled_dither ? RDPB_UPSCALE_SYNC_RESOLVE_DITHER : RDPB_UPSCALE_SYNC_RESOLVE);
 			upscaled_pass_counter++;
 		}
 

@@ -83,6 +83,9 @@ public:
 	bool init(rdpb_device *device, size_t rdram_size);
 	// Internal upscaling factor 1 << log2 (0: off).  Allocates the upscaled domain in the backend.
 	bool set_upscaling(uint32_t log2);
+	// Super-sampled read-back (ref RendererOptions, rdp_renderer.hpp:71-72): passes are rendered upscaled only and
+	// native RDRAM takes the average of each pixel's samples.  Needs upscaling; returns false otherwise.
+	bool set_super_sampled_readback(bool enable, bool dither);
 	// QuirkFlags (csrc/rdp_types.h); part of every state snapshot taken from now on.
 	void set_quirks(uint32_t quirk_flags);
 	uint32_t get_upscaling_log2() const { return upscale_log2; }
@@ -162,6 +165,7 @@ private:
 	bool rendered_ranges_valid = false;
 	bool uploads_may_read_previous_pass = false;
 	uint32_t upscale_log2 = 0;
+	bool super_sampled_readback = false, super_sampled_dither = false;
 	uint64_t flush_ns = 0; // time spent submitting passes (written by the thread that drives the renderer)
 	bool tmem_snapshot_valid = false;
 

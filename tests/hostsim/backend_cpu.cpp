@@ -256,6 +256,9 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 					dev->counters[1] += deferred ? pass_pixel_walk_deferred<SpecGeneric>(b, fb, view, px, x, y, tile)
 					                             : pass_pixel_walk<SpecGeneric>(b, fb, view, px, x, y, tile);
 					pass_pixel_end(fb, view, px, x, y, sl);
+					uint32_t *word = nullptr;
+					if (const uint32_t bits = pass_pixel_write_mask(b, fb, px, x, y, sl, word))
+						*word |= bits;
 				}
 			}
 			pass_tile_clear_masks(b, fb, tile);
@@ -274,7 +277,7 @@ int rdpb_upscaling_init(rdpb_device *dev, uint32_t scale_log2)
 		return -1;
 	dev->scale_log2 = scale_log2;
 	const size_t slices = size_t(1) << (2 * scale_log2);
-	dev->up_rdram.assign(slices * dev->rdram_size, 0);
+	dev->up_rdram.assign(slices * dev->rdram_size + size_t(kWriteMaskWords) * 4, 0); // + the super-sampled write mask
 	dev->up_hidden.assign(slices * (dev->rdram_size >> 1), 3); // rdp_renderer.cpp:593
 	dev->up_reference.assign(dev->rdram_size, 0);
 	dev->up_spans.resize(size_t(kMaxSpansPerPass) << scale_log2);
@@ -299,8 +302,20 @@ int rdpb_launch_upscale_sync(rdpb_device *dev, const void *fb_info, int stage)
 	u.depth_index = fb.depth_addr >> 1;
 	u.num_pixels = fb.width * fb.height;
 	u.alias = fb.color_addr == fb.depth_addr;
-	for (uint32_t i = 0; i < u.num_pixels; i++)
-		upscale_sync_pixel(u, i, stage == RDPB_UPSCALE_SYNC_POST);
+	u.width = fb.width;
+	u.dither = stage == RDPB_UPSCALE_SYNC_RESOLVE_DITHER;
+	if (stage == RDPB_UPSCALE_SYNC_RESOLVE || stage == RDPB_UPSCALE_SYNC_RESOLVE_DITHER)
+	{
+		for (uint32_t y = 0; y < fb.height; y++)
+			for (uint32_t x = 0; x < fb.width; x++)
+				upscale_resolve_pixel(u, x, y);
+		memset(dev->up_rdram.data() + size_t(u.num_slices) * dev->rdram_size, 0, size_t(kWriteMaskWords) * 4);
+	}
+	else
+	{
+		for (uint32_t i = 0; i < u.num_pixels; i++)
+			upscale_sync_pixel(u, i, stage == RDPB_UPSCALE_SYNC_POST);
+	}
 	dev->launches++;
 	return 0;
 }
@@ -310,7 +325,7 @@ int rdpb_upscaled_read(rdpb_device *dev, void *rdram_dst, void *hidden_dst)
 	if (!dev->scale_log2)
 		return -1;
 	if (rdram_dst)
-		memcpy(rdram_dst, dev->up_rdram.data(), dev->up_rdram.size());
+		memcpy(rdram_dst, dev->up_rdram.data(), (size_t(1) << (2 * dev->scale_log2)) * dev->rdram_size);
 	if (hidden_dst)
 		memcpy(hidden_dst, dev->up_hidden.data(), dev->up_hidden.size());
 	return 0;
