@@ -129,7 +129,8 @@ def tile_kernel_algorithmic_bytes(tiles_processed: int, frames: int):
 class Stream:
     """One independent command stream: its own CommandProcessor (RDRAM, CUDA stream, command thread) and frames."""
 
-    def __init__(self, rdp, lib, torch, local_rank, seed, n_frames, triangles, depth, upscale=1, downscale_steps=0):
+    def __init__(self, rdp, lib, torch, local_rank, seed, n_frames, triangles, depth, upscale=1, downscale_steps=0,
+                 super_sample=False):
         self.frames_np = build_frames(seed, n_frames, triangles)
         # Pinned host copies of the frames (the e2e leg feeds the API from these).
         self.pinned = [torch.from_numpy(f.view(np.int32)).pin_memory() for f in self.frames_np]
@@ -139,6 +140,8 @@ class Stream:
         rdram = self.rdram_t.numpy()
         rdram[wl.TEX_ADDR:wl.TEX_ADDR + 8 * 2048] = wl.c2_textures()
         flags = {1: 0, 2: 1 << 2, 4: 1 << 3, 8: 1 << 4}[upscale]  # RDP_B200_FLAG_UPSCALING_*
+        if super_sample:
+            flags |= 1 << 5  # RDP_B200_FLAG_SUPER_SAMPLED_READ_BACK
         self.proc = rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, flags=flags, cuda_device=local_rank)
         self.proc.begin_read_hidden_rdram()[:] = 0
         self.proc.end_write_hidden_rdram()
@@ -213,14 +216,16 @@ def run_ours(args):
     def stream_seed(s):
         return 1000 + (s * world + rank) if world > 1 else 2 + s
     streams = [Stream(rdp, lib, torch, local_rank, stream_seed(s), n_full if s == 0 else n_extra, args.triangles, E2E_DEPTH,
-                      args.upscale, args.downscale_steps)
+                      args.upscale, args.downscale_steps, args.super_sample)
                for s in range(s_max)]
     s0 = streams[0]
     prims_per_frame, _ = wl.frame_stats(s0.frames[0])
 
     # --- parity spot check against the oracle (rank 0): frame 0, RDRAM + scan-out ----------------------------------
     parity = "not checked"
-    if rank == 0 and not args.no_parity:
+    if args.super_sample:
+        parity = "not applicable: with super-sampled read-back native RDRAM holds the average of the upscaled samples (tests/test_super_sampled_readback.py)"
+    if rank == 0 and not args.no_parity and not args.super_sample:
         try:
             from oracle import angrylion
             if angrylion.available():
@@ -448,7 +453,9 @@ def run_ours(args):
                        **({"internal_upscaling": "%dx: every eligible pass is rendered a second time into a %dx%d upscaled domain; "
                                                  "scan-out of that domain with %d downscale step(s) (BASELINE C4-ii, not the headline config)"
                                                  % (args.upscale, 640 * args.upscale, 480 * args.upscale, args.downscale_steps)}
-                          if args.upscale > 1 else {})},
+                          if args.upscale > 1 else {}),
+                       **({"super_sampled_read_back": "passes are rendered upscaled only and resolved into native RDRAM"}
+                          if args.super_sample else {})},
             "streams": {str(S): {"frames_per_s": v["frames_per_s"], "ms_per_step": v["ms_per_step"]} for S, v in sweep.items()},
             "mpix_shaded_per_s": round(b["shaded_pairs"] / (b["ms"] / 1e3) / 1e6 * world, 2),
             "shaded_pixels_per_frame": int(b["shaded_pairs"] / max(args.steps * best, 1)),
@@ -564,6 +571,7 @@ def main():
                                                           "value/e2e report the best, the sweep is kept in the JSON line")
     ap.add_argument("--upscale", type=int, default=1, choices=[1, 2, 4, 8], help="internal upscaling factor (BASELINE C4-ii measurement)")
     ap.add_argument("--downscale-steps", type=int, default=0, help="halving steps of the upscaled scan-out")
+    ap.add_argument("--super-sample", action="store_true", help="with --upscale: super-sampled read-back (upscaled-only passes + resolve)")
     ap.add_argument("--small", action="store_true", help="fewer distinct frames (quick functional run; violates the L2 rule)")
     args = ap.parse_args()
     if args.impl == "reference":
