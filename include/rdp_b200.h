@@ -52,6 +52,8 @@ typedef struct rdp_b200_scanout_options
 	uint32_t downscale_steps;
 	uint32_t persist_frame_on_invalid_input;
 	uint32_t blend_previous_frame;
+	/* A serrated frame is scanned out as its one field at half height instead of being woven; with internal upscaling and
+	 * downscale_steps > 0 the halved field is then bob-deinterlaced (video_interface.cpp:1066-1123, 1355-1389). */
 	uint32_t upscale_deinterlacing;
 	uint32_t vi_aa, vi_scale, vi_serrate, vi_dither_filter, vi_divot_filter, vi_gamma_dither;
 } rdp_b200_scanout_options;

@@ -13,7 +13,8 @@
 //   k_upscale_resolve  super-sampled read-back: samples averaged into RDRAM (update_upscaled_domain_resolve.comp)
 //   k_vi_filter     VI AA / dither-reconstruction / divot from a shared-memory copy of the framebuffer neighbourhood
 //                   (extract_vram.comp + vi_fetch.frag + vi_divot.frag)
-//   k_vi_scale      VI scale, gamma, field merge (vi_scale.frag + vi_blend_fields.frag); k_vi_downscale halves the image
+//   k_vi_scale      VI scale, gamma, field merge (vi_scale.frag + vi_blend_fields.frag); k_vi_downscale halves the image,
+//                   k_vi_bob deinterlaces the halved field (vi_deinterlace.vert/.frag)
 // Nothing here is a dense contraction, so no tensor-core path exists; the work is integer ALU + coalesced
 // RDRAM loads/stores.  There is no CPU fallback: creation fails when no CUDA device is usable.
 //
@@ -1216,6 +1217,13 @@ __global__ void __launch_bounds__(256) k_vi_scale(ViFrame f, ViBuffers b)
 		vi_scale_thread(f, b, x, y);
 }
 
+__global__ void __launch_bounds__(256) k_vi_bob(const uint32_t *src, int width, int src_height, uint32_t *dst, int dst_height, uint32_t scale, int field)
+{
+	const int x = int(blockIdx.x * blockDim.x + threadIdx.x), y = int(blockIdx.y * blockDim.y + threadIdx.y);
+	if (x < width && y < dst_height)
+		vi_bob_thread(src, width, src_height, dst, scale, field != 0, x, y);
+}
+
 __global__ void __launch_bounds__(256) k_vi_downscale(const uint32_t *src, int src_width, uint32_t *dst, int dst_width, int dst_height)
 {
 	const int x = int(blockIdx.x * blockDim.x + threadIdx.x);
@@ -1767,9 +1775,11 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		{
 			const uint32_t *src = b.out;
 			int w = f.out_width, h = f.out_height;
+			// (+ the bob deinterlacer as one more step of the ping-pong)
+			const uint32_t steps = f.downscale_steps + (f.bob_scale ? 1u : 0u);
 			for (uint32_t i = 0; i < f.downscale_steps; i++)
 			{
-				uint32_t *dst = ((f.downscale_steps - i) & 1u) ? dev->vi_down[dev->vi_out_index] : dev->vi_filtered;
+				uint32_t *dst = ((steps - i) & 1u) ? dev->vi_down[dev->vi_out_index] : dev->vi_filtered;
 				const dim3 block(32, 8);
 				const dim3 grid((w / 2 + 31) / 32, (h / 2 + 7) / 8);
 				k_vi_downscale<<<grid, block, 0, vs>>>(src, w, dst, w / 2, h / 2);
@@ -1777,6 +1787,16 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 				src = dst;
 				w /= 2;
 				h /= 2;
+			}
+			if (f.bob_scale)
+			{
+				uint32_t *dst = dev->vi_down[dev->vi_out_index];
+				const int out_h = f.bob_scale == 1u ? 2 * h : h;
+				const dim3 block(32, 8);
+				const dim3 grid((w + 31) / 32, (out_h + 7) / 8);
+				k_vi_bob<<<grid, block, 0, vs>>>(src, w, h, dst, out_h, f.bob_scale, int(f.bob_field));
+				dev->launches++;
+				src = dst;
 			}
 			dev->vi_result[dev->vi_out_index] = const_cast<uint32_t *>(src);
 		}

@@ -66,6 +66,10 @@ struct ViFrame
 	// `downscale_steps` times (video_interface.cpp:1001-1064).
 	uint32_t scale_log2;
 	uint32_t downscale_steps;
+	// Bob deinterlacing of the halved image (video_interface.cpp:1066-1123, 1380-1389): 0 = off, else the scaling
+	// factor left after the halving steps (1, 2 or 4); bob_field = this is the field with VCurrentLine == 0.
+	uint32_t bob_scale;
+	uint32_t bob_field;
 
 	// RDRAM byte range [vram_lo, vram_hi) the filter can read (native addresses; video_interface.cpp:369-396).  The
 	// backend runs the scan-out on its own stream and holds back only render passes that write into this range.
@@ -444,6 +448,27 @@ RDP_HD void vi_downscale_thread(const uint32_t *src, int src_width, uint32_t *ds
 	for (int sh = 0; sh < 32; sh += 8)
 		out |= ((((p00 >> sh) & 0xffu) + ((p10 >> sh) & 0xffu) + ((p01 >> sh) & 0xffu) + ((p11 >> sh) & 0xffu) + 2u) >> 2) << sh;
 	dst[size_t(y) * size_t(dst_width) + size_t(x)] = out;
+}
+
+// Bob deinterlacing (ref upscale_deinterlace, video_interface.cpp:1066-1123 with vi_deinterlace.vert/.frag): the one
+// field of a serrated frame, scaled and halved, is resampled with a clamped linear filter at a vertical offset of
+// -+ scale / 4 source rows; at scale 1 the output also has twice the rows.  In texel space the sample position of output
+// row y is y / 2 - 1/2 or y / 2 (scale 1), y -+ scale / 4 (scale 2, 4): always a whole or a half row, so the filter is
+// either one source row or the mean of two neighbours (ties round up; the reference leaves that to the sampler).
+RDP_HD void vi_bob_thread(const uint32_t *src, int width, int src_height, uint32_t *dst, uint32_t scale, bool field, int x, int y)
+{
+	// twice the sample row
+	const int ty2 = scale == 1u ? (field ? y - 1 : y) : (field ? 2 * y - int(scale >> 1) : 2 * y + int(scale >> 1));
+	int r0 = ty2 >> 1;
+	int r1 = r0 + (ty2 & 1);
+	r0 = r0 < 0 ? 0 : (r0 >= src_height ? src_height - 1 : r0);
+	r1 = r1 < 0 ? 0 : (r1 >= src_height ? src_height - 1 : r1);
+	const uint32_t a = src[size_t(r0) * size_t(width) + size_t(x)];
+	const uint32_t b = src[size_t(r1) * size_t(width) + size_t(x)];
+	uint32_t out = 0;
+	for (int sh = 0; sh < 32; sh += 8)
+		out |= ((((a >> sh) & 0xffu) + ((b >> sh) & 0xffu) + 1u) >> 1) << sh;
+	dst[size_t(y) * size_t(width) + size_t(x)] = out;
 }
 
 void build_blender_lut(uint8_t *lut);

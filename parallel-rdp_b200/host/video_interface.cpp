@@ -429,6 +429,13 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 	}
 	// Halving steps of the finished image (ref downscale_stage, video_interface.cpp:1001-1064): at most down to 1x.
 	f.downscale_steps = std::min<uint32_t>(std::min(8u, options.downscale_steps), scale_log2);
+	// Bob deinterlacing (ref video_interface.cpp:1355-1389): only a serrated frame that was scanned out upscaled as one
+	// field (upscale_deinterlacing) and halved gets there; at a remaining scale of 1 the result has twice the rows.
+	f.bob_scale = 0;
+	f.bob_field = regs.v_current_line == 0 ? 1u : 0u;
+	if (f.downscale_steps != 0 && options.upscale_deinterlacing && (regs.status & VI_CONTROL_SERRATE_BIT) != 0)
+		f.bob_scale = std::max<uint32_t>(1u, uint32_t(scale) >> f.downscale_steps);
+	const unsigned bob_rows = f.bob_scale == 1 ? 2 : 1;
 	f.v_start = regs.v_start;
 
 	const int dx = -int(crop_left), dy = -int(crop_top);
@@ -476,12 +483,12 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 	prev_width = width;
 	prev_height = height;
 	prev_result_width = width >> f.downscale_steps;
-	prev_result_height = height >> f.downscale_steps;
+	prev_result_height = (height >> f.downscale_steps) * bob_rows;
 	frame_count++;
 
 	result.device_rgba8 = rdpb_vi_output_device_ptr(device);
 	result.width = width >> f.downscale_steps;
-	result.height = height >> f.downscale_steps;
+	result.height = (height >> f.downscale_steps) * bob_rows;
 	return result;
 }
 }

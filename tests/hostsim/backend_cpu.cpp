@@ -383,6 +383,17 @@ int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *line
 			h /= 2;
 			dev->launches++;
 		}
+		if (f.bob_scale)
+		{
+			std::vector<uint32_t> &dst = *bufs[f.downscale_steps & 1];
+			const int out_h = f.bob_scale == 1u ? 2 * h : h;
+			dst.assign(size_t(w) * out_h, 0);
+			for (int y = 0; y < out_h; y++)
+				for (int x = 0; x < w; x++)
+					vi_bob_thread(src, w, h, dst.data(), f.bob_scale, f.bob_field != 0, x, y);
+			src = dst.data();
+			dev->launches++;
+		}
 		dev->vi_result = src;
 	}
 	return 0;
