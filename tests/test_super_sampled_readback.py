@@ -126,6 +126,43 @@ def test_hostsim_fill_rectangle_resolves_exactly(flags):
         assert np.array_equal(up[s][lo:hi], native[lo:hi])
 
 
+def test_hostsim_cpu_writes_survive_the_next_resolve():
+    """What the write mask is for: a pixel the pass did not store to is not resolved, so a value the CPU put into native
+    RDRAM between two passes stays (and reaches every sample through the PRE synchronisation)."""
+    sbs = SideBySide("hostsim", with_oracle=False, flags=UPSCALE[2] | SSAA)
+    try:
+        sbs.clear_rdram()
+
+        def fill(x, y, w, h, color):
+            b = Builder()
+            b.set_color_image(0, 2, COLOR, 320)
+            b.set_scissor(0, 0, 320, 240)
+            b.om.cycle_type = rb.CYCLE_FILL
+            b.touch_other_modes()
+            b.flush_other_modes()
+            b.set_fill_color(color)
+            b.fill_rectangle(x, y, w, h)
+            b.sync_full()
+            sbs.run(b.take())
+            sbs.gpu.idle()
+
+        fill(0, 0, 320, 100, 0x08430843)
+        stripe = np.full(320 * 2 * 4, 0x5a, np.uint8)  # rows 40..43, inside the first rectangle
+        sbs.write_rdram(COLOR + 320 * 2 * 40, stripe)
+        fill(16, 60, 100, 30, 0xf801f801)  # same framebuffer, rows 60..89: rows 0..89 are synchronised and resolved
+        native = sbs.gpu.begin_read_rdram().copy()
+        up, _ = sbs.gpu.read_upscaled_rdram()
+    finally:
+        sbs.close()
+    n16 = native[COLOR:COLOR + 320 * 100 * 2].view(np.uint16).reshape(100, 160, 2)[:, :, ::-1].reshape(100, 320)
+    assert (n16[40:44] == 0x5a5a).all()
+    assert (n16[:40] == 0x0843).all() and (n16[44:60] == 0x0843).all()
+    assert (n16[60:90, 16:116] == 0xf801).all() and (n16[60:90, 116:] == 0x0843).all() and (n16[90:] == 0x0843).all()
+    for s in range(4):
+        u16 = up[s][COLOR:COLOR + 320 * 90 * 2].view(np.uint16).reshape(90, 160, 2)[:, :, ::-1].reshape(90, 320)
+        assert np.array_equal(u16, n16[:90])
+
+
 def _resolve16(up, addr, count, width, dither):
     n = up.shape[0]
     # 16-bit element i lives at i ^ 1; undo it per pair to get pixel order
