@@ -84,6 +84,22 @@ void rdp_b200_wait_for_timeline(rdp_b200_processor *p, uint64_t index);
 void rdp_b200_idle(rdp_b200_processor *p);
 void rdp_b200_begin_frame_context(rdp_b200_processor *p);
 
+/* set_validation_interface, rdp_device.cpp:230-233; ValidationInterface::report_rdp_crash and ValidationError,
+ * rdp_renderer.hpp:75-95: conditions under which real hardware locks up.  The callback replaces the C++ interface
+ * object; like it, it may be called from the command thread.  NULL removes it.  Set it while the processor is idle. */
+enum rdp_b200_validation_error
+{
+	RDP_B200_VALIDATION_FILL_4BPP = 0,
+	RDP_B200_VALIDATION_FILL_DEPTH_TEST,
+	RDP_B200_VALIDATION_FILL_DEPTH_WRITE,
+	RDP_B200_VALIDATION_FILL_IMAGE_READ_ENABLE,
+	RDP_B200_VALIDATION_COPY_32BPP,
+	RDP_B200_VALIDATION_LOAD_TILE_4BPP,
+	RDP_B200_VALIDATION_INVALID_MULTILINE_LOAD_TLUT
+};
+typedef void (*rdp_b200_validation_callback)(void *user, int error, const char *message);
+void rdp_b200_set_validation_callback(rdp_b200_processor *p, rdp_b200_validation_callback callback, void *user);
+
 /* set_quirks, rdp_device.cpp:961-968 */
 void rdp_b200_set_quirks(rdp_b200_processor *p, int native_resolution_tex_rect, int native_texture_lod);
 

@@ -46,6 +46,7 @@ def _bind(lib):
         "rdp_b200_idle": (None, [P]),
         "rdp_b200_begin_frame_context": (None, [P]),
         "rdp_b200_set_quirks": (None, [P, C.c_int, C.c_int]),
+        "rdp_b200_set_validation_callback": (None, [P, P, P]),
         "rdp_b200_begin_read_rdram": (P, [P]),
         "rdp_b200_end_write_rdram": (None, [P]),
         "rdp_b200_begin_read_hidden_rdram": (P, [P]),
@@ -210,6 +211,17 @@ class CommandProcessor:
 
     def end_vi_register_per_scanline(self):
         self.lib.rdp_b200_end_vi_register_per_scanline(self._h)
+
+    def set_validation_callback(self, fn):
+        """fn(error: int, message: str) for every condition that locks up real hardware (ValidationInterface,
+        rdp_renderer.hpp:75-95); None removes it.  Called from the command thread."""
+        if fn is None:
+            self._validation_cb = None
+            self.lib.rdp_b200_set_validation_callback(self._h, None, None)
+            return
+        proto = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p)
+        self._validation_cb = proto(lambda user, err, msg: fn(int(err), msg.decode()))  # kept alive with the processor
+        self.lib.rdp_b200_set_validation_callback(self._h, C.cast(self._validation_cb, C.c_void_p), None)
 
     def set_quirks(self, native_resolution_tex_rect: bool = True, native_texture_lod: bool = False):
         self.lib.rdp_b200_set_quirks(self._h, int(native_resolution_tex_rect), int(native_texture_lod))

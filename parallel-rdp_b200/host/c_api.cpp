@@ -9,6 +9,17 @@ using namespace RDP;
 struct rdp_b200_processor
 {
 	CommandProcessor impl;
+	// The C callback behind the reference's ValidationInterface object.
+	struct Validation final : ValidationInterface
+	{
+		rdp_b200_validation_callback callback = nullptr;
+		void *user = nullptr;
+		void report_rdp_crash(ValidationError err, const char *msg) override
+		{
+			if (callback)
+				callback(user, int(err), msg);
+		}
+	} validation;
 	rdp_b200_processor(int dev, void *rdram, size_t off, size_t size, size_t hidden, uint32_t flags)
 		: impl(DeviceConfig{dev}, rdram, off, size, hidden, flags)
 	{
@@ -69,6 +80,14 @@ uint64_t rdp_b200_signal_timeline(rdp_b200_processor *p) { return p->impl.signal
 void rdp_b200_wait_for_timeline(rdp_b200_processor *p, uint64_t index) { p->impl.wait_for_timeline(index); }
 void rdp_b200_idle(rdp_b200_processor *p) { p->impl.idle(); }
 void rdp_b200_begin_frame_context(rdp_b200_processor *p) { p->impl.begin_frame_context(); }
+
+void rdp_b200_set_validation_callback(rdp_b200_processor *p, rdp_b200_validation_callback callback, void *user)
+{
+	p->impl.idle(); // the command thread reads the interface pointer
+	p->validation.callback = callback;
+	p->validation.user = user;
+	p->impl.set_validation_interface(callback ? &p->validation : nullptr);
+}
 
 void rdp_b200_set_quirks(rdp_b200_processor *p, int native_resolution_tex_rect, int native_texture_lod)
 {

@@ -177,3 +177,69 @@ def test_bulk_vi_register_write_equals_fourteen_single_writes():
         finally:
             sbs.close()
     assert images[0].size and np.array_equal(images[0], images[1])
+
+
+def test_validation_callback_reports_hardware_lockups():
+    """rdp_b200_set_validation_callback (ValidationInterface, rdp_renderer.hpp:75-95; report sites
+    rdp_renderer.cpp:1425-1462, 3101-3107): Fill mode with depth compare / image read, Copy mode on a 32-bit target and a
+    multi-line TLUT load are reported, a legal clear is not."""
+    from harness.rdp_builder import Builder
+    p = _proc()
+    seen = []
+    try:
+        p.set_validation_callback(lambda err, msg: seen.append((err, msg)))
+        b = Builder()
+        b.set_color_image(0, 2, 0x100000, 320)
+        b.set_scissor(0, 0, 320, 240)
+        b.om.cycle_type = rb.CYCLE_FILL
+        b.touch_other_modes()
+        b.flush_other_modes()
+        b.set_fill_color(0x00010001)
+        b.fill_rectangle(0, 0, 64, 16)
+        b.sync_full()
+        p.enqueue_command_stream(b.take())
+        p.idle()
+        assert seen == []
+
+        b.om.z_compare = True
+        b.om.image_read = True
+        b.touch_other_modes()
+        b.flush_other_modes()
+        b.fill_rectangle(0, 0, 64, 16)
+        b.sync_full()
+        p.enqueue_command_stream(b.take())
+        p.idle()
+        assert {e for e, _ in seen} == {1, 3}  # FILL_DEPTH_TEST, FILL_IMAGE_READ_ENABLE
+        assert all("Fill mode" in m for _, m in seen)
+
+        del seen[:]
+        b.om.z_compare = False
+        b.om.image_read = False
+        b.om.cycle_type = rb.CYCLE_COPY
+        b.touch_other_modes()
+        b.flush_other_modes()
+        b.set_color_image(0, 3, 0x100000, 320)
+        b.tex_rect(0, 0, 0, 32, 8, 0, 0, 4 << 10, 1 << 10)
+        b.sync_full()
+        p.enqueue_command_stream(b.take())
+        p.idle()
+        assert {e for e, _ in seen} == {4}  # COPY_32BPP
+
+        del seen[:]
+        b.set_texture_image(wl.TEX_ADDR + 0x1000, 0, 2, 16)
+        b.set_tile(7, 0, 2, 8, 2048)
+        b.load_tlut(7, 0, 0, 16, 2)  # two lines
+        b.sync_full()
+        p.enqueue_command_stream(b.take())
+        p.idle()
+        assert {e for e, _ in seen} == {6}  # INVALID_MULTILINE_LOAD_TLUT
+
+        del seen[:]
+        p.set_validation_callback(None)
+        b.load_tlut(7, 0, 0, 16, 2)
+        b.sync_full()
+        p.enqueue_command_stream(b.take())
+        p.idle()
+        assert seen == []
+    finally:
+        p.close()
