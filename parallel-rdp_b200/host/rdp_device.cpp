@@ -71,6 +71,18 @@ CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, 
 	}
 	vi.init(device, rdram_size);
 
+	if (const char *env = getenv("PARALLEL_RDP_DUMP_PATH"))
+	{
+		dump_writer.reset(new RDPDumpWriter);
+		if (!dump_writer->init(env, uint32_t(rdram_size), uint32_t(hidden_size)))
+		{
+			fprintf(stderr, "[rdp-b200] Failed to init RDP dump: %s.\n", env);
+			dump_writer.reset();
+		}
+		else
+			fprintf(stderr, "[rdp-b200] Dumping RDP commands to: %s.\n", env);
+	}
+
 	if (const char *env = getenv("PARALLEL_RDP_SINGLE_THREADED_COMMAND"))
 		single_threaded_processing = strtol(env, nullptr, 0) > 0;
 	else
@@ -341,16 +353,49 @@ void CommandProcessor::enqueue_command_inner(unsigned num_words, const uint32_t 
 		ring.enqueue_command(num_words, words);
 }
 
+// Dumping (ref rdp_device.cpp:874-897): the first command after a SyncFull records what changed in RDRAM and hidden
+// RDRAM since the last record, every command is logged, SyncFull closes the list.
+void CommandProcessor::dump_begin_command_list()
+{
+	wait_for_timeline(signal_timeline());
+	dump_writer->flush_dram(begin_read_rdram(), uint32_t(rdram_size));
+	dump_writer->flush_hidden_dram(begin_read_hidden_rdram(), uint32_t(hidden_size));
+	dump_in_command_list = true;
+}
+
+void CommandProcessor::dump_end_frame()
+{
+	wait_for_timeline(signal_timeline());
+	dump_writer->flush_dram(begin_read_rdram(), uint32_t(rdram_size));
+	dump_writer->flush_hidden_dram(begin_read_hidden_rdram(), uint32_t(hidden_size));
+	dump_writer->end_frame();
+}
+
 void CommandProcessor::enqueue_command(unsigned num_words, const uint32_t *words)
 {
+	if (dump_writer && is_supported && !dump_in_command_list)
+		dump_begin_command_list();
+
 	enqueue_command_inner(num_words, words);
+
+	if (dump_writer && is_supported)
+	{
+		const uint32_t op = (words[0] >> 24) & 63u;
+		if (op == uint32_t(OP_SYNC_FULL))
+		{
+			dump_writer->signal_complete();
+			dump_in_command_list = false;
+		}
+		else
+			dump_writer->emit_command(op, words, num_words);
+	}
 }
 
 void CommandProcessor::enqueue_command_stream(size_t num_words, const uint32_t *words)
 {
 	if (!is_supported)
 		return;
-	if (!single_threaded_processing)
+	if (!single_threaded_processing && !dump_writer)
 	{
 		ring.enqueue_stream(num_words, words);
 		return;
@@ -361,7 +406,10 @@ void CommandProcessor::enqueue_command_stream(size_t num_words, const uint32_t *
 		const uint32_t len = command_length_words((words[pos] >> 24) & 63u);
 		if (pos + len > num_words)
 			break;
-		enqueue_command_inner(len, words + pos);
+		if (dump_writer)
+			enqueue_command(len, words + pos);
+		else
+			enqueue_command_inner(len, words + pos);
 		pos += len;
 	}
 }
@@ -390,7 +438,9 @@ void CommandProcessor::enqueue_command_stream_borrowed(size_t num_words, const u
 {
 	if (!is_supported)
 		return;
-	if (single_threaded_processing)
+	if (dump_writer)
+		enqueue_command_stream(num_words, words); // command by command, through the dump hooks
+	else if (single_threaded_processing)
 		execute_borrowed_stream(num_words, words);
 	else
 		ring.enqueue_stream_borrowed(num_words, words);
@@ -545,6 +595,8 @@ void CommandProcessor::begin_frame_context()
 void CommandProcessor::set_vi_register(VIRegister reg, uint32_t value)
 {
 	vi.set_vi_register(reg, value);
+	if (dump_writer)
+		dump_writer->set_vi_register(uint32_t(reg), value);
 }
 
 void CommandProcessor::begin_vi_register_per_scanline(VideoInterface::PerScanlineRegisterFlags f)
@@ -572,6 +624,8 @@ ScanoutImage CommandProcessor::scanout(const ScanoutOptions &opts)
 	if (!is_supported)
 		return {};
 	drain_command_ring();
+	if (dump_writer)
+		dump_end_frame();
 	// The command thread is idle now, so the renderer can be driven from this thread.
 	std::lock_guard<std::mutex> holder{idle_lock};
 	renderer.flush_queues();
@@ -608,6 +662,8 @@ uint64_t CommandProcessor::scanout_async(void *rgba, size_t capacity_pixels, uns
 {
 	if (!is_supported)
 		return 0;
+	if (dump_writer)
+		dump_end_frame();
 	auto *req = new ScanoutRequest;
 	vi.capture_registers(req->registers); // set_vi_register acts immediately on this thread: freeze what this frame saw
 	req->opts = opts;

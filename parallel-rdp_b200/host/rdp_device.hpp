@@ -11,6 +11,7 @@
 #include "command_ring.hpp"
 #include "rdp_renderer.hpp"
 #include "video_interface.hpp"
+#include "rdp_dump.hpp"
 #include <atomic>
 #include <memory>
 #include <mutex>
@@ -150,6 +151,12 @@ private:
 	void execute_scanout_request(ScanoutRequest *req);
 	bool is_supported = false;
 	bool single_threaded_processing = true;
+	// PARALLEL_RDP_DUMP_PATH: everything fed to the processor is also written to an RDPDUMP2 file
+	// (ref rdp_device.cpp:60-76, 874-897, 970-975, 1087-1093).
+	std::unique_ptr<RDPDumpWriter> dump_writer;
+	bool dump_in_command_list = false;
+	void dump_begin_command_list();
+	void dump_end_frame();
 
 	std::atomic<bool> host_rdram_dirty{true}; // CPU wrote RDRAM since the last upload
 	std::mutex idle_lock;

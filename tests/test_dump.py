@@ -191,3 +191,71 @@ def test_gpu_replays_dump_like_the_oracle(tmp_path):
     errs, checks = _validate_dump("cuda", path, None)
     assert not errs, errs
     assert checks == 6
+
+
+# --- PARALLEL_RDP_DUMP_PATH: the processor records what it is fed (ref rdp_device.cpp:60-76, 874-897, 970-975, 1087-1093) ---
+@pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
+def test_dump_path_env_records_a_replayable_dump(tmp_path, lib, monkeypatch):
+    path = str(tmp_path / "live.rdp")
+    monkeypatch.setenv("PARALLEL_RDP_DUMP_PATH", path)
+    rdram = np.zeros(RDRAM, np.uint8)
+    rdram[wl.TEX_ADDR:wl.TEX_ADDR + 8 * 2048] = wl.c2_textures()
+    p = rdp.CommandProcessor(rdram, HIDDEN, library=lib)
+    monkeypatch.delenv("PARALLEL_RDP_DUMP_PATH")  # the replaying processors below must not dump
+    try:
+        p.begin_read_hidden_rdram()[:] = 0
+        p.end_write_hidden_rdram()
+        p.end_write_rdram()
+        rng = np.random.RandomState(2)
+        opts = p.default_scanout_options()
+        for i, feed in enumerate(("single", "stream", "borrowed")):
+            frame = wl.c2_frame(rng, 120)
+            if feed == "single":
+                for cmd in split_commands(frame):
+                    p.enqueue_command(cmd)
+            elif feed == "stream":
+                p.enqueue_command_stream(frame)
+            else:
+                p.enqueue_command_stream_borrowed(frame)
+            for k, v in wl.c2_vi_registers(i & 1).items():
+                p.set_vi_register(k, v)
+            p.scanout_sync(opts)
+            # the "CPU" scribbles over a texture between frames
+            p.begin_read_rdram()[wl.TEX_ADDR + 64: wl.TEX_ADDR + 64 + 512] = rng.randint(0, 256, 512)
+            p.end_write_rdram()
+        p.idle()
+        live_rdram = p.begin_read_rdram().copy()
+        live_hidden = (p.begin_read_hidden_rdram() & 3).copy()
+    finally:
+        p.close()  # closes the dump
+    assert open(path, "rb").read(8) == b"RDPDUMP2"
+
+    # the file replays against the oracle like any other dump: 3 x (SIGNAL_COMPLETE + END_FRAME)
+    errs, checks = _validate_dump("hostsim", path, lib)
+    assert not errs, errs
+    assert checks == 6
+
+    # and a replay ends where the live run ended
+    player = rdp.DumpPlayer(path, library=lib)
+    q = rdp.CommandProcessor(np.zeros(RDRAM, np.uint8), HIDDEN, library=lib)
+    try:
+        while True:
+            n, stop = player.replay(q)
+            if stop == rdp.DUMP_EOF:
+                break
+            if stop == rdp.DUMP_END_FRAME:
+                q.scanout_sync(q.default_scanout_options())
+        q.idle()
+        # (the last scribble happened after the last recorded state, so compare outside it)
+        a, b = q.begin_read_rdram().copy(), live_rdram.copy()
+        a[wl.TEX_ADDR + 64: wl.TEX_ADDR + 64 + 512] = 0
+        b[wl.TEX_ADDR + 64: wl.TEX_ADDR + 64 + 512] = 0
+        assert np.array_equal(a, b)
+        assert np.array_equal(q.begin_read_hidden_rdram() & 3, live_hidden)
+    finally:
+        player.close()
+        q.close()
+    if ref_dump.available():
+        events = ref_dump.play(path)
+        assert sum(1 for e in events if e[0] == rdp.DUMP_SIGNAL_COMPLETE) == 3
+        assert sum(1 for e in events if e[0] == rdp.DUMP_END_FRAME) == 3
