@@ -41,6 +41,9 @@ struct rdpb_device
 	uint64_t deferred_passes = 0;
 	bool last_deferred = false;
 	unsigned long long counters[8] = {};
+	// RDP_HOSTSIM_HIZ=1 (test-only experiment, see hiz_check_tile): entries seen / rejected by the bound / with no passing
+	// fragment at all / rejected although a fragment passed (must stay 0)
+	unsigned long long hiz[4] = {};
 	std::string error;
 
 	PassBuffers buffers()
@@ -210,6 +213,117 @@ int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 	return 0;
 }
 
+// ---- experiment: conservative per-(tile, primitive) depth rejection ----------------------------------
+// Walks one tile primitive-major over private copies of its 32 pixels' depth state, exactly as phases A and B of the
+// deferred pipeline would (defer_candidate / defer_depth), and checks the rejection bound derived in DESIGN.md: an entry
+// in opaque Z-compare mode whose smallest fragment Z exceeds max(tileA, tileZ + 8 * P(dz)) cannot pass anywhere in the
+// tile.  tileA / tileZ are exact at the start of every 32-primitive batch and widened inside the batch by what the
+// earlier entries of the batch could have written.  Nothing is stored: the regular walk that follows renders the tile.
+static int hiz_pow2_floor(int v) { return v > 0 ? 1 << find_msb(uint32_t(v)) : 0; }
+
+static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo &fb, uint32_t tile, uint32_t tx, uint32_t ty)
+{
+	constexpr int kInf = 0x7fffffff;
+	FbView view[32];
+	PixelState px[32];
+	bool inside[32];
+	for (int l = 0; l < 32; l++)
+	{
+		const int x = int(tx * kTileW) + (l & 7), y = int(ty * kTileH) + (l >> 3);
+		inside[l] = x < int(fb.width) && y < int(fb.height);
+		pass_pixel_begin<SpecGeneric>(b, fb, view[l], px[l], x, y, 0);
+	}
+	const uint32_t *coarse = b.coarse_mask + size_t(tile) * fb.coarse_stride;
+	const uint32_t *fine = b.fine_mask + size_t(tile) * fb.mask_stride;
+	for (uint32_t group = 0; group < fb.mask_stride; group++)
+	{
+		if (!((coarse[group >> 5] >> (group & 31u)) & 1u))
+			continue;
+		// exact bounds at batch start
+		int cap_a = 0, cap_z = 0;
+		for (int l = 0; l < 32; l++)
+		{
+			if (!inside[l])
+				continue;
+			const int mem_depth = px[l].depth, mem_dz_c = px[l].dz;
+			const int memory_z = z_decompress(mem_depth);
+			int memory_dz = 1 << mem_dz_c;
+			const int precision = (mem_depth >> 11) & 0xf;
+			bool unbounded = memory_z == 0x3ffff;
+			if (precision < 3)
+			{
+				if (memory_dz != 0x8000)
+					memory_dz = imax(memory_dz << 1, 16 >> precision);
+				else
+					unbounded = true; // coplanar
+			}
+			cap_z = imax(cap_z, memory_z);
+			cap_a = unbounded ? kInf : imax(cap_a, memory_z + 8 * hiz_pow2_floor(memory_dz));
+		}
+		uint32_t bits = fine[group];
+		while (bits)
+		{
+			const uint32_t index = group * 32u + uint32_t(find_lsb(bits));
+			bits &= bits - 1u;
+			const PrimSetup &p = b.prims[index];
+			const PassState &st = b.states[p.state_id];
+			uint32_t cand[32];
+			int zmin = kInf, zmax = -1;
+			bool any = false, fill = false;
+			for (int l = 0; l < 32; l++)
+			{
+				cand[l] = 0;
+				const int x = int(tx * kTileW) + (l & 7), y = int(ty * kTileH) + (l >> 3);
+				if (!inside[l] || y < p.line_lo || y > p.line_hi)
+					continue;
+				const Span &sp = b.spans[p.span_base + uint32_t(y - p.line_lo)];
+				if (!sp.valid)
+					continue;
+				cand[l] = defer_candidate<SpecGeneric>(st, p, sp, x);
+				if (!(cand[l] & DC_VALID))
+					continue;
+				any = true;
+				if (cand[l] & DC_FILL)
+					fill = true;
+				else
+				{
+					zmin = imin(zmin, int(cand[l] & DC_Z_MASK));
+					zmax = imax(zmax, int(cand[l] & DC_Z_MASK));
+				}
+			}
+			if (!any || fill)
+				continue; // fill-mode entries never touch depth in a deferrable pass
+			const bool opaque_compare = (st.blend_flags & BF_Z_COMPARE) != 0u && st.z_mode == 0;
+			const int own = 8 * hiz_pow2_floor(int(p.dz));
+			const bool reject = opaque_compare && cap_a != kInf && zmin > imax(cap_a, cap_z + own);
+			bool passed = false;
+			for (int l = 0; l < 32; l++)
+				if ((cand[l] & DC_VALID) && defer_depth<SpecGeneric>(view[l], px[l], st, p.dz, p.dz_compressed, cand[l]))
+					passed = true;
+			dev->hiz[0]++;
+			dev->hiz[1] += reject;
+			dev->hiz[2] += !passed;
+			dev->hiz[3] += reject && passed;
+			// what this entry may have written, for the later entries of the batch
+			if (!reject && (st.blend_flags & BF_Z_UPDATE))
+			{
+				cap_z = imax(cap_z, zmax);
+				const int written_dz = 1 << int(p.dz_compressed);
+				if (written_dz == 0x8000)
+					cap_a = kInf;
+				else if (cap_a != kInf)
+					cap_a = imax(cap_a, zmax + 8 * imax(written_dz << 1, 16));
+			}
+		}
+	}
+}
+
+void rdpb_hostsim_hiz_stats(rdpb_device *dev, unsigned long long out[4])
+{
+	for (int i = 0; i < 4; i++)
+		out[i] = dev->hiz[i];
+}
+
 const char *rdpb_last_tile_variant(rdpb_device *dev) { return dev->last_deferred ? "generic+deferred" : "generic"; }
 
 int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary)
@@ -231,6 +345,7 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 	// the in-order walk (tests/test_hostsim_conformance.py runs the suites both ways).
 	const bool deferred = !sl && summary && getenv("RDP_HOSTSIM_DEFERRED") && deferrable_pass(*static_cast<const PassSummary *>(summary), fb);
 	dev->last_deferred = deferred;
+	const bool hiz = !sl && summary && getenv("RDP_HOSTSIM_HIZ") && deferrable_pass(*static_cast<const PassSummary *>(summary), fb);
 	if (deferred)
 		dev->deferred_passes++;
 	for (uint32_t ty = 0; ty < fb.tiles_y; ty++)
@@ -243,6 +358,8 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 				any = any || b.coarse_mask[size_t(tile) * fb.coarse_stride + cw] != 0;
 			if (!any)
 				continue;
+			if (hiz)
+				hiz_check_tile(dev, b, fb, tile, tx, ty);
 			for (int ly = 0; ly < int(kTileH); ly++)
 			{
 				for (int lx = 0; lx < int(kTileW); lx++)
