@@ -41,9 +41,10 @@ struct rdpb_device
 	uint64_t deferred_passes = 0;
 	bool last_deferred = false;
 	unsigned long long counters[8] = {};
-	// RDP_HOSTSIM_HIZ=1 (test-only experiment, see hiz_check_tile): entries seen / rejected by the bound / with no passing
-	// fragment at all / rejected although a fragment passed (must stay 0)
-	unsigned long long hiz[4] = {};
+	// RDP_HOSTSIM_HIZ=1 (test-only experiment, see hiz_check_tile): entries seen / rejected by the bound with the entry's Z
+	// bounded from its spans / with no passing fragment at all / rejected although a fragment passed (must stay 0) /
+	// rejected when the entry's smallest fragment Z is known exactly / span bound above a real fragment's Z (must stay 0)
+	unsigned long long hiz[6] = {};
 	std::string error;
 
 	PassBuffers buffers()
@@ -221,6 +222,45 @@ int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 // earlier entries of the batch could have written.  Nothing is stored: the regular walk that follows renders the tile.
 static int hiz_pow2_floor(int v) { return v > 0 ? 1 << find_msb(uint32_t(v)) : 0; }
 
+// Lower bound of the Z of every fragment the primitive can have in the tile at (x0, y0), from what the mask phase reads
+// anyway: the four lines' span headers.  Along a line Z is linear in x before the snapping, the centroid offsets add
+// between 0 and 3 quarter-steps of dz/dx and dz/dy (interpolate_depth), the final shift and clamp are monotone as long as
+// nothing wraps; if anything can wrap, no bound is given (-1).
+static int hiz_entry_z_lower_bound(const PassBuffers &b, const FbInfo &fb, const PrimSetup &p, int x0, int y0)
+{
+	long long t_lo = 0, t_hi = 0;
+	bool any = false;
+	const long long dzdx = p.dstzw_dx[2];
+	const long long ox = 3ll * (p.dstzw_dx[2] >> 10), oy = 3ll * (p.dstzw_dy[2] >> 10);
+	const long long off_lo = (ox < 0 ? ox : 0) + (oy < 0 ? oy : 0), off_hi = (ox > 0 ? ox : 0) + (oy > 0 ? oy : 0);
+	for (int ly = 0; ly < int(kTileH); ly++)
+	{
+		const int y = y0 + ly;
+		if (y >= int(fb.height) || y < p.line_lo || y > p.line_hi)
+			continue;
+		const Span &sp = b.spans[p.span_base + uint32_t(y - p.line_lo)];
+		if (!sp.valid)
+			continue;
+		const int xlo = imax(int(sp.start_x), x0), xhi = imin(imin(int(sp.end_x), x0 + int(kTileW) - 1), int(fb.width) - 1);
+		if (xlo > xhi)
+			continue;
+		for (int k = 0; k < 2; k++)
+		{
+			const long long z = (long long)(sp.stzw[2]) + dzdx * ((k ? xhi : xlo) - sp.base_x);
+			if (z < -2147483648ll || z > 2147483647ll)
+				return -1;
+			const long long snapped = (z >> 10) * 4;
+			const long long lo = (snapped + off_lo) >> 5, hi = (snapped + off_hi) >> 5;
+			t_lo = any ? (lo < t_lo ? lo : t_lo) : lo;
+			t_hi = any ? (hi > t_hi ? hi : t_hi) : hi;
+			any = true;
+		}
+	}
+	if (!any || t_lo < -131072 || t_hi >= 393216) // clamp_depth's 19-bit window
+		return -1;
+	return int(t_lo < 0 ? 0 : (t_lo > 0x3ffff ? 0x3ffff : t_lo));
+}
+
 static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo &fb, uint32_t tile, uint32_t tx, uint32_t ty)
 {
 	constexpr int kInf = 0x7fffffff;
@@ -295,7 +335,11 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 				continue; // fill-mode entries never touch depth in a deferrable pass
 			const bool opaque_compare = (st.blend_flags & BF_Z_COMPARE) != 0u && st.z_mode == 0;
 			const int own = 8 * hiz_pow2_floor(int(p.dz));
-			const bool reject = opaque_compare && cap_a != kInf && zmin > imax(cap_a, cap_z + own);
+			const int zlb = hiz_entry_z_lower_bound(b, fb, p, int(tx * kTileW), int(ty * kTileH));
+			const bool ideal = opaque_compare && cap_a != kInf && zmin > imax(cap_a, cap_z + own);
+			const bool reject = opaque_compare && cap_a != kInf && zlb >= 0 && zlb > imax(cap_a, cap_z + own);
+			dev->hiz[4] += ideal;
+			dev->hiz[5] += zlb > zmin;
 			bool passed = false;
 			for (int l = 0; l < 32; l++)
 				if ((cand[l] & DC_VALID) && defer_depth<SpecGeneric>(view[l], px[l], st, p.dz, p.dz_compressed, cand[l]))
@@ -318,9 +362,9 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 	}
 }
 
-void rdpb_hostsim_hiz_stats(rdpb_device *dev, unsigned long long out[4])
+void rdpb_hostsim_hiz_stats(rdpb_device *dev, unsigned long long out[6])
 {
-	for (int i = 0; i < 4; i++)
+	for (int i = 0; i < 6; i++)
 		out[i] = dev->hiz[i];
 }
 
