@@ -43,8 +43,9 @@ struct rdpb_device
 	unsigned long long counters[8] = {};
 	// RDP_HOSTSIM_HIZ=1 (test-only experiment, see hiz_check_tile): entries seen / rejected by the bound with the entry's Z
 	// bounded from its spans / with no passing fragment at all / rejected although a fragment passed (must stay 0) /
-	// rejected when the entry's smallest fragment Z is known exactly / span bound above a real fragment's Z (must stay 0)
-	unsigned long long hiz[6] = {};
+	// rejected when the entry's smallest fragment Z is known exactly / span bound above a real fragment's Z (must stay 0) /
+	// rejected with per-row instead of per-tile maxima (exact per-row Z) / of those, wrongly (must stay 0)
+	unsigned long long hiz[8] = {};
 	std::string error;
 
 	PassBuffers buffers()
@@ -279,8 +280,9 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 	{
 		if (!((coarse[group >> 5] >> (group & 31u)) & 1u))
 			continue;
-		// exact bounds at batch start
+		// exact bounds at batch start (whole tile, and per row for the per-row variant)
 		int cap_a = 0, cap_z = 0;
+		int row_a[4] = {}, row_z[4] = {};
 		for (int l = 0; l < 32; l++)
 		{
 			if (!inside[l])
@@ -299,6 +301,8 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 			}
 			cap_z = imax(cap_z, memory_z);
 			cap_a = unbounded ? kInf : imax(cap_a, memory_z + 8 * hiz_pow2_floor(memory_dz));
+			row_z[l >> 3] = imax(row_z[l >> 3], memory_z);
+			row_a[l >> 3] = unbounded ? kInf : imax(row_a[l >> 3], memory_z + 8 * hiz_pow2_floor(memory_dz));
 		}
 		uint32_t bits = fine[group];
 		while (bits)
@@ -309,6 +313,7 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 			const PassState &st = b.states[p.state_id];
 			uint32_t cand[32];
 			int zmin = kInf, zmax = -1;
+			int rmin[4] = { kInf, kInf, kInf, kInf }, rmax[4] = { -1, -1, -1, -1 };
 			bool any = false, fill = false;
 			for (int l = 0; l < 32; l++)
 			{
@@ -329,6 +334,8 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 				{
 					zmin = imin(zmin, int(cand[l] & DC_Z_MASK));
 					zmax = imax(zmax, int(cand[l] & DC_Z_MASK));
+					rmin[l >> 3] = imin(rmin[l >> 3], int(cand[l] & DC_Z_MASK));
+					rmax[l >> 3] = imax(rmax[l >> 3], int(cand[l] & DC_Z_MASK));
 				}
 			}
 			if (!any || fill)
@@ -338,6 +345,10 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 			const int zlb = hiz_entry_z_lower_bound(b, fb, p, int(tx * kTileW), int(ty * kTileH));
 			const bool ideal = opaque_compare && cap_a != kInf && zmin > imax(cap_a, cap_z + own);
 			const bool reject = opaque_compare && cap_a != kInf && zlb >= 0 && zlb > imax(cap_a, cap_z + own);
+			bool by_row = opaque_compare;
+			for (int r = 0; r < 4 && by_row; r++)
+				if (rmax[r] >= 0 && !(row_a[r] != kInf && rmin[r] > imax(row_a[r], row_z[r] + own)))
+					by_row = false;
 			dev->hiz[4] += ideal;
 			dev->hiz[5] += zlb > zmin;
 			bool passed = false;
@@ -348,7 +359,23 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 			dev->hiz[1] += reject;
 			dev->hiz[2] += !passed;
 			dev->hiz[3] += reject && passed;
+			dev->hiz[6] += by_row;
+			dev->hiz[7] += by_row && passed;
 			// what this entry may have written, for the later entries of the batch
+			if (!by_row && (st.blend_flags & BF_Z_UPDATE))
+			{
+				const int wdz = 1 << int(p.dz_compressed);
+				for (int r = 0; r < 4; r++)
+				{
+					if (rmax[r] < 0)
+						continue;
+					row_z[r] = imax(row_z[r], rmax[r]);
+					if (wdz == 0x8000)
+						row_a[r] = kInf;
+					else if (row_a[r] != kInf)
+						row_a[r] = imax(row_a[r], rmax[r] + 8 * imax(wdz << 1, 16));
+				}
+			}
 			if (!reject && (st.blend_flags & BF_Z_UPDATE))
 			{
 				cap_z = imax(cap_z, zmax);
@@ -362,9 +389,9 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 	}
 }
 
-void rdpb_hostsim_hiz_stats(rdpb_device *dev, unsigned long long out[6])
+void rdpb_hostsim_hiz_stats(rdpb_device *dev, unsigned long long out[8])
 {
-	for (int i = 0; i < 6; i++)
+	for (int i = 0; i < 8; i++)
 		out[i] = dev->hiz[i];
 }
 

@@ -22,9 +22,10 @@ def _stats(sbs):
     sbs.gpu.idle()
     lib = sbs.gpu.lib
     lib.rdp_b200_backend_device.restype = C.c_void_p
-    out = (C.c_ulonglong * 6)()
+    out = (C.c_ulonglong * 8)()
     lib.rdpb_hostsim_hiz_stats(C.c_void_p(lib.rdp_b200_backend_device(sbs.gpu._h)), out)
-    return dict(zip(("entries", "rejected", "hidden", "false_rejections", "rejected_with_exact_zmin", "unsound_z_bounds"), out))
+    return dict(zip(("entries", "rejected", "hidden", "false_rejections", "rejected_with_exact_zmin", "unsound_z_bounds",
+                     "rejected_per_row", "false_rejections_per_row"), out))
 
 
 @pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
@@ -42,7 +43,7 @@ def test_bound_never_rejects_a_visible_entry_on_c2(monkeypatch):
     finally:
         sbs.close()
     print(s)
-    assert s["false_rejections"] == 0 and s["unsound_z_bounds"] == 0
+    assert s["false_rejections"] == 0 and s["unsound_z_bounds"] == 0 and s["false_rejections_per_row"] == 0
     assert s["entries"] > 400000
     # about a third of the entries have no visible fragment; the conservative bound finds a good part of those
     assert 0.25 * s["entries"] < s["hidden"] < 0.40 * s["entries"]
@@ -63,4 +64,4 @@ def test_bound_never_rejects_a_visible_entry_in_depth_suites(name, monkeypatch):
     finally:
         sbs.close()
     assert s["entries"] > 0
-    assert s["false_rejections"] == 0 and s["unsound_z_bounds"] == 0
+    assert s["false_rejections"] == 0 and s["unsound_z_bounds"] == 0 and s["false_rejections_per_row"] == 0
