@@ -46,6 +46,9 @@ struct rdpb_device
 	// rejected when the entry's smallest fragment Z is known exactly / span bound above a real fragment's Z (must stay 0) /
 	// rejected with per-row instead of per-tile maxima (exact per-row Z) / of those, wrongly (must stay 0)
 	unsigned long long hiz[8] = {};
+	// same switch: (primitive, tile) entries a pass would have with other tile shapes, and the pixels inside the spans
+	// ([0] 8x4, [1] 16x4, [2] 8x8, [3] 16x8, [4] covered pixels)
+	unsigned long long tile_shapes[5] = {};
 	std::string error;
 
 	PassBuffers buffers()
@@ -389,6 +392,53 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 	}
 }
 
+// How many (primitive, tile) entries the pass has under other tile shapes: per-entry work (list gather, mask phase,
+// slot enumeration) scales with this count, lane utilisation with covered pixels / (entries * tile pixels).
+static void hiz_tile_shape_stats(rdpb_device *dev, const PassBuffers &b, const FbInfo &fb)
+{
+	static const int shapes[4][2] = { { 8, 4 }, { 16, 4 }, { 8, 8 }, { 16, 8 } };
+	for (uint32_t i = 0; i < fb.num_prims; i++)
+	{
+		const PrimSetup &p = b.prims[i];
+		if (p.flags & SF_NO_PIXELS)
+			continue;
+		for (int s = 0; s < 4; s++)
+		{
+			const int tw = shapes[s][0], th = shapes[s][1];
+			int row = -1, lo = 0, hi = -1;
+			for (int y = imax(p.line_lo, 0); y <= imin(p.line_hi, int(fb.height) - 1); y++)
+			{
+				const Span &sp = b.spans[p.span_base + uint32_t(y - p.line_lo)];
+				if (y / th != row)
+				{
+					if (hi >= lo)
+						dev->tile_shapes[s] += uint64_t(hi / tw - lo / tw + 1);
+					row = y / th;
+					lo = 1 << 20;
+					hi = -1;
+				}
+				if (!sp.valid)
+					continue;
+				const int xl = imax(int(sp.start_x), 0), xh = imin(int(sp.end_x), int(fb.width) - 1);
+				if (xl > xh)
+					continue;
+				lo = imin(lo, xl);
+				hi = imax(hi, xh);
+				if (s == 0)
+					dev->tile_shapes[4] += uint64_t(xh - xl + 1);
+			}
+			if (hi >= lo)
+				dev->tile_shapes[s] += uint64_t(hi / tw - lo / tw + 1);
+		}
+	}
+}
+
+void rdpb_hostsim_tile_shape_stats(rdpb_device *dev, unsigned long long out[5])
+{
+	for (int i = 0; i < 5; i++)
+		out[i] = dev->tile_shapes[i];
+}
+
 void rdpb_hostsim_hiz_stats(rdpb_device *dev, unsigned long long out[8])
 {
 	for (int i = 0; i < 8; i++)
@@ -417,6 +467,8 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 	const bool deferred = !sl && summary && getenv("RDP_HOSTSIM_DEFERRED") && deferrable_pass(*static_cast<const PassSummary *>(summary), fb);
 	dev->last_deferred = deferred;
 	const bool hiz = !sl && summary && getenv("RDP_HOSTSIM_HIZ") && deferrable_pass(*static_cast<const PassSummary *>(summary), fb);
+	if (hiz)
+		hiz_tile_shape_stats(dev, b, fb);
 	if (deferred)
 		dev->deferred_passes++;
 	for (uint32_t ty = 0; ty < fb.tiles_y; ty++)
