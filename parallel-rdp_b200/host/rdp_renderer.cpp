@@ -221,6 +221,8 @@ void Renderer::ensure_pass()
 	pass_reads_tmem = false;
 	reset_summary();
 	state_dirty = true;
+	memset(state_table, 0, sizeof(state_table));
+	current_state = 0;
 }
 
 void Renderer::reset_summary()
@@ -233,10 +235,38 @@ void Renderer::reset_summary()
 
 void Renderer::snapshot_state()
 {
-	PassState &dst = static_cast<PassState *>(pass.states)[num_states++];
+	// Build the snapshot in the next free slot; keep the slot only if the pass has no identical one yet.
+	PassState *states = static_cast<PassState *>(pass.states);
+	PassState &dst = states[num_states];
 	dst = regs;
 	finalize_state(dst);
 	state_dirty = false;
+
+	static_assert(sizeof(PassState) % 8 == 0, "hashed as 64-bit words");
+	uint64_t h = 0xcbf29ce484222325ull;
+	{
+		uint64_t words[sizeof(PassState) / 8];
+		memcpy(words, &dst, sizeof(PassState));
+		for (uint64_t w : words)
+			h = (h ^ w) * 0x100000001b3ull + (h >> 29);
+	}
+	uint32_t slot = uint32_t(h >> 20) & (StateTableSize - 1);
+	while (state_table[slot])
+	{
+		const uint32_t idx = state_table[slot] - 1u;
+		if (state_hash[idx] == h && memcmp(&states[idx], &dst, sizeof(PassState)) == 0)
+		{
+			current_state = idx;
+			const bool found_tlut = (states[idx].raster_flags & RF_TLUT) != 0;
+			for (int i = 0; i < 8; i++)
+				state_tile_kind_bits[i] = 1u << resolve_texel_kind(states[idx].tiles[i].fmt, states[idx].tiles[i].size, found_tlut);
+			return; // already counted in the summary
+		}
+		slot = (slot + 1) & (StateTableSize - 1);
+	}
+	state_table[slot] = uint16_t(num_states + 1u);
+	state_hash[num_states] = h;
+	current_state = num_states++;
 
 	// Fill-mode states are handled by every tile-kernel instantiation; only the others constrain the choice.
 	if (dst.raster_flags & RF_FILL)
@@ -351,7 +381,7 @@ void Renderer::draw_primitive(const uint32_t *words, unsigned count)
 		snapshot_state();
 	}
 
-	const PassState &st = static_cast<const PassState *>(pass.states)[num_states - 1];
+	const PassState &st = static_cast<const PassState *>(pass.states)[current_state];
 
 	int line_lo, line_hi;
 	primitive_line_range(words, st.raster_flags, st.sc_ylo, st.sc_yhi, line_lo, line_hi);
@@ -359,7 +389,7 @@ void Renderer::draw_primitive(const uint32_t *words, unsigned count)
 	PrimRecord &rec = static_cast<PrimRecord *>(pass.records)[num_prims];
 	rec.word_offset = place_words(words, count);
 	rec.span_base = num_spans;
-	rec.state_id = uint16_t(num_states - 1);
+	rec.state_id = uint16_t(current_state);
 	rec.tmem_instance = uint16_t(num_uploads);
 	rec.line_lo = int16_t(line_lo);
 	rec.line_hi = int16_t(line_hi);

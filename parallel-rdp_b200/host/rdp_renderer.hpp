@@ -138,6 +138,12 @@ private:
 	rdpb_pass_buffers pass = {};
 	bool pass_open = false;
 	uint32_t num_words = 0, num_prims = 0, num_states = 0, num_uploads = 0, num_spans = 0, num_jobs = 0;
+	// State snapshots are interned per pass (ref StateCache, rdp_data_structures.hpp:256-362): a stream that toggles between
+	// a few states does not grow the table.  Open addressing over the snapshot's hash; entries are index + 1.
+	enum { StateTableSize = 4096 };
+	uint16_t state_table[StateTableSize] = {};
+	uint64_t state_hash[rdpb::kMaxStatesPerPass] = {};
+	uint32_t current_state = 0;
 	bool pass_reads_tmem = false;
 	// Where the pass's command words come from: runs of host words and their offsets in the device word buffer.
 	// Staged runs point into pass.words; borrowed runs point into the caller's stream (gaps between primitives --

@@ -243,3 +243,33 @@ def test_validation_callback_reports_hardware_lockups():
         assert seen == []
     finally:
         p.close()
+
+
+@pytest.mark.skipif(not angrylion.available(), reason="oracle/_ref not built")
+def test_state_snapshots_are_interned_per_pass():
+    """A stream that toggles between two states for every primitive stays one pass: snapshots are interned (the reference's
+    StateCache, rdp_data_structures.hpp:256-362), not appended until the 1024-entry table forces a flush."""
+    from harness.rdp_builder import Builder
+    from sidebyside import SideBySide
+    sbs = SideBySide("hostsim")
+    try:
+        sbs.clear_rdram()
+        b = Builder()
+        b.set_color_image(0, 2, 0x100000, 320)
+        b.set_scissor(0, 0, 320, 240)
+        b.om.cycle_type = rb.CYCLE_FILL
+        b.touch_other_modes()
+        b.flush_other_modes()
+        rng = np.random.RandomState(5)
+        for i in range(3000):
+            b.set_fill_color(0xf801f801 if i & 1 else 0x07c107c1)
+            x, y = int(rng.randint(0, 300)), int(rng.randint(0, 220))
+            b.fill_rectangle(x, y, int(rng.randint(1, 20)), int(rng.randint(1, 20)))
+        b.sync_full()
+        before = sbs.gpu.pass_count()
+        sbs.run(b.take())
+        assert not sbs.compare_rdram()
+        assert sbs.gpu.primitive_count() >= 3000
+        assert sbs.gpu.pass_count() - before == 1
+    finally:
+        sbs.close()
