@@ -49,6 +49,9 @@ struct rdpb_device
 	// same switch: (primitive, tile) entries a pass would have with other tile shapes, and the pixels inside the spans
 	// ([0] 8x4, [1] 16x4, [2] 8x8, [3] 16x8, [4] covered pixels)
 	unsigned long long tile_shapes[5] = {};
+	// same switch: fragments entering phase A (coverage + Z) / surviving phase B (what phases C and D shade and blend) /
+	// fragments of entries the span-based bound rejects (phase A + B work it would save)
+	unsigned long long hiz_fragments[3] = {};
 	std::string error;
 
 	PassBuffers buffers()
@@ -356,8 +359,17 @@ static void hiz_check_tile(rdpb_device *dev, const PassBuffers &b, const FbInfo 
 			dev->hiz[5] += zlb > zmin;
 			bool passed = false;
 			for (int l = 0; l < 32; l++)
-				if ((cand[l] & DC_VALID) && defer_depth<SpecGeneric>(view[l], px[l], st, p.dz, p.dz_compressed, cand[l]))
+			{
+				if (!(cand[l] & DC_VALID))
+					continue;
+				dev->hiz_fragments[0]++;
+				dev->hiz_fragments[2] += reject;
+				if (defer_depth<SpecGeneric>(view[l], px[l], st, p.dz, p.dz_compressed, cand[l]))
+				{
 					passed = true;
+					dev->hiz_fragments[1]++;
+				}
+			}
 			dev->hiz[0]++;
 			dev->hiz[1] += reject;
 			dev->hiz[2] += !passed;
@@ -431,6 +443,12 @@ static void hiz_tile_shape_stats(rdpb_device *dev, const PassBuffers &b, const F
 				dev->tile_shapes[s] += uint64_t(hi / tw - lo / tw + 1);
 		}
 	}
+}
+
+void rdpb_hostsim_fragment_stats(rdpb_device *dev, unsigned long long out[3])
+{
+	for (int i = 0; i < 3; i++)
+		out[i] = dev->hiz_fragments[i];
 }
 
 void rdpb_hostsim_tile_shape_stats(rdpb_device *dev, unsigned long long out[5])
