@@ -106,6 +106,17 @@ void rdp_b200_set_quirks(rdp_b200_processor *p, int native_resolution_tex_rect, 
 /* Memory interaction, rdp_device.cpp:997-1036 */
 void *rdp_b200_begin_read_rdram(rdp_b200_processor *p);
 void rdp_b200_end_write_rdram(rdp_b200_processor *p);
+/* Extension (the CUDA replacement for VK_EXT_external_memory_host coherency; the reference's incoherent path tracks
+ * 1 KiB pages, rdp_renderer.cpp:2523-2583): the CPU wrote RDRAM bytes [offset, offset + size).  May be called at any
+ * time from the emulator thread.  The range is uploaded -- whole 1 KiB pages inside it, exact bytes at its two ends, so
+ * nothing the CPU did not declare ever overwrites what the GPU rendered next to it -- before the next command that
+ * makes the GPU read RDRAM (primitive, texture load, scan-out), in command order.  rdp_b200_end_write_rdram() is the
+ * same statement about the whole of RDRAM.  In the other direction every timeline signal copies back exactly the byte
+ * ranges passes rendered to since the previous one (asynchronously; rdp_b200_wait_for_timeline => they have landed).
+ * CPU writes that are never declared are not seen by the GPU: see INTEGRATION.md "RDRAM coherency". */
+void rdp_b200_mark_rdram_written(rdp_b200_processor *p, size_t offset, size_t size);
+/* out[0..3] = bytes / copies host -> device, bytes / copies device -> host since creation. */
+void rdp_b200_rdram_mirror_stats(rdp_b200_processor *p, uint64_t out4[4]);
 void *rdp_b200_begin_read_hidden_rdram(rdp_b200_processor *p);
 void rdp_b200_end_write_hidden_rdram(rdp_b200_processor *p);
 size_t rdp_b200_get_rdram_size(const rdp_b200_processor *p);
@@ -150,6 +161,10 @@ const char *rdp_b200_last_tile_variant(rdp_b200_processor *p);
 void rdp_b200_host_timing(rdp_b200_processor *p, double out3[3]);
 /* The backend device handle (rdpb_device*, include/rdp_b200_backend.h) for the measurement entry points. */
 void *rdp_b200_backend_device(rdp_b200_processor *p);
+/* Extension (stream farms: many processors per host): pins this processor's command thread to the given CPUs, e.g. the
+ * cores of the NUMA node its GPU hangs off.  Without it the thread inherits the creating thread's affinity mask (so a
+ * process pinned by its launcher needs nothing).  Returns 0, -1 when the platform cannot pin threads. */
+int rdp_b200_set_command_thread_affinity(rdp_b200_processor *p, const int *cpus, unsigned num_cpus);
 
 /* ---- Internal upscaling (RDP_B200_FLAG_UPSCALING_2X/4X/8X; ref rdp_device.hpp:43-51, rdp_renderer.cpp:545-600) -------
  * Eligible passes are rendered a second time at S x S the resolution into a separate upscaled domain of S*S RDRAM

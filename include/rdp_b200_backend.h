@@ -58,6 +58,9 @@ int rdpb_register_host_memory(rdpb_device *dev, void *ptr, size_t size);
 int rdpb_unregister_host_memory(rdpb_device *dev, void *ptr);
 int rdpb_rdram_write(rdpb_device *dev, uint32_t offset, const void *src, uint32_t size, int sync);
 int rdpb_rdram_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size, int sync);
+/* Asynchronous read-back of `num_ranges` {offset, size} pairs into host_base + offset on a side stream, behind all work
+ * submitted so far, with a timeline point after the copies: rdpb_wait(value) => the bytes are in host memory. */
+int rdpb_rdram_read_fenced(rdpb_device *dev, void *host_base, const uint32_t *ranges, uint32_t num_ranges, uint64_t value);
 int rdpb_hidden_write(rdpb_device *dev, uint32_t offset, const void *src, uint32_t size, int sync);
 int rdpb_hidden_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size, int sync);
 int rdpb_hidden_fill(rdpb_device *dev, uint8_t value);

@@ -49,6 +49,9 @@ def _bind(lib):
         "rdp_b200_set_validation_callback": (None, [P, P, P]),
         "rdp_b200_begin_read_rdram": (P, [P]),
         "rdp_b200_end_write_rdram": (None, [P]),
+        "rdp_b200_mark_rdram_written": (None, [P, SZ, SZ]),
+        "rdp_b200_rdram_mirror_stats": (None, [P, P]),
+        "rdp_b200_set_command_thread_affinity": (C.c_int, [P, P, C.c_uint]),
         "rdp_b200_begin_read_hidden_rdram": (P, [P]),
         "rdp_b200_end_write_hidden_rdram": (None, [P]),
         "rdp_b200_get_rdram_size": (SZ, [P]),
@@ -181,6 +184,19 @@ class CommandProcessor:
 
     def end_write_rdram(self):
         self.lib.rdp_b200_end_write_rdram(self._h)
+
+    def mark_rdram_written(self, offset: int, size: int):
+        """The CPU wrote self.rdram[offset:offset + size] (extension; see include/rdp_b200.h)."""
+        self.lib.rdp_b200_mark_rdram_written(self._h, offset, size)
+
+    def rdram_mirror_stats(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        self.lib.rdp_b200_rdram_mirror_stats(self._h, out)
+        return {"h2d_bytes": int(out[0]), "h2d_copies": int(out[1]), "d2h_bytes": int(out[2]), "d2h_copies": int(out[3])}
+
+    def set_command_thread_affinity(self, cpus):
+        arr = (C.c_int * len(cpus))(*[int(c) for c in cpus])
+        return self.lib.rdp_b200_set_command_thread_affinity(self._h, arr, len(cpus))
 
     def begin_read_hidden_rdram(self) -> np.ndarray:
         p = self.lib.rdp_b200_begin_read_hidden_rdram(self._h)

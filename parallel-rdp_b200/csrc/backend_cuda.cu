@@ -1381,6 +1381,11 @@ struct rdpb_device
 	uint32_t vi_lo = 0, vi_hi = 0;   // RDRAM bytes it reads (lo >= hi: unknown)
 	cudaEvent_t readback_done[2] = {};
 	bool readback_in_flight[2] = {};
+	// RDRAM read-back (rdpb_rdram_read_fenced) on stream_down: forked behind the compute stream; an operation that
+	// writes RDRAM inside [rb_lo, rb_hi) while the copies may still be running waits for them.
+	cudaEvent_t rdram_rb_fork = nullptr, rdram_rb_done = nullptr;
+	bool rdram_rb_busy = false;
+	uint32_t rdram_rb_lo = 0, rdram_rb_hi = 0;
 	unsigned staging_index = 0;
 
 	uint32_t *d_words[kStagingSlots] = {};  // device-side input slots, one per staging slot
@@ -1426,7 +1431,10 @@ struct rdpb_device
 	bool vi_lines_in_flight[2] = {};
 
 	std::mutex timeline_lock;
-	std::deque<std::pair<uint64_t, cudaEvent_t>> timeline;
+	// Points recorded on the compute stream (timeline signals) and on the read-back stream (scan-out fences): each
+	// queue is in its own stream's order, so retiring everything older than a matched point is only valid per queue.
+	enum { kTimelineCompute = 0, kTimelineDown = 1, kTimelineQueues = 2 };
+	std::deque<std::pair<uint64_t, cudaEvent_t>> timeline[kTimelineQueues];
 	std::deque<cudaEvent_t> free_events;
 
 	// measurement plumbing
@@ -1555,6 +1563,41 @@ static bool writes_scanout_range(const rdpb_device *dev, const FbInfo &fb)
 	return (c_lo < dev->vi_hi && dev->vi_lo < c_hi) || (d_lo < dev->vi_hi && dev->vi_lo < d_hi);
 }
 
+// Byte range [lo, hi) of RDRAM a pass rendering into `fb` can write (colour and depth image); false: wraps, unknown.
+static bool pass_write_range(const FbInfo &fb, uint64_t &lo, uint64_t &hi)
+{
+	const uint64_t pixels = uint64_t(fb.width >> fb.scale_log2) * (fb.height >> fb.scale_log2);
+	const uint32_t bpp = fb.fmt == FB_RGBA8888 ? 4u : ((fb.fmt == FB_RGBA5551 || fb.fmt == FB_IA88) ? 2u : 1u);
+	const uint64_t c_lo = fb.color_addr, c_hi = c_lo + pixels * bpp;
+	const uint64_t d_lo = fb.depth_addr, d_hi = d_lo + pixels * 2u;
+	lo = std::min(c_lo, d_lo);
+	hi = std::max(c_hi, d_hi);
+	return c_hi <= fb.rdram_size && d_hi <= fb.rdram_size;
+}
+
+// Make the compute stream wait for an RDRAM read-back still in flight if the bytes [lo, hi) about to be written
+// overlap what it copies (lo >= hi: unknown, always wait).
+static int join_rdram_readback(rdpb_device *dev, uint64_t lo, uint64_t hi)
+{
+	if (!dev->rdram_rb_busy)
+		return 0;
+	if (lo < hi && (hi <= dev->rdram_rb_lo || dev->rdram_rb_hi <= lo))
+		return 0;
+	CK(cudaStreamWaitEvent(dev->stream, dev->rdram_rb_done, 0));
+	dev->rdram_rb_busy = false;
+	return 0;
+}
+
+static int join_rdram_readback(rdpb_device *dev, const FbInfo &fb)
+{
+	uint64_t lo = 0, hi = 0;
+	if (!dev->rdram_rb_busy)
+		return 0;
+	if (!pass_write_range(fb, lo, hi))
+		lo = hi = 0;
+	return join_rdram_readback(dev, lo, hi);
+}
+
 // ---- profiling helpers ---------------------------------------------------------------------------------------
 static int prof_begin(rdpb_device *dev, int kind, cudaStream_t stream = nullptr)
 {
@@ -1649,6 +1692,8 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		// The first kernels of a pass (set-up, spans) never write RDRAM; this one does.
 		if (writes_scanout_range(dev, op.fb) && join_vi(dev) != 0)
 			return -1;
+		if (join_rdram_readback(dev, op.fb) != 0)
+			return -1;
 		if (join_front(dev, op.parity & 1u) != 0)
 			return -1;
 		const int s = prof_begin(dev, op.variant == &kFillPassVariant ? RDPB_KERNEL_FILL_PASS : RDPB_KERNEL_TILES);
@@ -1693,6 +1738,8 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	case GOP_UPSCALE_SYNC:
 	{
 		if (writes_scanout_range(dev, op.fb) && join_vi(dev) != 0)
+			return -1;
+		if (join_rdram_readback(dev, op.fb) != 0)
 			return -1;
 		UpscaleSync u;
 		u.rdram = dev->rdram;
@@ -1868,6 +1915,9 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	auto *dev = new rdpb_device;
 	dev->ordinal = cuda_ordinal;
 	dev->rdram_size = rdram_size;
+	// Every kernel addresses hidden RDRAM with the mask (rdram_size >> 1) - 1 whatever the caller asked for: the device
+	// buffer is never smaller than that (the caller-visible size only bounds the begin_read / end_write copies).
+	hidden_size = std::max(hidden_size, rdram_size >> 1);
 	dev->hidden_size = hidden_size;
 	dev->debug_summary = getenv("RDP_B200_DEBUG_PASSES") != nullptr;
 
@@ -1909,6 +1959,8 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		need(cudaEventCreateWithFlags(&dev->scratch_free[q], cudaEventDisableTiming), "cudaEventCreate");
 	}
 	need(cudaEventCreateWithFlags(&dev->host_write_done, cudaEventDisableTiming), "cudaEventCreate");
+	need(cudaEventCreateWithFlags(&dev->rdram_rb_fork, cudaEventDisableTiming), "cudaEventCreate");
+	need(cudaEventCreateWithFlags(&dev->rdram_rb_done, cudaEventDisableTiming), "cudaEventCreate");
 	for (auto &e : dev->readback_done)
 		need(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
 	need(cudaMalloc(&dev->rdram, rdram_size), "cudaMalloc rdram");
@@ -2036,8 +2088,9 @@ void rdpb_device_destroy(rdpb_device *dev)
 		if (dev->kernels_done[i])
 			cudaEventDestroy(dev->kernels_done[i]);
 	}
-	for (auto &t : dev->timeline)
-		cudaEventDestroy(t.second);
+	for (auto &q : dev->timeline)
+		for (auto &t : q)
+			cudaEventDestroy(t.second);
 	for (auto &e : dev->free_events)
 		cudaEventDestroy(e);
 	for (auto &p : dev->prof_pool)
@@ -2062,6 +2115,10 @@ void rdpb_device_destroy(rdpb_device *dev)
 	}
 	if (dev->host_write_done)
 		cudaEventDestroy(dev->host_write_done);
+	if (dev->rdram_rb_fork)
+		cudaEventDestroy(dev->rdram_rb_fork);
+	if (dev->rdram_rb_done)
+		cudaEventDestroy(dev->rdram_rb_done);
 	for (auto &e : dev->readback_done)
 		if (e)
 			cudaEventDestroy(e);
@@ -2101,6 +2158,8 @@ static int copy_common(rdpb_device *dev, void *dst, const void *src, size_t size
 	use_device(dev);
 	// Slow-path copies (RDRAM / hidden RDRAM up and down, synchronous image reads): order them behind the scan-out too.
 	if (join_vi(dev) != 0)
+		return -1;
+	if (kind == cudaMemcpyHostToDevice && join_rdram_readback(dev, 0, 0) != 0)
 		return -1;
 	CK(cudaMemcpyAsync(dst, src, size, kind, dev->stream));
 	if (kind == cudaMemcpyHostToDevice && dev->stream_front != dev->stream)
@@ -2468,6 +2527,41 @@ int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint
 	return signal_on(dev, fence_value, dev->stream_down);
 }
 
+// Asynchronous copy of `num_ranges` {offset, size} byte ranges of RDRAM into host_base + offset on the read-back stream,
+// behind everything the compute stream has been given so far, followed by a timeline point there: rdpb_wait(value)
+// returns once the bytes are in host memory.  Rendering goes on meanwhile; only an operation that writes the same
+// bytes waits for the copies (join_rdram_readback).
+int rdpb_rdram_read_fenced(rdpb_device *dev, void *host_base, const uint32_t *ranges, uint32_t num_ranges, uint64_t value)
+{
+	use_device(dev);
+	// The scan-out in flight only reads RDRAM: no need to wait for it.  A previous read-back is on the same stream.
+	CK(cudaEventRecord(dev->rdram_rb_fork, dev->stream));
+	CK(cudaStreamWaitEvent(dev->stream_down, dev->rdram_rb_fork, 0));
+	uint32_t lo = ~0u, hi = 0;
+	for (uint32_t i = 0; i < num_ranges; i++)
+	{
+		const uint32_t offset = ranges[2 * i], size = ranges[2 * i + 1];
+		if (!size || uint64_t(offset) + size > dev->rdram_size)
+			continue;
+		CK(cudaMemcpyAsync(static_cast<uint8_t *>(host_base) + offset, dev->rdram + offset, size, cudaMemcpyDeviceToHost, dev->stream_down));
+		lo = std::min(lo, offset);
+		hi = std::max(hi, offset + size);
+	}
+	if (dev->stream_down != dev->stream)
+	{
+		CK(cudaEventRecord(dev->rdram_rb_done, dev->stream_down));
+		if (dev->rdram_rb_busy)
+		{
+			lo = std::min(lo, dev->rdram_rb_lo);
+			hi = std::max(hi, dev->rdram_rb_hi);
+		}
+		dev->rdram_rb_busy = true;
+		dev->rdram_rb_lo = lo;
+		dev->rdram_rb_hi = hi;
+	}
+	return signal_on(dev, value, dev->stream_down);
+}
+
 int rdpb_signal(rdpb_device *dev, uint64_t value)
 {
 	return signal_on(dev, value, dev->stream);
@@ -2486,7 +2580,7 @@ static int signal_on(rdpb_device *dev, uint64_t value, cudaStream_t stream)
 	else
 		CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
 	CK(cudaEventRecord(ev, stream));
-	dev->timeline.emplace_back(value, ev);
+	dev->timeline[stream == dev->stream ? rdpb_device::kTimelineCompute : rdpb_device::kTimelineDown].emplace_back(value, ev);
 	return 0;
 }
 
@@ -2495,19 +2589,27 @@ int rdpb_wait(rdpb_device *dev, uint64_t value)
 	use_device(dev);
 	cudaEvent_t ev = nullptr;
 	{
-		// Points are recorded in stream order, so everything queued before `value` completes no later than it.
-		// Values come from independent counters (timeline, scan-out fences): match by identity, not by magnitude.
+		// Within one queue points are recorded in stream order, so everything queued before `value` on the same stream
+		// completes no later than it.  Values come from independent counters (timeline, scan-out fences): match by
+		// identity, not by magnitude.  Points of the other stream are left alone -- a scan-out fence recorded before an
+		// idle() has not necessarily been reached when the compute stream's point has.
 		std::lock_guard<std::mutex> holder{dev->timeline_lock};
-		size_t found = dev->timeline.size();
-		for (size_t i = 0; i < dev->timeline.size(); i++)
-			if (dev->timeline[i].first == value)
-				found = i;
-		if (found == dev->timeline.size())
+		for (auto &queue : dev->timeline)
+		{
+			size_t found = queue.size();
+			for (size_t i = 0; i < queue.size(); i++)
+				if (queue[i].first == value)
+					found = i;
+			if (found == queue.size())
+				continue;
+			ev = queue[found].second;
+			for (size_t i = 0; i < found; i++)
+				dev->free_events.push_back(queue[i].second);
+			queue.erase(queue.begin(), queue.begin() + found + 1);
+			break;
+		}
+		if (!ev)
 			return 0; // already retired
-		ev = dev->timeline[found].second;
-		for (size_t i = 0; i < found; i++)
-			dev->free_events.push_back(dev->timeline[i].second);
-		dev->timeline.erase(dev->timeline.begin(), dev->timeline.begin() + found + 1);
 	}
 	CK(cudaEventSynchronize(ev));
 	std::lock_guard<std::mutex> holder{dev->timeline_lock};
@@ -2524,6 +2626,7 @@ int rdpb_sync(rdpb_device *dev)
 	CK(cudaStreamSynchronize(dev->stream_vi));
 	CK(cudaStreamSynchronize(dev->stream_down));
 	dev->vi_busy = false;
+	dev->rdram_rb_busy = false;
 	return 0;
 }
 

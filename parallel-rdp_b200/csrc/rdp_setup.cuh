@@ -63,10 +63,6 @@ RDP_HD uint32_t command_length_words(uint32_t op)
 	case OP_TRI_SHADE_TEX_Z: return 44;
 	case OP_TEX_RECT:
 	case OP_TEX_RECT_FLIP: return 4;
-	case OP_META_SIGNAL_TIMELINE: return 3;
-	case OP_META_SCANOUT: return 3;
-	case OP_META_FLUSH:
-	case OP_META_IDLE: return 1;
 	default: return 2;
 	}
 }

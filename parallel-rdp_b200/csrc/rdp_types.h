@@ -45,11 +45,8 @@ enum : uint32_t
 enum Op : uint32_t
 {
 	OP_NOP = 0x00,
-	OP_META_SIGNAL_TIMELINE = 0x01,
-	OP_META_FLUSH = 0x02,
-	OP_META_IDLE = 0x03,
-	OP_META_SET_QUIRKS = 0x04,
-	OP_META_SCANOUT = 0x05, // words[1..2] = pointer to a heap-allocated scan-out request (command thread executes it)
+	// 0x01..0x07 are no-ops on hardware, two words like every other state command.  (The reference uses 1..4 as its
+	// in-band Meta* commands; here meta operations are a ring record kind of their own, command_ring.hpp.)
 	OP_TRI_FILL = 0x08,
 	OP_TRI_FILL_Z = 0x09,
 	OP_TRI_TEX = 0x0a,

@@ -99,6 +99,8 @@ void rdp_b200_set_quirks(rdp_b200_processor *p, int native_resolution_tex_rect, 
 
 void *rdp_b200_begin_read_rdram(rdp_b200_processor *p) { return p->impl.begin_read_rdram(); }
 void rdp_b200_end_write_rdram(rdp_b200_processor *p) { p->impl.end_write_rdram(); }
+void rdp_b200_mark_rdram_written(rdp_b200_processor *p, size_t offset, size_t size) { p->impl.mark_rdram_written(offset, size); }
+void rdp_b200_rdram_mirror_stats(rdp_b200_processor *p, uint64_t out4[4]) { p->impl.get_rdram_mirror_stats(out4); }
 void *rdp_b200_begin_read_hidden_rdram(rdp_b200_processor *p) { return p->impl.begin_read_hidden_rdram(); }
 void rdp_b200_end_write_hidden_rdram(rdp_b200_processor *p) { p->impl.end_write_hidden_rdram(); }
 size_t rdp_b200_get_rdram_size(const rdp_b200_processor *p) { return p->impl.get_rdram_size(); }
@@ -168,6 +170,16 @@ uint64_t rdp_b200_primitive_count(rdp_b200_processor *p) { return p->impl.get_pr
 uint64_t rdp_b200_pass_count(rdp_b200_processor *p) { return p->impl.get_pass_counter(); }
 void rdp_b200_host_timing(rdp_b200_processor *p, double out3[3]) { p->impl.get_host_timing(out3); }
 void *rdp_b200_backend_device(rdp_b200_processor *p) { return p->impl.get_backend_device(); }
+int rdp_b200_set_command_thread_affinity(rdp_b200_processor *p, const int *cpus, unsigned num_cpus)
+{
+#if defined(__linux__)
+	p->impl.set_command_thread_affinity(std::vector<int>(cpus, cpus + num_cpus));
+	return 0;
+#else
+	(void)p; (void)cpus; (void)num_cpus;
+	return -1;
+#endif
+}
 const char *rdp_b200_last_tile_variant(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_last_tile_variant(p->impl.get_backend_device()) : ""; }
 void *rdp_b200_cuda_stream(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_stream(p->impl.get_backend_device()) : nullptr; }
 

@@ -45,7 +45,9 @@ CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, 
 		host_rdram = owned_rdram.get();
 		host_rdram_registered = rdpb_register_host_memory(device, host_rdram, rdram_size) == 0;
 	}
-	host_rdram_dirty = true;
+	mirror.init(rdram_size);
+	mirror.mark_all_written();
+	renderer.set_rdram_mirror(&mirror);
 
 	host_hidden.assign(hidden_size, 0x03);
 	rdpb_hidden_fill(device, 0x03);
@@ -281,35 +283,6 @@ void CommandProcessor::enqueue_command_direct(unsigned num_words, const uint32_t
 	const uint32_t op = (words[0] >> 24) & 63u;
 	switch (op)
 	{
-	case OP_META_SIGNAL_TIMELINE:
-	{
-		flush_and_signal();
-		const uint64_t value = words[1] | (uint64_t(words[2]) << 32);
-		readback_gpu_writes(false);
-		rdpb_signal(device, value);
-		signalled_timeline.store(value, std::memory_order_release);
-		break;
-	}
-	case OP_META_FLUSH:
-		flush_and_signal();
-		break;
-	case OP_META_IDLE:
-	{
-		// The producer went quiet: kick recorded work so latency stays bounded (rdp_renderer.cpp:2383-2392).
-		// scanout() drives the renderer from the caller's thread; never race it.
-		std::unique_lock<std::mutex> holder{idle_lock, std::try_to_lock};
-		if (holder.owns_lock())
-			renderer.flush_queues();
-		break;
-	}
-	case OP_META_SET_QUIRKS:
-		quirks.u.words[0] = words[1];
-		apply_quirks();
-		break;
-	case OP_META_SCANOUT:
-		execute_scanout_request(reinterpret_cast<ScanoutRequest *>(uintptr_t(uint64_t(words[1]) | (uint64_t(words[2]) << 32))));
-		break;
-
 	case OP_TRI_FILL: case OP_TRI_FILL_Z: case OP_TRI_TEX: case OP_TRI_TEX_Z:
 	case OP_TRI_SHADE: case OP_TRI_SHADE_Z: case OP_TRI_SHADE_TEX: case OP_TRI_SHADE_TEX_Z:
 	case OP_TEX_RECT: case OP_TEX_RECT_FLIP: case OP_FILL_RECT:
@@ -338,9 +311,66 @@ void CommandProcessor::enqueue_command_direct(unsigned num_words, const uint32_t
 	case OP_SET_TEXTURE_IMAGE: op_set_texture_image(words); break;
 	case OP_SET_MASK_IMAGE: op_set_mask_image(words); break;
 	case OP_SET_COLOR_IMAGE: op_set_color_image(words); break;
-	default: break; // Nop, SyncLoad/Pipe/Tile and undefined opcodes
+	default: break; // Nop (opcodes 0..7 included), SyncLoad/Pipe/Tile and undefined opcodes
 	}
 	(void)num_words;
+}
+
+// Meta records arrive through CommandRing::enqueue_meta (or directly in single-threaded mode): a record kind of
+// their own, so no command word a guest or a dump file supplies can become one (the reference's Op::Meta*,
+// rdp_device.cpp:899-927, travel in-band but carry no pointers).
+void CommandProcessor::execute_meta(RingMeta kind, const uint32_t *payload, unsigned num_words)
+{
+	switch (kind)
+	{
+	case RingMeta::SignalTimeline:
+	{
+		if (num_words < 2)
+			break;
+		flush_and_signal();
+		const uint64_t value = payload[0] | (uint64_t(payload[1]) << 32);
+		// Device RDRAM first takes what the CPU declared (so a read-back never returns bytes older than the host's), then
+		// the rendered ranges travel back behind everything submitted so far; the point is recorded behind the copies.
+		sync_host_rdram_to_device();
+		if (!readback_gpu_writes(value, false))
+			rdpb_signal(device, value);
+		signalled_timeline.store(value, std::memory_order_release);
+		break;
+	}
+	case RingMeta::Flush:
+		flush_and_signal();
+		break;
+	case RingMeta::Idle:
+	{
+		// The producer went quiet: kick recorded work so latency stays bounded (rdp_renderer.cpp:2383-2392).
+		// scanout() drives the renderer from the caller's thread; never race it.
+		std::unique_lock<std::mutex> holder{idle_lock, std::try_to_lock};
+		if (holder.owns_lock())
+			renderer.flush_queues();
+		break;
+	}
+	case RingMeta::SetQuirks:
+		if (num_words < 1)
+			break;
+		quirks.u.words[0] = payload[0];
+		apply_quirks();
+		break;
+	case RingMeta::Scanout:
+		if (num_words < 2)
+			break;
+		execute_scanout_request(reinterpret_cast<ScanoutRequest *>(uintptr_t(uint64_t(payload[0]) | (uint64_t(payload[1]) << 32))));
+		break;
+	}
+}
+
+void CommandProcessor::enqueue_meta(RingMeta kind, unsigned num_words, const uint32_t *payload)
+{
+	if (!is_supported)
+		return;
+	if (single_threaded_processing)
+		execute_meta(kind, payload, num_words);
+	else
+		ring.enqueue_meta(kind, num_words, payload);
 }
 
 void CommandProcessor::enqueue_command_inner(unsigned num_words, const uint32_t *words)
@@ -454,40 +484,69 @@ void CommandProcessor::apply_quirks()
 
 void CommandProcessor::set_quirks(const Quirks &q)
 {
-	const uint32_t words[2] = { uint32_t(OP_META_SET_QUIRKS) << 24, q.u.words[0] };
-	enqueue_command_inner(2, words);
+	enqueue_meta(RingMeta::SetQuirks, 1, &q.u.words[0]);
 }
 
 // ---------------------------------------------------------------------------------------------
-// RDRAM mirror.  The caller's RDRAM range is the CPU-side copy; the GPU renders into a device buffer.
-// end_write_rdram() marks the CPU copy as newer; it is uploaded before the next GPU access.  Timeline signals
-// copy back what the GPU wrote.  (Replaces VK_EXT_external_memory_host / the reference's incoherent path.)
+// RDRAM mirror (host/rdram_mirror.hpp).  The caller's RDRAM range is the CPU-side copy; the GPU renders into a device
+// buffer.  Replaces VK_EXT_external_memory_host / the reference's incoherent path (rdp_renderer.cpp:2523-2907,
+// rdp_device.cpp:1195-1258).
+//   host -> device: what the CPU declared written (mark_rdram_written: 1 KiB pages + exact partial pages;
+//                   end_write_rdram: everything) is uploaded before the next command that can make the GPU read
+//                   RDRAM -- a primitive, a texture load, a scan-out -- in command order.
+//   device -> host: timeline signals copy back exactly the byte ranges passes rendered to, on the read-back stream.
 // ---------------------------------------------------------------------------------------------
 void CommandProcessor::sync_host_rdram_to_device()
 {
-	if (!host_rdram_dirty)
+	if (!mirror.has_host_writes())
 		return;
-	if (renderer.has_pending_gpu_writes())
-		readback_gpu_writes(true);
-	rdpb_rdram_write(device, 0, host_rdram, uint32_t(rdram_size), host_rdram_registered ? 0 : 1);
-	host_rdram_dirty = false;
+	// "Anything may have changed" would upload stale host bytes over pixels the GPU has not returned yet: fetch them first.
+	if (mirror.whole_range_dirty() && mirror.has_gpu_writes())
+		readback_gpu_writes(0, true);
+	mirror.consume_host_writes([&](uint32_t offset, uint32_t size) {
+		rdpb_rdram_write(device, offset, host_rdram + offset, size, host_rdram_registered ? 0 : 1);
+	});
 }
 
-void CommandProcessor::readback_gpu_writes(bool wait)
+// Copies the ranges passes rendered to since the last read-back into the caller's RDRAM.  With a fence value the copies
+// run on the read-back stream and the timeline point is recorded behind them (returns true); otherwise they are
+// synchronous on the compute stream.
+bool CommandProcessor::readback_gpu_writes(uint64_t fence_value, bool wait)
 {
-	if (renderer.has_pending_gpu_writes())
+	if (!mirror.has_gpu_writes())
 	{
-		uint32_t lo, hi;
-		renderer.get_pending_gpu_write_range(lo, hi);
-		lo &= ~63u;
-		hi = (hi + 63u) & ~63u;
-		if (hi > rdram_size)
-			hi = uint32_t(rdram_size);
-		rdpb_rdram_read(device, lo, host_rdram + lo, hi - lo, (wait || !host_rdram_registered) ? 1 : 0);
-		renderer.clear_pending_gpu_writes();
+		if (wait)
+			rdpb_sync(device);
+		return false;
 	}
-	else if (wait)
-		rdpb_sync(device);
+	if (fence_value && host_rdram_registered && !wait)
+	{
+		std::vector<uint32_t> ranges;
+		mirror.consume_gpu_writes([&](uint32_t offset, uint32_t size) {
+			ranges.push_back(offset);
+			ranges.push_back(size);
+		});
+		return rdpb_rdram_read_fenced(device, host_rdram, ranges.data(), uint32_t(ranges.size() / 2), fence_value) == 0;
+	}
+	mirror.consume_gpu_writes([&](uint32_t offset, uint32_t size) {
+		rdpb_rdram_read(device, offset, host_rdram + offset, size, 0);
+	});
+	rdpb_sync(device);
+	return false;
+}
+
+void CommandProcessor::mark_rdram_written(size_t offset, size_t size)
+{
+	mirror.mark_written(offset, size);
+}
+
+void CommandProcessor::get_rdram_mirror_stats(uint64_t out[4]) const
+{
+	const RdramMirror::Stats st = mirror.get_stats();
+	out[0] = st.h2d_bytes;
+	out[1] = st.h2d_copies;
+	out[2] = st.d2h_bytes;
+	out[3] = st.d2h_copies;
 }
 
 void CommandProcessor::flush_and_signal()
@@ -502,9 +561,9 @@ void *CommandProcessor::begin_read_rdram()
 
 void CommandProcessor::end_write_rdram()
 {
-	// Only meaningful while idle (as in the reference, where it unmaps the buffer).
+	// Only meaningful while idle (as in the reference, where it unmaps the buffer): everything may have changed.
 	drain_command_ring();
-	host_rdram_dirty = true;
+	mirror.mark_all_written();
 }
 
 void *CommandProcessor::begin_read_hidden_rdram()
@@ -551,15 +610,14 @@ void CommandProcessor::drain_command_ring()
 
 void CommandProcessor::flush()
 {
-	const uint32_t words[1] = { uint32_t(OP_META_FLUSH) << 24 };
-	enqueue_command_inner(1, words);
+	enqueue_meta(RingMeta::Flush, 0, nullptr);
 }
 
 uint64_t CommandProcessor::signal_timeline()
 {
 	timeline_value++;
-	const uint32_t words[3] = { uint32_t(OP_META_SIGNAL_TIMELINE) << 24, uint32_t(timeline_value), uint32_t(timeline_value >> 32) };
-	enqueue_command_inner(3, words);
+	const uint32_t words[2] = { uint32_t(timeline_value), uint32_t(timeline_value >> 32) };
+	enqueue_meta(RingMeta::SignalTimeline, 2, words);
 	return timeline_value;
 }
 
@@ -568,12 +626,8 @@ void CommandProcessor::wait_for_timeline(uint64_t index)
 	if (!is_supported)
 		return;
 	// The command thread records the timeline point in stream order; wait for it to be recorded, then for the GPU.
-	while (signalled_timeline.load(std::memory_order_acquire) < index)
-	{
-		if (single_threaded_processing)
-			break;
-		std::this_thread::yield();
-	}
+	if (!single_threaded_processing && ring.is_running())
+		ring.wait_until_at_least(signalled_timeline, index);
 	rdpb_wait(device, index);
 }
 
@@ -674,9 +728,9 @@ uint64_t CommandProcessor::scanout_async(void *rgba, size_t capacity_pixels, uns
 	req->fence = (1ull << 63) | ++scanout_fence_counter; // own namespace, never collides with the timeline
 
 	const uint64_t ptr = uint64_t(reinterpret_cast<uintptr_t>(req));
-	const uint32_t words[3] = { uint32_t(OP_META_SCANOUT) << 24, uint32_t(ptr), uint32_t(ptr >> 32) };
+	const uint32_t words[2] = { uint32_t(ptr), uint32_t(ptr >> 32) };
 	const uint64_t fence = req->fence;
-	enqueue_command_inner(3, words);
+	enqueue_meta(RingMeta::Scanout, 2, words);
 	return fence;
 }
 
@@ -718,16 +772,8 @@ void CommandProcessor::scanout_wait(uint64_t fence)
 		return;
 	// The command thread records the fence in stream order; wait for it to get there, then for the GPU.
 	const uint64_t index = fence & ~(1ull << 63);
-	unsigned spins = 0;
-	while (recorded_scanout_fence.load(std::memory_order_acquire) < index)
-	{
-		if (single_threaded_processing)
-			break;
-		if (++spins < 2000)
-			std::this_thread::yield();
-		else
-			std::this_thread::sleep_for(std::chrono::microseconds(20));
-	}
+	if (!single_threaded_processing && ring.is_running())
+		ring.wait_until_at_least(recorded_scanout_fence, index);
 	rdpb_wait(device, fence);
 }
 

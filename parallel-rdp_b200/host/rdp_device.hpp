@@ -99,6 +99,11 @@ public:
 	// Interact with memory.  Pointers are valid while the processor is idle.
 	void *begin_read_rdram();
 	void end_write_rdram();
+	// Extension: the CPU wrote [offset, offset + size) of RDRAM (may be called at any time, from the emulator thread).
+	// Uploaded -- whole 1 KiB pages inside the range, exact bytes at its ends -- before the next command that makes the
+	// GPU read RDRAM.  end_write_rdram() is the same statement about the whole range.
+	void mark_rdram_written(size_t offset, size_t size);
+	void get_rdram_mirror_stats(uint64_t out[4]) const; // bytes / copies host -> device, bytes / copies device -> host
 	void *begin_read_hidden_rdram();
 	void end_write_hidden_rdram();
 	size_t get_rdram_size() const;
@@ -133,6 +138,7 @@ public:
 	// Seconds the command thread spent [0] executing ring records in total, [1] inside pass submission
 	// (Renderer::flush_queues), [2] inside queued scan-outs.  [0] - [1] - [2] is command parsing / pass recording.
 	void get_host_timing(double out[3]) const;
+	void set_command_thread_affinity(const std::vector<int> &cpus) { ring.set_affinity(cpus); }
 	void add_ring_busy_ns(uint64_t ns) { ring_busy_ns.fetch_add(ns, std::memory_order_relaxed); }
 
 private:
@@ -158,7 +164,7 @@ private:
 	void dump_begin_command_list();
 	void dump_end_frame();
 
-	std::atomic<bool> host_rdram_dirty{true}; // CPU wrote RDRAM since the last upload
+	RdramMirror mirror; // what the CPU wrote since the last upload / what passes rendered since the last read-back
 	std::mutex idle_lock;
 
 	Renderer renderer;
@@ -178,9 +184,11 @@ private:
 	void apply_quirks();
 
 	void enqueue_command_inner(unsigned num_words, const uint32_t *words);
+	void enqueue_meta(RingMeta kind, unsigned num_words, const uint32_t *payload);
+	void execute_meta(RingMeta kind, const uint32_t *payload, unsigned num_words);
 	void drain_command_ring();
 	void sync_host_rdram_to_device();
-	void readback_gpu_writes(bool wait);
+	bool readback_gpu_writes(uint64_t fence_value, bool wait);
 	void flush_and_signal();
 
 	void op_set_color_image(const uint32_t *w);

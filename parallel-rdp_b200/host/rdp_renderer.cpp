@@ -438,19 +438,8 @@ void Renderer::draw_primitive(const uint32_t *words, unsigned count)
 
 void Renderer::note_gpu_write(uint32_t addr, uint32_t bytes)
 {
-	if (!bytes)
-		return;
-	addr &= uint32_t(rdram_size - 1);
-	uint32_t end = addr + bytes;
-	if (end > rdram_size)
-	{
-		// Wrapped: be conservative.
-		gpu_dirty_lo = 0;
-		gpu_dirty_hi = uint32_t(rdram_size);
-		return;
-	}
-	gpu_dirty_lo = std::min(gpu_dirty_lo, addr);
-	gpu_dirty_hi = std::max(gpu_dirty_hi, end);
+	if (mirror)
+		mirror->note_gpu_write(addr, bytes);
 }
 
 void Renderer::flush_queues()

@@ -6,6 +6,7 @@
 // dirty flag instead of memcmp-searched caches, and a pass holds up to 16 Ki primitives.
 #pragma once
 #include "rdp_b200_backend.h"
+#include "rdram_mirror.hpp"
 #include "rdp_types.h"
 #include "rdp_spec.h"
 #include <stddef.h>
@@ -108,9 +109,8 @@ public:
 	void load_tile(uint32_t tile, const LoadTileInfo &info);
 
 	void flush_queues();
-	bool has_pending_gpu_writes() const { return gpu_dirty_hi > gpu_dirty_lo; }
-	void get_pending_gpu_write_range(uint32_t &lo, uint32_t &hi) const { lo = gpu_dirty_lo; hi = gpu_dirty_hi; }
-	void clear_pending_gpu_writes() { gpu_dirty_lo = ~0u; gpu_dirty_hi = 0; }
+	// Where passes note the byte ranges they render to (device -> host side of the RDRAM mirror).
+	void set_rdram_mirror(RdramMirror *m) { mirror = m; }
 	void invalidate_tmem_snapshot() { tmem_snapshot_valid = false; }
 
 	uint64_t get_primitive_counter() const { return base_primitive_index; }
@@ -175,7 +175,7 @@ private:
 	uint64_t flush_ns = 0; // time spent submitting passes (written by the thread that drives the renderer)
 	bool tmem_snapshot_valid = false;
 
-	uint32_t gpu_dirty_lo = ~0u, gpu_dirty_hi = 0;
+	RdramMirror *mirror = nullptr;
 
 	void ensure_pass();
 	void snapshot_state();

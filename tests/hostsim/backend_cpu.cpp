@@ -141,6 +141,12 @@ int rdpb_rdram_read(rdpb_device *dev, uint32_t offset, void *dst, uint32_t size,
 	memcpy(dst, dev->rdram.data() + offset, size);
 	return 0;
 }
+int rdpb_rdram_read_fenced(rdpb_device *dev, void *host_base, const uint32_t *ranges, uint32_t num_ranges, uint64_t)
+{
+	for (uint32_t i = 0; i < num_ranges; i++)
+		memcpy(static_cast<uint8_t *>(host_base) + ranges[2 * i], dev->rdram.data() + ranges[2 * i], ranges[2 * i + 1]);
+	return 0;
+}
 int rdpb_hidden_write(rdpb_device *dev, uint32_t offset, const void *src, uint32_t size, int)
 {
 	memcpy(dev->hidden.data() + offset, src, size);
