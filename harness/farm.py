@@ -2,7 +2,8 @@
 
 A command stream is serial through its own RDRAM, so streams are the shard boundary: rank r of W renders the streams k
 with k mod W == r, and no collective touches the data path (results are per-stream RDRAM + scan-out).  Stream k runs
-workload 2 + (k mod 2) of BASELINE.json (C2 triangles, C3 fill-rate) with seed 1000 + k."""
+workload 2 + (k mod 3) of BASELINE.json with seed 1000 + k: C2 triangles, C3 fill-rate, C4 = the C2
+triangle workload rendered with 4x internal upscaling and scanned out through two halving steps."""
 from __future__ import annotations
 
 import hashlib
@@ -16,29 +17,46 @@ def streams_for_rank(num_streams: int, rank: int, world: int) -> list[int]:
     return [k for k in range(num_streams) if k % world == rank]
 
 
+KINDS = ("c2", "c3", "c4")
+UPSCALING_4X = 1 << 3  # RDP_B200_FLAG_UPSCALING_4X
+
+
 def stream_kind(k: int) -> str:
-    return "c2" if k % 2 == 0 else "c3"
+    return KINDS[k % 3]
+
+
+def stream_flags(k: int) -> int:
+    return UPSCALING_4X if stream_kind(k) == "c4" else 0
 
 
 def stream_frames(k: int, frames: int, c2_triangles: int, c3_rects: int):
     rng = np.random.RandomState(1000 + k)
-    if stream_kind(k) == "c2":
+    if stream_kind(k) in ("c2", "c4"):
         return [wl.c2_frame(rng, c2_triangles) for _ in range(frames)]
     return [wl.c3_frame(rng, c3_rects) for _ in range(frames)]
 
 
-def render_stream(make_processor, k: int, frames: int, c2_triangles: int, c3_rects: int) -> str:
-    """Render stream k on a fresh processor; returns a digest of its final RDRAM, hidden RDRAM and last scan-out."""
+def stream_rdram_image(k: int) -> np.ndarray:
+    """Initial RDRAM of stream k: zeros + the textures its workload loads."""
     rdram = np.zeros(wl.RDRAM_SIZE, np.uint8)
-    if stream_kind(k) == "c2":
+    if stream_kind(k) in ("c2", "c4"):
         rdram[wl.TEX_ADDR:wl.TEX_ADDR + 8 * 2048] = wl.c2_textures()
-        regs = wl.c2_vi_registers
     else:
         tex, tlut = wl.c3_assets()
         rdram[wl.TEX_ADDR:wl.TEX_ADDR + tex.size] = tex
         rdram[wl.TEX_ADDR + 0x1000:wl.TEX_ADDR + 0x1000 + tlut.size] = tlut
-        regs = wl.c3_vi_registers
-    proc = make_processor(rdram)
+    return rdram
+
+
+def stream_vi_registers(k: int):
+    return wl.c3_vi_registers if stream_kind(k) == "c3" else wl.c2_vi_registers
+
+
+def render_stream(make_processor, k: int, frames: int, c2_triangles: int, c3_rects: int) -> str:
+    """Render stream k on a fresh processor (make_processor(rdram, flags)); returns a digest of its final RDRAM, hidden RDRAM and last scan-out."""
+    rdram = stream_rdram_image(k)
+    regs = stream_vi_registers(k)
+    proc = make_processor(rdram, stream_flags(k))
     try:
         proc.begin_read_hidden_rdram()[:] = 0
         proc.end_write_hidden_rdram()
@@ -46,6 +64,7 @@ def render_stream(make_processor, k: int, frames: int, c2_triangles: int, c3_rec
         opts = proc.default_scanout_options()
         opts.blend_previous_frame = 1
         opts.upscale_deinterlacing = 0
+        opts.downscale_steps = 2 if stream_kind(k) == "c4" else 0
         h = hashlib.sha256()
         for i, words in enumerate(stream_frames(k, frames, c2_triangles, c3_rects)):
             proc.enqueue_command_stream(words)

@@ -136,7 +136,11 @@ enum
 	RDPB_KERNEL_TILES = 3,
 	RDPB_KERNEL_VI_FILTER = 4,
 	RDPB_KERNEL_VI_SCALE = 5,
-	RDPB_KERNEL_COUNT = 6
+	RDPB_KERNEL_TILES_UPSCALED = 6,    /* the tile kernel of an upscaled pass */
+	RDPB_KERNEL_SPAN_BIN_UPSCALED = 7,
+	RDPB_KERNEL_UPSCALE_SYNC = 8,      /* PRE / POST / RESOLVE of the upscaled domain */
+	RDPB_KERNEL_VI_DOWNSCALE = 9,      /* halving steps (+ bob) of an upscaled scan-out */
+	RDPB_KERNEL_COUNT = 10
 };
 
 /* Per-kernel device time from CUDA events recorded around every launch on the launching stream. */

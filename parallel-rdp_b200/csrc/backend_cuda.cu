@@ -1460,6 +1460,7 @@ struct rdpb_device
 	uint32_t variant_blocks_per_sm[32] = {}; // resident blocks per SM of each tile-kernel instantiation (lazy)
 	uint32_t tile_blocks_per_sm_override = 0;
 	bool debug_summary = false;
+	bool bench_report = false; // PARALLEL_RDP_BENCH: per-kernel timing table on destroy
 	std::string error;
 
 	PassBuffers buffers(const GpuOp &op) const
@@ -1666,7 +1667,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 			// with super-sampled read-back there is no native tile kernel, so wait here.
 			if (join_front(dev, op.parity & 1u) != 0)
 				return -1;
-			const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN);
+			const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN_UPSCALED);
 			k_span_bin<true><<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
 			prof_end(dev, s);
 		}
@@ -1696,7 +1697,8 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 			return -1;
 		if (join_front(dev, op.parity & 1u) != 0)
 			return -1;
-		const int s = prof_begin(dev, op.variant == &kFillPassVariant ? RDPB_KERNEL_FILL_PASS : RDPB_KERNEL_TILES);
+		const int s = prof_begin(dev, op.variant == &kFillPassVariant ? RDPB_KERNEL_FILL_PASS :
+		                              (op.fb.scale_log2 ? RDPB_KERNEL_TILES_UPSCALED : RDPB_KERNEL_TILES));
 		if (op.variant == &kFillPassVariant)
 		{
 			// Pixel grid, rounded up to whole tiles so that every tile's masks are cleared.
@@ -1756,6 +1758,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		u.alias = op.fb.color_addr == op.fb.depth_addr;
 		u.width = op.fb.width;
 		u.dither = op.count == RDPB_UPSCALE_SYNC_RESOLVE_DITHER;
+		const int ps = prof_begin(dev, RDPB_KERNEL_UPSCALE_SYNC);
 		if (op.count == RDPB_UPSCALE_SYNC_RESOLVE || op.count == RDPB_UPSCALE_SYNC_RESOLVE_DITHER)
 		{
 			k_upscale_resolve<<<dim3((op.fb.width + 31u) / 32u, (op.fb.height + 7u) / 8u), dim3(32, 8), 0, dev->stream>>>(u);
@@ -1766,6 +1769,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		}
 		else
 			k_upscale_sync<<<(u.num_pixels + 255u) / 256u, 256, 0, dev->stream>>>(u, int(op.count));
+		prof_end(dev, ps);
 		dev->launches++;
 		break;
 	}
@@ -1824,6 +1828,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 			int w = f.out_width, h = f.out_height;
 			// (+ the bob deinterlacer as one more step of the ping-pong)
 			const uint32_t steps = f.downscale_steps + (f.bob_scale ? 1u : 0u);
+			const int ps = prof_begin(dev, RDPB_KERNEL_VI_DOWNSCALE, vs);
 			for (uint32_t i = 0; i < f.downscale_steps; i++)
 			{
 				uint32_t *dst = ((steps - i) & 1u) ? dev->vi_down[dev->vi_out_index] : dev->vi_filtered;
@@ -1845,6 +1850,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 				dev->launches++;
 				src = dst;
 			}
+			prof_end(dev, ps, vs);
 			dev->vi_result[dev->vi_out_index] = const_cast<uint32_t *>(src);
 		}
 		if (!check(dev, cudaEventRecord(dev->vi_done, vs), "cudaEventRecord"))
@@ -2025,6 +2031,18 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		need(cudaStreamSynchronize(dev->stream), "initial sync");
 	}
 
+	// PARALLEL_RDP_BENCH (the reference's switch for its per-stage GPU timestamps, rdp_renderer.cpp:2404-2466 +
+	// Granite's timestamp report): per-kernel CUDA-event times, reported on stderr when the processor is destroyed.
+	if (ok)
+	{
+		const char *env = getenv("PARALLEL_RDP_BENCH");
+		if (env && strtol(env, nullptr, 0) > 0)
+		{
+			dev->bench_report = true;
+			rdpb_profile_enable(dev, 1, 1u << 16);
+		}
+	}
+
 	dev->cur_words = dev->d_words[0];
 	dev->cur_records = reinterpret_cast<PrimRecord *>(dev->d_inputs[0]);
 	dev->cur_states = nullptr;
@@ -2045,6 +2063,20 @@ void rdpb_device_destroy(rdpb_device *dev)
 		return;
 	use_device(dev);
 	cudaDeviceSynchronize();
+	if (dev->bench_report)
+	{
+		static const char *names[RDPB_KERNEL_COUNT] = { "front (texture loads + set-up)", "fill pass", "span + bin", "tiles", "vi filter", "vi scale",
+			                                            "tiles (upscaled)", "span + bin (upscaled)", "upscale sync / resolve", "vi downscale" };
+		fprintf(stderr, "[rdp-b200] PARALLEL_RDP_BENCH: %llu kernel launches%s\n", (unsigned long long)dev->launches,
+		        dev->prof_used >= dev->prof_pool.size() ? " (timing slots exhausted: totals cover the first launches only)" : "");
+		for (int k = 0; k < RDPB_KERNEL_COUNT; k++)
+		{
+			uint32_t n = 0;
+			double ms = 0.0;
+			if (rdpb_profile_read(dev, k, &n, &ms) == 0 && n)
+				fprintf(stderr, "[rdp-b200]   %-32s %8u launches %12.3f ms  %9.3f us/launch\n", names[k], n, ms, 1e3 * ms / n);
+		}
+	}
 	cudaFree(dev->rdram);
 	cudaFree(dev->hidden);
 	cudaFreeHost(dev->tmem_host);
@@ -2653,7 +2685,8 @@ int rdpb_profile_enable(rdpb_device *dev, int on, uint32_t max_launches)
 int rdpb_profile_read(rdpb_device *dev, int kind, uint32_t *launches, double *total_ms)
 {
 	use_device(dev);
-	CK(cudaStreamSynchronize(dev->stream));
+	if (rdpb_sync(dev) != 0) // the events sit on the front, compute and scan-out streams
+		return -1;
 	uint32_t n = 0;
 	double total = 0.0;
 	for (size_t i = 0; i < dev->prof_used; i++)

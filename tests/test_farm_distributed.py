@@ -24,7 +24,7 @@ dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 lib = build_hostsim()
 mine = farm.streams_for_rank({n}, rank, world)
-digests = {{k: farm.render_stream(lambda rdram: rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, library=lib), k, {frames}, {tris}, {rects}) for k in mine}}
+digests = {{k: farm.render_stream(lambda rdram, flags: rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, flags=flags, library=lib), k, {frames}, {tris}, {rects}) for k in mine}}
 # timing plumbing of bench.py: barrier on both sides, max over ranks
 dist.barrier()
 t = torch.tensor([10.0 + rank], dtype=torch.float64)
@@ -49,7 +49,7 @@ def test_round_robin_assignment():
             assert all(k % world == r for k in mine)
             seen += mine
         assert sorted(seen) == list(range(1024))
-    assert [farm.stream_kind(k) for k in range(4)] == ["c2", "c3", "c2", "c3"]
+    assert [farm.stream_kind(k) for k in range(4)] == ["c2", "c3", "c4", "c2"]  # config 2 + (k mod 3)
 
 
 @pytest.mark.timeout(600)
@@ -72,5 +72,5 @@ def test_two_gloo_ranks_render_the_same_streams_as_one_process(tmp_path):
     rdp = importlib.import_module("parallel-rdp_b200")
     lib = build_hostsim()
     for k in range(NUM_STREAMS):
-        serial = farm.render_stream(lambda rdram: rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, library=lib), k, FRAMES, TRIS, RECTS)
+        serial = farm.render_stream(lambda rdram, flags: rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, flags=flags, library=lib), k, FRAMES, TRIS, RECTS)
         assert serial == res["digests"][str(k)], f"stream {k} differs between the sharded and the serial run"
