@@ -8,6 +8,7 @@
 #include "rdp_b200.h"
 
 #include <atomic>
+#include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -65,6 +66,47 @@ struct farm_slot
 
 }
 
+// The driver binds to the rdp library it is told about (farm_bind) through dlsym on that library's own handle: it is
+// loaded RTLD_LOCAL like any plugin, so its C++ symbols cannot interpose on another library's in the same process.
+namespace
+{
+struct Api
+{
+	decltype(&rdp_b200_wait_for_timeline) wait_for_timeline;
+	decltype(&rdp_b200_scanout_wait) scanout_wait;
+	decltype(&rdp_b200_enqueue_command_stream_borrowed) enqueue_command_stream_borrowed;
+	decltype(&rdp_b200_set_vi_registers) set_vi_registers;
+	decltype(&rdp_b200_signal_timeline) signal_timeline;
+	decltype(&rdp_b200_scanout) scanout;
+	decltype(&rdp_b200_scanout_async) scanout_async;
+	decltype(&rdp_b200_idle) idle;
+	decltype(&rdp_b200_end_write_rdram) end_write_rdram;
+	decltype(&rdp_b200_begin_read_hidden_rdram) begin_read_hidden_rdram;
+	decltype(&rdp_b200_get_hidden_rdram_size) get_hidden_rdram_size;
+	decltype(&rdp_b200_end_write_hidden_rdram) end_write_hidden_rdram;
+	decltype(&rdp_b200_get_tmem) get_tmem;
+	decltype(&rdp_b200_default_scanout_options) default_scanout_options;
+} api;
+}
+
+extern "C" int farm_bind(const char *rdp_library_path)
+{
+	void *h = dlopen(rdp_library_path, RTLD_NOW | RTLD_LOCAL);
+	if (!h)
+	{
+		fprintf(stderr, "farm_bind: %s\n", dlerror());
+		return -1;
+	}
+	bool ok = true;
+#define BIND(name) ok = ok && (api.name = reinterpret_cast<decltype(api.name)>(dlsym(h, "rdp_b200_" #name))) != nullptr
+	BIND(wait_for_timeline); BIND(scanout_wait); BIND(enqueue_command_stream_borrowed); BIND(set_vi_registers);
+	BIND(signal_timeline); BIND(scanout); BIND(scanout_async); BIND(idle); BIND(end_write_rdram);
+	BIND(begin_read_hidden_rdram); BIND(get_hidden_rdram_size); BIND(end_write_hidden_rdram); BIND(get_tmem);
+	BIND(default_scanout_options);
+#undef BIND
+	return ok ? 0 : -1;
+}
+
 namespace
 {
 struct InFlight
@@ -85,12 +127,12 @@ struct StreamRunner
 		InFlight &f = ring[slot];
 		if (f.timeline)
 		{
-			rdp_b200_wait_for_timeline(s->proc, f.timeline);
+			api.wait_for_timeline(s->proc, f.timeline);
 			f.timeline = 0;
 		}
 		if (f.fence)
 		{
-			rdp_b200_scanout_wait(s->proc, f.fence);
+			api.scanout_wait(s->proc, f.fence);
 			f.fence = 0;
 			if (!(flags & FARM_NO_SCANOUT_COPY) && s->expect_w && (f.w != s->expect_w || f.h != s->expect_h))
 				return false;
@@ -104,18 +146,18 @@ struct StreamRunner
 		if (!retire(slot, flags))
 			return false;
 		const uint32_t fi = index % s->num_frames;
-		rdp_b200_enqueue_command_stream_borrowed(s->proc, size_t(s->frame_words[fi]), s->frames[fi]);
-		rdp_b200_set_vi_registers(s->proc, s->vi_fields + 14u * (index & 1u));
+		api.enqueue_command_stream_borrowed(s->proc, size_t(s->frame_words[fi]), s->frames[fi]);
+		api.set_vi_registers(s->proc, s->vi_fields + 14u * (index & 1u));
 		InFlight &f = ring[slot];
 		if (flags & FARM_READ_BACK_RDRAM)
-			f.timeline = rdp_b200_signal_timeline(s->proc);
+			f.timeline = api.signal_timeline(s->proc);
 		if (flags & FARM_NO_SCANOUT_COPY)
 		{
 			unsigned w = 0, h = 0;
-			rdp_b200_scanout(s->proc, &s->opts, &w, &h);
+			api.scanout(s->proc, &s->opts, &w, &h);
 		}
 		else
-			f.fence = rdp_b200_scanout_async(s->proc, &s->opts, s->outs[slot], size_t(s->out_capacity), &f.w, &f.h);
+			f.fence = api.scanout_async(s->proc, &s->opts, s->outs[slot], size_t(s->out_capacity), &f.w, &f.h);
 		issued++;
 		return true;
 	}
@@ -223,15 +265,15 @@ int farm_run_pool(const farm_slot *slots, uint32_t num_slots, const farm_job *jo
 			st.job = &job;
 			st.frame = 0;
 			rdp_b200_processor *p = st.slot->proc;
-			rdp_b200_idle(p);
+			api.idle(p);
 			if (job.rdram_image)
 				memcpy(st.slot->rdram, job.rdram_image, size_t(st.slot->rdram_bytes));
 			else
 				memset(st.slot->rdram, 0, size_t(st.slot->rdram_bytes));
-			rdp_b200_end_write_rdram(p);
-			memset(rdp_b200_begin_read_hidden_rdram(p), 0, rdp_b200_get_hidden_rdram_size(p));
-			rdp_b200_end_write_hidden_rdram(p);
-			memset(rdp_b200_get_tmem(p), 0, 4096);
+			api.end_write_rdram(p);
+			memset(api.begin_read_hidden_rdram(p), 0, api.get_hidden_rdram_size(p));
+			api.end_write_hidden_rdram(p);
+			memset(api.get_tmem(p), 0, 4096);
 			farm_stream &s = st.stream;
 			memset(&s, 0, sizeof(s));
 			s.proc = p;
@@ -242,7 +284,7 @@ int farm_run_pool(const farm_slot *slots, uint32_t num_slots, const farm_job *jo
 			s.vi_fields = job.vi_fields;
 			s.outs = st.slot->outs;
 			s.out_capacity = st.slot->out_capacity;
-			rdp_b200_default_scanout_options(&s.opts);
+			api.default_scanout_options(&s.opts);
 			s.opts.blend_previous_frame = 1;
 			s.opts.upscale_deinterlacing = 0;
 			s.opts.downscale_steps = job.downscale_steps;

@@ -1,7 +1,7 @@
 """ctypes front of harness/farm_driver.cpp: the native driver loops bench.py's end-to-end legs and the C5 stream farm
 run in (only public C-ABI calls of include/rdp_b200.h; see the .cpp).  The driver library carries no link-time
-dependency: it binds to whichever rdp library the process loaded with RTLD_GLOBAL (the product, or the host simulator in
-the CPU tests)."""
+dependency: farm_bind() resolves the entry points on the handle of whichever rdp library it is given (the product, or the
+host simulator in the CPU tests)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -48,14 +48,17 @@ def build(force: bool = False) -> str:
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-o", LIB, SRC, "-I", os.path.join(ROOT, "include"),
-                    "-lpthread"], check=True)
+                    "-lpthread", "-ldl"], check=True)
     return LIB
 
 
 def load(rdp_library_path: str):
-    """Loads the driver against the rdp library at `rdp_library_path` (made global first so the driver's calls bind to it)."""
-    C.CDLL(rdp_library_path, mode=C.RTLD_GLOBAL)
+    """Loads the driver and binds it (dlsym on the library's own handle) to the rdp library at `rdp_library_path`."""
     lib = C.CDLL(build())
+    lib.farm_bind.restype = C.c_int
+    lib.farm_bind.argtypes = [C.c_char_p]
+    if lib.farm_bind(rdp_library_path.encode()) != 0:
+        raise RuntimeError("farm driver: cannot bind to " + rdp_library_path)
     lib.farm_run.restype = C.c_int
     lib.farm_run.argtypes = [C.POINTER(FarmStream), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.farm_run_pool.restype = C.c_int

@@ -79,7 +79,8 @@ int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_w
  * decode `num_prims` primitives from their raw command words and allocate their span jobs.  update_tmem & 2: the
  * pass's texture loads may read memory the previous pass renders to -- the CUDA backend runs set-up work ahead of the
  * previous pass's tile kernel unless told so.  update_tmem & 4: the pass samples TMEM (the CUDA backend keeps two sets
- * of TMEM snapshots and refreshes the one this pass uses when it is out of date even if bit 0 is clear). */
+ * of TMEM snapshots and refreshes the one this pass uses when it is out of date even if bit 0 is clear).  update_tmem & 8: a
+ * native rdpb_launch_span_bin follows for this pass (it then closes the pass's set-up side; otherwise this call does). */
 int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims);
 int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info /* rdpb::FbInfo */);
 /* `summary` (rdpb::PassSummary) describes what the pass's states have in common; the backend uses it to pick a

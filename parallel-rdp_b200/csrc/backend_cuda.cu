@@ -1336,7 +1336,9 @@ struct GpuOp
 	int kind;
 	uint32_t count, count2, flag;
 	uint32_t parity; // scratch set of the pass the operation belongs to
+	uint32_t slot;   // staging slot of the pass (names its front_done / pass_done events)
 	uint32_t hazard; // GOP_FRONT: the pass's texture loads may read what the previous pass renders
+	uint32_t last_front_op; // GOP_FRONT: no native span launch follows, so front_done is recorded here
 	const TileVariant *variant;
 	FbInfo fb;
 	ViFrame vi;
@@ -1362,14 +1364,22 @@ struct rdpb_device
 	unsigned long long *d_counters = nullptr;
 
 	uint8_t *staging[kStagingSlots] = {};
-	cudaEvent_t staging_done[kStagingSlots] = {};   // recorded on stream_up: the slot's uploads have landed
-	bool staging_in_flight[kStagingSlots] = {};
-	cudaEvent_t kernels_done[kStagingSlots] = {};   // recorded on stream: the pass that read the slot's device inputs is done
-	bool kernels_in_flight[kStagingSlots] = {};
-	bool pass_upload_pending = false;               // the compute stream has not yet waited for this pass's uploads
+	// Two events per pass (round 1 used seven): front_done[slot] on the front stream behind the pass's uploads, set-up
+	// and span kernels; pass_done[slot] on the compute stream behind its last kernel.
+	//   front_done  gates the pass's tile kernel (compute stream) and the reuse of the slot's host staging memory;
+	//   pass_done   gates the front-stream work of the next pass of the same parity: it overwrites the scratch set the
+	//               tile kernel read, and -- four passes later -- the slot's device-side inputs.
+	cudaEvent_t front_done[kStagingSlots] = {};
+	bool front_in_flight[kStagingSlots] = {};       // recorded; the host has not waited for it since
+	bool front_pending[kStagingSlots] = {};         // recorded; the compute stream has not waited for it yet
+	cudaEvent_t pass_done[kStagingSlots] = {};
+	cudaEvent_t last_pass_done[2] = {};             // per scratch-set parity: pass_done of the latest pass that used it
+	bool pass_upload_pending = false;               // uploads issued for this pass and front_done not yet recorded behind them
+	bool front_gate_passed = false;                 // this pass: the front stream already waits for last_pass_done (before its uploads)
 
-	// Copy engines run beside the SMs: pass inputs go up on stream_up while the previous pass computes, scan-out
-	// images come down on stream_down while the next frame renders.
+	// Copy engines run beside the SMs: pass inputs go up on the front stream while the previous pass's tile kernel
+	// computes; RDRAM read-backs come down on stream_down while the next frame renders.  (stream_up is the front stream:
+	// uploads and the set-up kernels that read them are in one queue, so nothing has to order them.)
 	cudaStream_t stream_up = nullptr, stream_down = nullptr;
 	bool side_streams_owned = true;
 	cudaEvent_t vi_done = nullptr;
@@ -1379,8 +1389,6 @@ struct rdpb_device
 	cudaEvent_t vi_fork = nullptr;   // compute stream -> scan-out stream: everything the scan-out must see
 	bool vi_busy = false;            // a scan-out was launched and the compute stream has not waited for it since
 	uint32_t vi_lo = 0, vi_hi = 0;   // RDRAM bytes it reads (lo >= hi: unknown)
-	cudaEvent_t readback_done[2] = {};
-	bool readback_in_flight[2] = {};
 	// RDRAM read-back (rdpb_rdram_read_fenced) on stream_down: forked behind the compute stream; an operation that
 	// writes RDRAM inside [rb_lo, rb_hi) while the copies may still be running waits for them.
 	cudaEvent_t rdram_rb_fork = nullptr, rdram_rb_done = nullptr;
@@ -1399,9 +1407,6 @@ struct rdpb_device
 	Span *d_spans = nullptr;      // [2][kMaxSpansPerPass]
 	uint32_t cur_parity = 0;                  // parity of the pass being submitted
 	cudaStream_t stream_front = nullptr;      // k_front + native k_span_bin of every pass, in submission order
-	cudaEvent_t span_done[2] = {};            // stream_front: the pass's set-up + spans are complete
-	cudaEvent_t scratch_free[2] = {};         // compute stream: the last pass that used this scratch set is done with it
-	bool front_pending[2] = {};               // span_done[q] recorded and the compute stream has not waited for it yet
 	cudaEvent_t host_write_done = nullptr;    // compute stream: last host -> RDRAM copy (texture loads read RDRAM)
 	bool host_write_pending = false;
 	// Snapshot 0 of a set is TMEM as it was when the set was last refreshed; live TMEM moves on with every pass that
@@ -1433,7 +1438,7 @@ struct rdpb_device
 	std::mutex timeline_lock;
 	// Points recorded on the compute stream (timeline signals) and on the read-back stream (scan-out fences): each
 	// queue is in its own stream's order, so retiring everything older than a matched point is only valid per queue.
-	enum { kTimelineCompute = 0, kTimelineDown = 1, kTimelineQueues = 2 };
+	enum { kTimelineCompute = 0, kTimelineDown = 1, kTimelineVi = 2, kTimelineQueues = 3 };
 	std::deque<std::pair<uint64_t, cudaEvent_t>> timeline[kTimelineQueues];
 	std::deque<cudaEvent_t> free_events;
 
@@ -1536,14 +1541,38 @@ static int join_vi(rdpb_device *dev)
 	return 0;
 }
 
-// Make the compute stream wait for the set-up + span kernels of the pass using scratch set q.
-static int join_front(rdpb_device *dev, uint32_t q)
+// Make the compute stream wait for the uploads, set-up and span kernels of the pass in staging slot `slot`.
+static int join_front(rdpb_device *dev, uint32_t slot)
 {
-	if (dev->front_pending[q])
+	if (dev->front_pending[slot])
 	{
-		CK(cudaStreamWaitEvent(dev->stream, dev->span_done[q], 0));
-		dev->front_pending[q] = false;
+		CK(cudaStreamWaitEvent(dev->stream, dev->front_done[slot], 0));
+		dev->front_pending[slot] = false;
 	}
+	return 0;
+}
+
+// Front-stream side of a pass boundary: before anything of the pass with scratch parity q touches that scratch set
+// (or, live, the staging slot's device inputs), the latest pass that used them must have finished on the compute stream.
+static int front_gate(rdpb_device *dev, uint32_t q, bool hazard)
+{
+	cudaStream_t fs = dev->stream_front;
+	if (fs == dev->stream)
+		return 0;
+	if (dev->last_pass_done[q])
+		CK(cudaStreamWaitEvent(fs, dev->last_pass_done[q], 0));
+	// Texture loads that may read what the previous pass (the other parity) renders wait for it as well.
+	if (hazard && dev->last_pass_done[q ^ 1u])
+		CK(cudaStreamWaitEvent(fs, dev->last_pass_done[q ^ 1u], 0));
+	return 0;
+}
+
+static int record_front_done(rdpb_device *dev, uint32_t slot)
+{
+	CK(cudaEventRecord(dev->front_done[slot], dev->stream_front));
+	dev->front_in_flight[slot] = true;
+	dev->front_pending[slot] = dev->stream_front != dev->stream;
+	dev->pass_upload_pending = false;
 	return 0;
 }
 
@@ -1635,9 +1664,12 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		const uint32_t q = op.parity & 1u;
 		if (fs != dev->stream)
 		{
-			if (!check(dev, cudaStreamWaitEvent(fs, dev->scratch_free[q], 0), "cudaStreamWaitEvent"))
+			// (Live, rdpb_pass_upload already put this wait in front of the pass's uploads.)
+			if (!dev->front_gate_passed && front_gate(dev, q, false) != 0)
 				return -1;
-			if (op.hazard && !check(dev, cudaStreamWaitEvent(fs, dev->scratch_free[q ^ 1u], 0), "cudaStreamWaitEvent"))
+			dev->front_gate_passed = false;
+			if (op.hazard && dev->last_pass_done[q ^ 1u] &&
+			    !check(dev, cudaStreamWaitEvent(fs, dev->last_pass_done[q ^ 1u], 0), "cudaStreamWaitEvent"))
 				return -1;
 			if (dev->host_write_pending)
 			{
@@ -1650,12 +1682,8 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		k_front<<<tmem_blocks + setup_blocks, kFrontThreads, 0, fs>>>(dev->buffers(op), tmem_blocks, op.count2, dev->rdram_size, op.count);
 		prof_end(dev, s, fs);
 		dev->launches++;
-		if (fs != dev->stream)
-		{
-			if (!check(dev, cudaEventRecord(dev->span_done[q], fs), "cudaEventRecord"))
-				return -1;
-			dev->front_pending[q] = true;
-		}
+		if (op.last_front_op && record_front_done(dev, op.slot) != 0)
+			return -1;
 		break;
 	}
 	case GOP_SPAN:
@@ -1665,7 +1693,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		{
 			// The upscaled pass follows the native tile kernel on the compute stream (which has waited for the set-up);
 			// with super-sampled read-back there is no native tile kernel, so wait here.
-			if (join_front(dev, op.parity & 1u) != 0)
+			if (join_front(dev, op.slot) != 0)
 				return -1;
 			const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN_UPSCALED);
 			k_span_bin<true><<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
@@ -1674,16 +1702,12 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		else
 		{
 			cudaStream_t fs = dev->stream_front;
-			const uint32_t q = op.parity & 1u;
 			const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN, fs);
 			k_span_bin<false><<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, fs>>>(dev->buffers(op), op.fb);
 			prof_end(dev, s, fs);
-			if (fs != dev->stream)
-			{
-				if (!check(dev, cudaEventRecord(dev->span_done[q], fs), "cudaEventRecord"))
-					return -1;
-				dev->front_pending[q] = true;
-			}
+			// The native span launch is the last front-stream operation of a pass.
+			if (record_front_done(dev, op.slot) != 0)
+				return -1;
 		}
 		dev->launches++;
 		break;
@@ -1695,7 +1719,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 			return -1;
 		if (join_rdram_readback(dev, op.fb) != 0)
 			return -1;
-		if (join_front(dev, op.parity & 1u) != 0)
+		if (join_front(dev, op.slot) != 0)
 			return -1;
 		const int s = prof_begin(dev, op.variant == &kFillPassVariant ? RDPB_KERNEL_FILL_PASS :
 		                              (op.fb.scale_log2 ? RDPB_KERNEL_TILES_UPSCALED : RDPB_KERNEL_TILES));
@@ -1731,10 +1755,14 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		// A pass that launched set-up work but nothing on the compute stream (texture loads only) still has to be
 		// ordered before whatever the compute stream does next; then the scratch set is free for the pass after next.
 		const uint32_t q = op.parity & 1u;
-		if (join_front(dev, q) != 0)
+		if (join_front(dev, op.slot) != 0)
 			return -1;
-		if (dev->stream_front != dev->stream && !check(dev, cudaEventRecord(dev->scratch_free[q], dev->stream), "cudaEventRecord"))
-			return -1;
+		if (dev->stream_front != dev->stream)
+		{
+			if (!check(dev, cudaEventRecord(dev->pass_done[op.slot], dev->stream), "cudaEventRecord"))
+				return -1;
+			dev->last_pass_done[q] = dev->pass_done[op.slot];
+		}
 		return 0;
 	}
 	case GOP_UPSCALE_SYNC:
@@ -1784,14 +1812,8 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 			    !check(dev, cudaStreamWaitEvent(vs, dev->vi_fork, 0), "cudaStreamWaitEvent"))
 				return -1;
 		}
+		// (The image about to be overwritten was copied to the host, if at all, on this same stream: rdpb_vi_read_output_fenced.)
 		dev->vi_out_index ^= 1u;
-		if (dev->readback_in_flight[dev->vi_out_index])
-		{
-			// The image about to be overwritten may still be on its way to the host.
-			if (!check(dev, cudaStreamWaitEvent(vs, dev->readback_done[dev->vi_out_index], 0), "cudaStreamWaitEvent"))
-				return -1;
-			dev->readback_in_flight[dev->vi_out_index] = false;
-		}
 		ViBuffers b;
 		const ViFrame &f = op.vi;
 		b.rdram = f.scale_log2 ? dev->up_rdram : dev->rdram;
@@ -1870,17 +1892,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 static int submit(rdpb_device *dev, GpuOp &op)
 {
 	op.parity = dev->cur_parity;
-	if (dev->pass_upload_pending)
-	{
-		// First kernel of the pass: everything uploaded so far for it (stream_up) must have landed.  The same event
-		// gates the reuse of the pass's host staging slot.  A pass starts on the front stream (set-up); the compute
-		// stream inherits the dependency when it waits for the set-up.
-		cudaStream_t first = (op.kind == GOP_FRONT || (op.kind == GOP_SPAN && !op.fb.scale_log2)) ? dev->stream_front : dev->stream;
-		if (!check(dev, cudaEventRecord(dev->staging_done[dev->staging_index], dev->stream_up), "cudaEventRecord") ||
-		    !check(dev, cudaStreamWaitEvent(first, dev->staging_done[dev->staging_index], 0), "cudaStreamWaitEvent"))
-			return -1;
-		dev->pass_upload_pending = false;
-	}
+	op.slot = dev->staging_index;
 	op.words = dev->cur_words;
 	op.records = dev->cur_records;
 	op.states = dev->cur_states;
@@ -1942,33 +1954,26 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	if (getenv("RDP_B200_SINGLE_STREAM"))
 	{
 		// Diagnostic: no copy/compute overlap (everything in one stream's order).
-		dev->stream_up = dev->stream_down = dev->stream;
+		dev->stream_down = dev->stream;
 		dev->side_streams_owned = false;
 	}
 	else
 	{
-		need(cudaStreamCreateWithFlags(&dev->stream_up, cudaStreamNonBlocking), "cudaStreamCreate up");
 		need(cudaStreamCreateWithFlags(&dev->stream_down, cudaStreamNonBlocking), "cudaStreamCreate down");
 	}
 	need(cudaEventCreateWithFlags(&dev->vi_done, cudaEventDisableTiming), "cudaEventCreate");
 	need(cudaEventCreateWithFlags(&dev->vi_fork, cudaEventDisableTiming), "cudaEventCreate");
-	if (dev->stream_up == dev->stream)
-		dev->stream_vi = dev->stream_front = dev->stream; // RDP_B200_SINGLE_STREAM: everything in one queue
+	if (dev->stream_down == dev->stream)
+		dev->stream_vi = dev->stream_front = dev->stream_up = dev->stream; // RDP_B200_SINGLE_STREAM: everything in one queue
 	else
 	{
 		need(cudaStreamCreateWithFlags(&dev->stream_vi, cudaStreamNonBlocking), "cudaStreamCreate vi");
 		need(cudaStreamCreateWithFlags(&dev->stream_front, cudaStreamNonBlocking), "cudaStreamCreate front");
-	}
-	for (int q = 0; q < 2; q++)
-	{
-		need(cudaEventCreateWithFlags(&dev->span_done[q], cudaEventDisableTiming), "cudaEventCreate");
-		need(cudaEventCreateWithFlags(&dev->scratch_free[q], cudaEventDisableTiming), "cudaEventCreate");
+		dev->stream_up = dev->stream_front;
 	}
 	need(cudaEventCreateWithFlags(&dev->host_write_done, cudaEventDisableTiming), "cudaEventCreate");
 	need(cudaEventCreateWithFlags(&dev->rdram_rb_fork, cudaEventDisableTiming), "cudaEventCreate");
 	need(cudaEventCreateWithFlags(&dev->rdram_rb_done, cudaEventDisableTiming), "cudaEventCreate");
-	for (auto &e : dev->readback_done)
-		need(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
 	need(cudaMalloc(&dev->rdram, rdram_size), "cudaMalloc rdram");
 	need(cudaMalloc(&dev->hidden, hidden_size), "cudaMalloc hidden");
 	need(cudaHostAlloc(&dev->tmem_host, kTmemBytes, cudaHostAllocMapped), "cudaHostAlloc tmem");
@@ -2005,8 +2010,8 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	for (unsigned i = 0; i < kStagingSlots; i++)
 	{
 		need(cudaHostAlloc(&dev->staging[i], StagingLayout::total, cudaHostAllocDefault), "cudaHostAlloc staging");
-		need(cudaEventCreateWithFlags(&dev->staging_done[i], cudaEventDisableTiming), "cudaEventCreate");
-		need(cudaEventCreateWithFlags(&dev->kernels_done[i], cudaEventDisableTiming), "cudaEventCreate");
+		need(cudaEventCreateWithFlags(&dev->front_done[i], cudaEventDisableTiming), "cudaEventCreate");
+		need(cudaEventCreateWithFlags(&dev->pass_done[i], cudaEventDisableTiming), "cudaEventCreate");
 	}
 
 	if (ok)
@@ -2115,10 +2120,10 @@ void rdpb_device_destroy(rdpb_device *dev)
 	for (unsigned i = 0; i < kStagingSlots; i++)
 	{
 		cudaFreeHost(dev->staging[i]);
-		if (dev->staging_done[i])
-			cudaEventDestroy(dev->staging_done[i]);
-		if (dev->kernels_done[i])
-			cudaEventDestroy(dev->kernels_done[i]);
+		if (dev->front_done[i])
+			cudaEventDestroy(dev->front_done[i]);
+		if (dev->pass_done[i])
+			cudaEventDestroy(dev->pass_done[i]);
 	}
 	for (auto &q : dev->timeline)
 		for (auto &t : q)
@@ -2138,24 +2143,12 @@ void rdpb_device_destroy(rdpb_device *dev)
 		cudaStreamDestroy(dev->stream_vi);
 	if (dev->stream_front && dev->stream_front != dev->stream)
 		cudaStreamDestroy(dev->stream_front);
-	for (int q = 0; q < 2; q++)
-	{
-		if (dev->span_done[q])
-			cudaEventDestroy(dev->span_done[q]);
-		if (dev->scratch_free[q])
-			cudaEventDestroy(dev->scratch_free[q]);
-	}
 	if (dev->host_write_done)
 		cudaEventDestroy(dev->host_write_done);
 	if (dev->rdram_rb_fork)
 		cudaEventDestroy(dev->rdram_rb_fork);
 	if (dev->rdram_rb_done)
 		cudaEventDestroy(dev->rdram_rb_done);
-	for (auto &e : dev->readback_done)
-		if (e)
-			cudaEventDestroy(e);
-	if (dev->stream_up && dev->side_streams_owned)
-		cudaStreamDestroy(dev->stream_up);
 	if (dev->stream_down && dev->side_streams_owned)
 		cudaStreamDestroy(dev->stream_down);
 	if (dev->stream)
@@ -2239,11 +2232,13 @@ int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
 	dev->cur_parity ^= 1u;
 	dev->staging_index = (dev->staging_index + 1) % kStagingSlots;
 	const unsigned i = dev->staging_index;
-	if (dev->staging_in_flight[i])
+	if (dev->front_in_flight[i])
 	{
-		CK(cudaEventSynchronize(dev->staging_done[i]));
-		dev->staging_in_flight[i] = false;
+		// The slot's host staging memory was last read by the uploads of the pass four back.
+		CK(cudaEventSynchronize(dev->front_done[i]));
+		dev->front_in_flight[i] = false;
 	}
+	dev->front_gate_passed = false;
 	uint8_t *base = dev->staging[i];
 	out->words = reinterpret_cast<uint32_t *>(base + StagingLayout::words_off);
 	out->records = base + StagingLayout::records_off;
@@ -2274,12 +2269,11 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 
 	uint32_t *words = dev->d_words[i];
 	uint8_t *block = dev->d_inputs[i];
-	// The previous pass that used this device slot may still be reading it.
-	if (dev->kernels_in_flight[i])
-	{
-		CK(cudaStreamWaitEvent(dev->stream_up, dev->kernels_done[i], 0));
-		dev->kernels_in_flight[i] = false;
-	}
+	// The device-side input slot was last read by the pass four back, the scratch set by the pass two back: the front
+	// stream waits for the latter (the compute stream is in order, so that covers both) before the uploads.
+	if (front_gate(dev, dev->cur_parity & 1u, false) != 0)
+		return -1;
+	dev->front_gate_passed = true;
 	if (dev->recording)
 	{
 		// Keep this pass's inputs resident in the arena so the pass can be replayed without host traffic.
@@ -2297,8 +2291,7 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 
 	if (block_bytes)
 		CK(cudaMemcpyAsync(block, block_host, block_bytes, cudaMemcpyHostToDevice, dev->stream_up));
-	// staging_done[i] is recorded once, behind the last copy of the pass (first kernel submission, or pass end).
-	dev->staging_in_flight[i] = true;
+	// front_done[i] is recorded once, behind the last front-stream operation of the pass (span launch, or pass end).
 	dev->pass_upload_pending = true;
 
 	dev->cur_words = words;
@@ -2346,6 +2339,7 @@ int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, u
 	op.count2 = num_uploads;
 	op.flag = refresh ? 1u : 0u;
 	op.hazard = (update_tmem & 2) ? 1u : 0u;
+	op.last_front_op = (update_tmem & 8) ? 0u : 1u; // bit 3: a native span launch follows and closes the front-stream side
 	return submit(dev, op);
 }
 
@@ -2384,23 +2378,19 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 int rdpb_pass_end(rdpb_device *dev)
 {
 	use_device(dev);
-	const unsigned i = dev->staging_index;
 	if (dev->pass_upload_pending)
 	{
-		// Nothing was launched for this pass: its copies still need their completion event for the slot's reuse.
-		CK(cudaEventRecord(dev->staging_done[i], dev->stream_up));
-		dev->pass_upload_pending = false;
+		// No kernel closed the front-stream side of this pass: its copies still need their completion event (staging reuse).
+		if (record_front_done(dev, dev->staging_index) != 0)
+			return -1;
 	}
 	GpuOp op = {};
 	op.kind = GOP_PASS_END;
 	op.parity = dev->cur_parity;
+	op.slot = dev->staging_index;
 	if (dev->recording)
 		dev->log.push_back(op);
-	if (issue(dev, op) != 0)
-		return -1;
-	CK(cudaEventRecord(dev->kernels_done[i], dev->stream));
-	dev->kernels_in_flight[i] = true;
-	return 0;
+	return issue(dev, op);
 }
 
 int rdpb_upscaling_init(rdpb_device *dev, uint32_t scale_log2)
@@ -2545,18 +2535,17 @@ int rdpb_vi_read_output(rdpb_device *dev, void *dst, uint32_t width, uint32_t he
 
 static int signal_on(rdpb_device *dev, uint64_t value, cudaStream_t stream);
 
-// Asynchronous read-back of the current scan-out image on the download stream, followed by a timeline point there:
-// waiting for `fence_value` means the pixels are in `dst`.  The compute stream is never blocked by the copy.
+// Asynchronous read-back of the current scan-out image behind the scan-out on its stream, followed by a timeline point
+// there: waiting for `fence_value` means the pixels are in `dst`.  The compute stream is never blocked by the copy.
 int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, uint64_t fence_value)
 {
 	use_device(dev);
+	// The copy follows the scan-out kernels on their own stream: nothing to order it behind them, and the next scan-out
+	// into this image (two fields later) queues behind the copy by itself.
 	const unsigned idx = dev->vi_out_index;
-	CK(cudaStreamWaitEvent(dev->stream_down, dev->vi_done, 0)); // recorded behind the scan-out on its stream
 	if (width && height)
-		CK(cudaMemcpyAsync(dst, vi_result_ptr(dev, idx), size_t(width) * height * 4, cudaMemcpyDeviceToHost, dev->stream_down));
-	CK(cudaEventRecord(dev->readback_done[idx], dev->stream_down));
-	dev->readback_in_flight[idx] = true;
-	return signal_on(dev, fence_value, dev->stream_down);
+		CK(cudaMemcpyAsync(dst, vi_result_ptr(dev, idx), size_t(width) * height * 4, cudaMemcpyDeviceToHost, dev->stream_vi));
+	return signal_on(dev, fence_value, dev->stream_vi);
 }
 
 // Asynchronous copy of `num_ranges` {offset, size} byte ranges of RDRAM into host_base + offset on the read-back stream,
@@ -2612,7 +2601,8 @@ static int signal_on(rdpb_device *dev, uint64_t value, cudaStream_t stream)
 	else
 		CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
 	CK(cudaEventRecord(ev, stream));
-	dev->timeline[stream == dev->stream ? rdpb_device::kTimelineCompute : rdpb_device::kTimelineDown].emplace_back(value, ev);
+	dev->timeline[stream == dev->stream ? rdpb_device::kTimelineCompute :
+	              (stream == dev->stream_vi ? rdpb_device::kTimelineVi : rdpb_device::kTimelineDown)].emplace_back(value, ev);
 	return 0;
 }
 

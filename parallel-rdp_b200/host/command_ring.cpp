@@ -266,15 +266,7 @@ void CommandRing::thread_loop()
 			processor->execute_borrowed_stream(size_t(total), words);
 		}
 		else if (header & kHeaderStream)
-		{
-			uint32_t pos = 0;
-			while (pos < n)
-			{
-				const uint32_t len = rdpb::command_length_words((payload[pos] >> 24) & 63u);
-				processor->enqueue_command_direct(len, payload + pos);
-				pos += len;
-			}
-		}
+			processor->execute_command_run(n, payload);
 		else
 			processor->enqueue_command_direct(n, payload);
 		idle_kick_due = true;

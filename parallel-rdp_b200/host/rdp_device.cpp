@@ -444,23 +444,35 @@ void CommandProcessor::enqueue_command_stream(size_t num_words, const uint32_t *
 	}
 }
 
-void CommandProcessor::execute_borrowed_stream(size_t num_words, const uint32_t *words)
+// A run of whole commands, executed in place.  Triangle runs -- nearly all of a 3-D frame -- go to the renderer in one
+// call (Renderer::draw_triangle_run); everything else is dispatched command by command.
+void CommandProcessor::execute_command_run(size_t num_words, const uint32_t *words)
 {
-	renderer.begin_borrowed_source(words, num_words);
-	// Only the first cache line of each command is read here (opcode, Y bounds, tile); commands are up to 176 bytes
-	// apart, which defeats the hardware streamer, so fetch a few commands ahead explicitly.
 	size_t pos = 0;
 	while (pos < num_words)
 	{
-		__builtin_prefetch(words + pos + 512);
-		__builtin_prefetch(words + pos + 512 + 16);
-		__builtin_prefetch(words + pos + 512 + 32);
-		const uint32_t len = command_length_words((words[pos] >> 24) & 63u);
+		const uint32_t op = (words[pos] >> 24) & 63u;
+		if (op >= OP_TRI_FILL && op <= OP_TRI_SHADE_TEX_Z)
+		{
+			sync_host_rdram_to_device();
+			const size_t used = renderer.draw_triangle_run(words + pos, num_words - pos);
+			if (!used)
+				break; // truncated trailing triangle
+			pos += used;
+			continue;
+		}
+		const uint32_t len = command_length_words(op);
 		if (pos + len > num_words)
 			break;
 		enqueue_command_direct(len, words + pos);
 		pos += len;
 	}
+}
+
+void CommandProcessor::execute_borrowed_stream(size_t num_words, const uint32_t *words)
+{
+	renderer.begin_borrowed_source(words, num_words);
+	execute_command_run(num_words, words);
 	renderer.end_borrowed_source();
 }
 

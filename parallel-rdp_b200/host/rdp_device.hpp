@@ -93,6 +93,7 @@ public:
 	void enqueue_command_stream_borrowed(size_t num_words, const uint32_t *words);
 	// Called by the command thread for a borrowed record.
 	void execute_borrowed_stream(size_t num_words, const uint32_t *words);
+	void execute_command_run(size_t num_words, const uint32_t *words);
 
 	void set_quirks(const Quirks &quirks);
 

@@ -436,6 +436,135 @@ void Renderer::draw_primitive(const uint32_t *words, unsigned count)
 		flush_queues();
 }
 
+// A run of back-to-back triangle commands (opcodes 0x08..0x0f), the hot loop of a 3-D frame: 10^8 of them per second
+// at the target rate (hard part 0), so everything that does not depend on the individual triangle -- the
+// state snapshot, the scissor, which texel kinds its tiles can fetch, where borrowed words go -- is resolved once per
+// run and the per-triangle work is: two words read (Y bounds, tile), one 16-byte record written, three counters.
+// Returns the number of words consumed (stops at the first command that is not a triangle, or is cut short).
+size_t Renderer::draw_triangle_run(const uint32_t *words, size_t num_words)
+{
+	size_t pos = 0;
+	while (pos < num_words)
+	{
+		const uint32_t op0 = (words[pos] >> 24) & 63u;
+		if (op0 < OP_TRI_FILL || op0 > OP_TRI_SHADE_TEX_Z)
+			break;
+		// Anything unusual goes through the general path, one primitive at a time.
+		if (validation || !pass_open || state_dirty)
+		{
+			const uint32_t len = command_length_words(op0);
+			if (pos + len > num_words)
+				break;
+			draw_primitive(words + pos, len);
+			pos += len;
+			continue;
+		}
+
+		const PassState &st = static_cast<const PassState *>(pass.states)[current_state];
+		const uint32_t rf = st.raster_flags;
+		const int sc_ylo = int(st.sc_ylo), sc_yhi = int(st.sc_yhi);
+		const bool reads_tmem = !(rf & RF_FILL);
+		const bool samples = reads_tmem && (rf & (RF_USES_TEXEL0 | RF_USES_TEXEL1 | RF_USES_PIPELINED_TEXEL1)) != 0;
+		uint32_t all_tiles = 0;
+		for (int i = 0; i < 8; i++)
+			all_tiles |= state_tile_kind_bits[i];
+		const bool z_update = (st.blend_flags & BF_Z_UPDATE) != 0;
+		PrimRecord *records = static_cast<PrimRecord *>(pass.records);
+		uint32_t kinds = 0, height = fb.deduced_height;
+		uint32_t prims = num_prims, spans = num_spans, jobs = num_jobs;
+		bool any = false;
+		// Borrowed words (the zero-copy feed): the whole run extends one segment of the caller's buffer, so a triangle's
+		// offset in the device word buffer is plain pointer arithmetic.  seg_src == nullptr: copy through place_words.
+		const uint32_t *seg_src = nullptr;
+		uint32_t seg_dst = 0;
+		if (words + pos >= borrowed_base && words + num_words <= borrowed_end)
+		{
+			const uint32_t first_len = command_length_words(op0);
+			if (pos + first_len > num_words)
+				break;
+			place_words(words + pos, first_len); // opens or extends the segment (the loop below places the same command again: same offset)
+			seg_src = segments.back().src;
+			seg_dst = segments.back().dst;
+		}
+
+		while (pos < num_words)
+		{
+			const uint32_t *w = words + pos;
+			const uint32_t op = (w[0] >> 24) & 63u;
+			if (op < OP_TRI_FILL || op > OP_TRI_SHADE_TEX_Z)
+				break;
+			const uint32_t len = 8u + ((op & 4u) << 2) + ((op & 2u) << 3) + ((op & 1u) << 2);
+			if (pos + len > num_words)
+				break;
+			// The first line of a command a dozen commands ahead (runs are mostly one triangle type: same stride).
+			__builtin_prefetch(w + 24u * len);
+
+			const int yl = sign_extend<14>(w[0]), yh = sign_extend<14>(w[1]);
+			int line_lo = imax(yh, sc_ylo) >> 2;
+			int line_hi = imin(yl - 1, sc_yhi - 1) >> 2;
+			if (line_hi - line_lo > 1023)
+				line_hi = line_lo + 1023;
+
+			PrimRecord &rec = records[prims];
+			if (seg_src)
+			{
+				rec.word_offset = seg_dst + uint32_t(w - seg_src);
+				num_words = rec.word_offset + len;
+			}
+			else
+				rec.word_offset = place_words(w, len);
+			rec.span_base = spans;
+			rec.state_id = uint16_t(current_state);
+			rec.tmem_instance = uint16_t(num_uploads);
+			rec.line_lo = int16_t(line_lo);
+			rec.line_hi = int16_t(line_hi);
+			prims++;
+			if (line_hi >= line_lo)
+			{
+				spans += uint32_t(line_hi - line_lo + 2);
+				jobs += span_job_count(line_lo, line_hi);
+				height = std::max(height, uint32_t(line_hi + 1));
+			}
+			if (samples)
+			{
+				const uint32_t t = (w[0] >> 16) & 7u;
+				if (rf & RF_TEX_LOD)
+					kinds |= all_tiles;
+				else
+				{
+					if (rf & (RF_USES_TEXEL0 | RF_USES_PIPELINED_TEXEL1))
+						kinds |= state_tile_kind_bits[t];
+					if (rf & RF_USES_TEXEL1)
+						kinds |= state_tile_kind_bits[(t + 1) & 7u];
+				}
+			}
+			pos += len;
+			any = true;
+			if (prims == kMaxPrimsPerPass || num_words_in_pass() + 44 + 1024 > kMaxPassWords || spans + kMaxFbHeight + 2 > kMaxSpansPerPass)
+				break;
+		}
+
+		if (seg_src)
+			segments.back().count = num_words - seg_dst;
+		num_prims = prims;
+		num_spans = spans;
+		num_jobs = jobs;
+		fb.deduced_height = height;
+		summary.texel_kinds |= kinds;
+		if (any)
+		{
+			if (reads_tmem)
+				pass_reads_tmem = true;
+			fb.color_write_pending = true;
+			if (z_update)
+				fb.depth_write_pending = true;
+		}
+		if (num_prims == kMaxPrimsPerPass || num_words + 44 + 1024 > kMaxPassWords || num_spans + kMaxFbHeight + 2 > kMaxSpansPerPass)
+			flush_queues();
+	}
+	return pos;
+}
+
 void Renderer::note_gpu_write(uint32_t addr, uint32_t bytes)
 {
 	if (mirror)
@@ -468,7 +597,14 @@ void Renderer::flush_queues()
 	const bool update_tmem = num_uploads != 0 || (need_render && pass_reads_tmem && !tmem_snapshot_valid);
 	if (update_tmem)
 		tmem_snapshot_valid = num_uploads == 0;
-	rdpb_launch_front(device, (update_tmem ? 1 : 0) | (uploads_may_read_previous_pass ? 2 : 0) | ((need_render && pass_reads_tmem) ? 4 : 0),
+	// (Decided here because the front launch has to know whether a native span launch follows it.)
+	FbInfo probe = {};
+	probe.width = fb.width;
+	probe.fmt = uint32_t(fb.fmt);
+	const bool ssaa_pass = need_render && super_sampled_readback && upscale_log2 != 0 && pass_can_super_sample(probe, upscale_log2);
+	const bool native_span_follows = need_render && !ssaa_pass && num_jobs != 0;
+	rdpb_launch_front(device, (update_tmem ? 1 : 0) | (uploads_may_read_previous_pass ? 2 : 0) | ((need_render && pass_reads_tmem) ? 4 : 0) |
+	                              (native_span_follows ? 8 : 0),
 	                  num_uploads, need_render ? num_prims : 0);
 
 	if (need_render)

@@ -103,6 +103,9 @@ public:
 	void set_depth_framebuffer(uint32_t addr);
 
 	void draw_primitive(const uint32_t *words, unsigned num_words);
+	// Consumes the leading run of triangle commands of `words`; returns the words consumed (rdp_renderer.cpp).
+	size_t draw_triangle_run(const uint32_t *words, size_t num_words);
+	uint32_t num_words_in_pass() const { return num_words; }
 	// While a borrowed source is active, primitives whose words lie inside it are uploaded from there (no host copy).
 	void begin_borrowed_source(const uint32_t *words, size_t num_words) { borrowed_base = words; borrowed_end = words + num_words; }
 	void end_borrowed_source() { borrowed_base = borrowed_end = nullptr; }

@@ -27,6 +27,7 @@ p = rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, library=HOSTSIM_LIB)
 opts = p.default_scanout_options()
 for mode in ("stream", "stream+scanout"):
     for it in range(2):
+        h0 = p.host_timing()
         t0 = time.perf_counter()
         n = 200
         for i in range(n):
@@ -35,5 +36,7 @@ for mode in ("stream", "stream+scanout"):
                 p.scanout(opts)
         p.idle()
         dt = time.perf_counter() - t0
-    print(f"{mode}: {n / dt:.0f} frames/s host-only, {1e6 * dt / n:.1f} us/frame, {1e9 * dt / n / 5001:.1f} ns/primitive")
+    h1 = p.host_timing()
+    print(f"{mode}: {n / dt:.0f} frames/s host-only, {1e6 * dt / n:.1f} us/frame, {1e9 * dt / n / 5001:.1f} ns/primitive; command thread us/frame: "
+          + ", ".join(f"{k} {1e6 * (h1[k] - h0[k]) / n:.1f}" for k in h1))
 p.close()
