@@ -599,6 +599,7 @@ def run_ours(args):
                     "ms_per_step": eb["ms_per_step"], "command_thread_us_per_frame": eb["command_thread_us_per_frame"],
                     "producer_threads": eb["producer_threads"],
                     "streams": {str(S): v["frames_per_s"] for S, v in e2e_sweep.items()},
+                    "command_thread_us_per_frame_by_streams": {str(S): v["command_thread_us_per_frame"] for S, v in e2e_sweep.items()},
                     "path": "rdp_b200_enqueue_command_stream_borrowed + rdp_b200_set_vi_registers + rdp_b200_scanout_async/_wait "
                             "(pinned host buffers, %d frames in flight per stream), called from harness/farm_driver.cpp" % args.e2e_depth},
             "e2e_rdram": e2e_rdram,

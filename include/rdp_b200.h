@@ -157,8 +157,9 @@ void *rdp_b200_cuda_stream(rdp_b200_processor *p);
 /* Name of the tile-kernel instantiation the most recent render pass ran ("generic" = the uber-kernel fallback). */
 const char *rdp_b200_last_tile_variant(rdp_b200_processor *p);
 /* Seconds the command thread spent: [0] executing ring records, [1] of that submitting passes, [2] of that in queued
- * scan-outs; [0] - [1] - [2] is command parsing / pass recording. */
-void rdp_b200_host_timing(rdp_b200_processor *p, double out3[3]);
+ * scan-outs, [3] of that blocked on a staging slot the GPU had not released yet (back-pressure: the GPU is the
+ * bottleneck); [0] - [1] - [2] - [3] is command parsing / pass recording. */
+void rdp_b200_host_timing(rdp_b200_processor *p, double out4[4]);
 /* The backend device handle (rdpb_device*, include/rdp_b200_backend.h) for the measurement entry points. */
 void *rdp_b200_backend_device(rdp_b200_processor *p);
 /* Extension (stream farms: many processors per host): pins this processor's command thread to the given CPUs, e.g. the

@@ -295,9 +295,10 @@ class CommandProcessor:
         return self.lib.rdp_b200_pass_count(self._h)
 
     def host_timing(self):
-        out = (C.c_double * 3)()
+        out = (C.c_double * 4)()
         self.lib.rdp_b200_host_timing(self._h, out)
-        return {"ring_busy_s": out[0], "submit_s": out[1], "scanout_s": out[2], "parse_s": out[0] - out[1] - out[2]}
+        return {"ring_busy_s": out[0], "submit_s": out[1], "scanout_s": out[2], "backpressure_s": out[3],
+                "parse_s": out[0] - out[1] - out[2] - out[3]}
 
     def upscaling_factor(self) -> int:
         return self.lib.rdp_b200_upscaling_factor(self._h)

@@ -52,6 +52,12 @@ __attribute__((constructor)) static void rdpb_request_work_queues()
 namespace
 {
 constexpr unsigned kStagingSlots = 4;
+// Per-pass device scratch (decoded primitives, spans, bin masks, span jobs, TMEM snapshots) exists three times and passes
+// rotate through the sets: the set-up and span kernels of a pass run on the front stream while the tile kernels of the
+// two passes before it may still be reading theirs.  (Two sets are not enough for a 3-D frame: it is a small clear pass
+// followed by the big scene pass, so with two sets every scene pass lands on the same set as the previous frame's scene
+// pass and its set-up cannot start before that tile kernel has finished.)
+constexpr unsigned kScratchSets = 3;
 
 struct StagingLayout
 {
@@ -121,51 +127,56 @@ __device__ __forceinline__ void front_tmem_replay(const PassBuffers &b, uint32_t
 		live[slot] = uint16_t(value);
 }
 
-__global__ void __launch_bounds__(kFrontThreads) k_front(PassBuffers b, uint32_t tmem_blocks, uint32_t num_uploads,
-                                                         uint32_t rdram_size, uint32_t num_prims)
-{
-	// Stream order puts this launch after the previous pass's tile kernel: reset its tile counter here.
-	if (blockIdx.x == 0 && threadIdx.x == 0)
-		b.job_counter[1] = 0;
-	if (blockIdx.x < tmem_blocks)
-	{
-		front_tmem_replay(b, num_uploads, rdram_size);
-		return;
-	}
+// Primitive set-up: a block takes kSetupPrimsPerBlock consecutive primitives.  Eight threads fetch each primitive's
+// command -- up to 22 64-bit words, contiguous in the pass's word buffer -- so a warp-wide load touches eight fully
+// used sectors (round 1 had each thread walk its own command at a 176-byte stride: 32 quarter-used sectors per load,
+// 22 loads per thread, all of a frame's fetches squeezed through the load/store units of 20 SMs).  The words land in
+// shared memory at an odd row stride and the block's first warp decodes one primitive per lane from there, conflict
+// free.  5,000 triangles are 157 blocks: every SM has one, where round 1's 256-primitive blocks used 20 SMs.
+constexpr uint32_t kSetupPrimsPerBlock = 32;
+constexpr uint32_t kSetupFetchThreads = kFrontThreads / kSetupPrimsPerBlock; // 8
+constexpr uint32_t kSetupRowWords = 45; // 44 command words + 1: rows start in different banks
 
-	const uint32_t i = (blockIdx.x - tmem_blocks) * kFrontThreads + threadIdx.x;
+__device__ __forceinline__ void front_setup(const PassBuffers &b, uint32_t first, uint32_t num_prims)
+{
+	__shared__ uint32_t s_words[kSetupPrimsPerBlock][kSetupRowWords];
+	{
+		const uint32_t g = threadIdx.x / kSetupFetchThreads, t = threadIdx.x % kSetupFetchThreads;
+		const uint32_t i = first + g;
+		if (i < num_prims)
+		{
+			const uint32_t word_offset = b.records[i].word_offset;
+			const uint2 *w2 = reinterpret_cast<const uint2 *>(b.words + word_offset); // commands are 64-bit units: word_offset is even
+			const uint32_t op = (__ldg(reinterpret_cast<const uint32_t *>(w2)) >> 24) & 63u;
+			// Triangles: 8 edge words + 16 shade + 16 texture + 4 depth (bits 2, 1, 0 of the opcode); rectangles 2 or 4.
+			const uint32_t len = op >= OP_TRI_FILL && op <= OP_TRI_SHADE_TEX_Z ? 8u + ((op & 4u) ? 16u : 0u) + ((op & 2u) ? 16u : 0u) + ((op & 1u) ? 4u : 0u)
+			                                                                      : (op == OP_FILL_RECT ? 2u : 4u);
+#pragma unroll
+			for (uint32_t k = t; k < 22u; k += kSetupFetchThreads)
+			{
+				uint2 v = make_uint2(0u, 0u);
+				if (2u * k < len)
+					v = __ldg(w2 + k);
+				s_words[g][2u * k] = v.x;
+				s_words[g][2u * k + 1u] = v.y;
+			}
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x >= 32u)
+		return;
+
+	const uint32_t lane = threadIdx.x;
+	const uint32_t i = first + lane;
 	uint32_t njobs = 0;
 	if (i < num_prims)
 	{
-		// The decode reads its command words one dependent group after another; with ~1 warp per SM in this launch
-		// nothing hides those round trips.  Fetch the whole command first -- every load independent -- and decode
-		// from the local copy.
 		const PrimRecord rec = b.records[i];
-		const uint32_t *w = b.words + rec.word_offset;
-		const uint2 *w2 = reinterpret_cast<const uint2 *>(w); // commands are 64-bit units: word_offset is even
-		uint32_t local_words[44];
-		const uint2 head = __ldg(w2);
-		const uint32_t op = (head.x >> 24) & 63u;
-		// Triangles: 8 edge words + 16 shade + 16 texture + 4 depth (bits 2, 1, 0 of the opcode); rectangles 2 or 4.
-		const uint32_t len = op >= OP_TRI_FILL && op <= OP_TRI_SHADE_TEX_Z ? 8u + ((op & 4u) ? 16u : 0u) + ((op & 2u) ? 16u : 0u) + ((op & 1u) ? 4u : 0u)
-		                                                                      : (op == OP_FILL_RECT ? 2u : 4u);
-		local_words[0] = head.x;
-		local_words[1] = head.y;
-#pragma unroll
-		for (uint32_t k = 1; k < 22; k++)
-		{
-			uint2 v = make_uint2(0u, 0u);
-			if (2u * k < len)
-				v = __ldg(w2 + k);
-			local_words[2 * k] = v.x;
-			local_words[2 * k + 1] = v.y;
-		}
-		decode_primitive(local_words, b.states[rec.state_id], rec, b.prims[i]);
+		decode_primitive(s_words[lane], b.states[rec.state_id], rec, b.prims[i]);
 		njobs = span_job_count(rec.line_lo, rec.line_hi);
 	}
 
 	// Warp-wide exclusive scan of the job counts, one atomic per warp, then every lane writes its own jobs.
-	const uint32_t lane = threadIdx.x & 31u;
 	uint32_t incl = njobs;
 #pragma unroll
 	for (int off = 1; off < 32; off <<= 1)
@@ -183,6 +194,20 @@ __global__ void __launch_bounds__(kFrontThreads) k_front(PassBuffers b, uint32_t
 		b.jobs[base + k] = span_job_pack(i, k);
 }
 
+__global__ void __launch_bounds__(kFrontThreads) k_front(PassBuffers b, uint32_t tmem_blocks, uint32_t num_uploads,
+                                                         uint32_t rdram_size, uint32_t num_prims)
+{
+	// Stream order puts this launch after the previous pass's tile kernel: reset its tile counter here.
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		b.job_counter[1] = 0;
+	if (blockIdx.x < tmem_blocks)
+	{
+		front_tmem_replay(b, num_uploads, rdram_size);
+		return;
+	}
+	front_setup(b, (blockIdx.x - tmem_blocks) * kSetupPrimsPerBlock, num_prims);
+}
+
 // One warp per span job (primitive, 32-line chunk); lane = scanline.  Each 4-lane group is one tile row: the
 // group shuffle-reduces the row's X range, then its lanes split the row's tiles and OR the primitive's bit in.
 template <bool UPSCALED>
@@ -192,6 +217,9 @@ __global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
 	const int lane = int(threadIdx.x & 31u);
 	if (job_index >= fb.num_jobs)
 		return;
+	// Launched as a programmatic dependent of the set-up kernel (same stream): the blocks are resident and past their
+	// prologue when the set-up kernel's last block retires, instead of being launched only then.
+	cudaGridDependencySynchronize();
 	const uint32_t job = b.jobs[job_index];
 	const uint32_t prim = job & 0xffffu;
 	const PrimSetup &p = b.prims[prim];
@@ -1335,7 +1363,7 @@ struct GpuOp
 {
 	int kind;
 	uint32_t count, count2, flag;
-	uint32_t parity; // scratch set of the pass the operation belongs to
+	uint32_t parity; // scratch set (0 .. kScratchSets - 1) of the pass the operation belongs to
 	uint32_t slot;   // staging slot of the pass (names its front_done / pass_done events)
 	uint32_t hazard; // GOP_FRONT: the pass's texture loads may read what the previous pass renders
 	uint32_t last_front_op; // GOP_FRONT: no native span launch follows, so front_done is recorded here
@@ -1359,7 +1387,7 @@ struct rdpb_device
 
 	uint8_t *rdram = nullptr, *hidden = nullptr;
 	uint8_t *tmem_host = nullptr, *tmem_dev = nullptr; // same mapped pinned allocation
-	uint8_t *tmem_instances = nullptr; // two sets (pass parity), kTmemBytes * (kMaxUploadsPerPass + 1) each
+	uint8_t *tmem_instances = nullptr; // kScratchSets sets, kTmemBytes * (kMaxUploadsPerPass + 1) each
 	uint8_t *blend_lut = nullptr, *gamma_lut = nullptr;
 	unsigned long long *d_counters = nullptr;
 
@@ -1367,15 +1395,16 @@ struct rdpb_device
 	// Two events per pass (round 1 used seven): front_done[slot] on the front stream behind the pass's uploads, set-up
 	// and span kernels; pass_done[slot] on the compute stream behind its last kernel.
 	//   front_done  gates the pass's tile kernel (compute stream) and the reuse of the slot's host staging memory;
-	//   pass_done   gates the front-stream work of the next pass of the same parity: it overwrites the scratch set the
+	//   pass_done   gates the front-stream work of the next pass on the same scratch set: it overwrites what the
 	//               tile kernel read, and -- four passes later -- the slot's device-side inputs.
 	cudaEvent_t front_done[kStagingSlots] = {};
 	bool front_in_flight[kStagingSlots] = {};       // recorded; the host has not waited for it since
 	bool front_pending[kStagingSlots] = {};         // recorded; the compute stream has not waited for it yet
 	cudaEvent_t pass_done[kStagingSlots] = {};
-	cudaEvent_t last_pass_done[2] = {};             // per scratch-set parity: pass_done of the latest pass that used it
+	cudaEvent_t last_pass_done[kScratchSets] = {};  // per scratch set: pass_done of the latest pass that used it
+	cudaEvent_t prev_pass_done = nullptr;           // pass_done of the latest pass, whatever its set
+	bool front_gate_passed = false;                 // this pass: the front stream already waits for its scratch set (before the uploads)
 	bool pass_upload_pending = false;               // uploads issued for this pass and front_done not yet recorded behind them
-	bool front_gate_passed = false;                 // this pass: the front stream already waits for last_pass_done (before its uploads)
 
 	// Copy engines run beside the SMs: pass inputs go up on the front stream while the previous pass's tile kernel
 	// computes; RDRAM read-backs come down on stream_down while the next frame renders.  (stream_up is the front stream:
@@ -1398,20 +1427,20 @@ struct rdpb_device
 
 	uint32_t *d_words[kStagingSlots] = {};  // device-side input slots, one per staging slot
 	uint8_t *d_inputs[kStagingSlots] = {};  // records | states | texture-load descriptors
-	// Per-pass scratch exists twice, indexed by the pass's parity: the set-up and span kernels of pass p + 1 run on
+	// Per-pass scratch exists kScratchSets times, indexed by the pass's set: the set-up and span kernels of pass p + 1 run on
 	// their own stream while the tile kernel of pass p is still reading pass p's set.
 	static constexpr size_t kTmemSetBytes = size_t(kTmemBytes) * (kMaxUploadsPerPass + 1);
 	static constexpr size_t kFineWords = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 32);
 	static constexpr size_t kCoarseWords = size_t(kMaxTilesX) * kMaxTilesY * (kMaxPrimsPerPass / 1024);
 	PrimSetup *d_prims = nullptr; // [2][kMaxPrimsPerPass]
 	Span *d_spans = nullptr;      // [2][kMaxSpansPerPass]
-	uint32_t cur_parity = 0;                  // parity of the pass being submitted
+	uint32_t cur_parity = 0;                  // scratch set of the pass being submitted
 	cudaStream_t stream_front = nullptr;      // k_front + native k_span_bin of every pass, in submission order
 	cudaEvent_t host_write_done = nullptr;    // compute stream: last host -> RDRAM copy (texture loads read RDRAM)
 	bool host_write_pending = false;
 	// Snapshot 0 of a set is TMEM as it was when the set was last refreshed; live TMEM moves on with every pass that
 	// loads textures (and with host pokes, which arrive as a refresh request without uploads).
-	uint64_t tmem_epoch = 1, snapshot_epoch[2] = {};
+	uint64_t tmem_epoch = 1, snapshot_epoch[kScratchSets] = {};
 	// internal upscaling: S*S slices of RDRAM / hidden RDRAM, the native-sized shadow, the upscaled pass's spans + masks
 	uint32_t scale_log2 = 0;
 	uint8_t *up_rdram = nullptr, *up_hidden = nullptr, *up_reference = nullptr;
@@ -1466,6 +1495,7 @@ struct rdpb_device
 	uint32_t tile_blocks_per_sm_override = 0;
 	bool debug_summary = false;
 	bool bench_report = false; // PARALLEL_RDP_BENCH: per-kernel timing table on destroy
+	bool use_pdl = true;       // span kernel launched as a programmatic dependent of the set-up kernel (RDP_B200_NO_PDL turns it off)
 	std::string error;
 
 	PassBuffers buffers(const GpuOp &op) const
@@ -1475,7 +1505,7 @@ struct rdpb_device
 		b.records = op.records;
 		b.states = op.states;
 		b.uploads = op.uploads;
-		const size_t q = op.parity & 1u;
+		const size_t q = op.parity % kScratchSets;
 		b.prims = d_prims + q * kMaxPrimsPerPass;
 		b.spans = d_spans + q * size_t(kMaxSpansPerPass);
 		b.fine_mask = d_fine + q * kFineWords;
@@ -1552,18 +1582,15 @@ static int join_front(rdpb_device *dev, uint32_t slot)
 	return 0;
 }
 
-// Front-stream side of a pass boundary: before anything of the pass with scratch parity q touches that scratch set
-// (or, live, the staging slot's device inputs), the latest pass that used them must have finished on the compute stream.
-static int front_gate(rdpb_device *dev, uint32_t q, bool hazard)
+// Front-stream side of a pass boundary: before the set-up kernels of a pass overwrite scratch set q, the latest pass
+// that used the set must have finished on the compute stream.
+static int front_gate(rdpb_device *dev, uint32_t q)
 {
 	cudaStream_t fs = dev->stream_front;
 	if (fs == dev->stream)
 		return 0;
 	if (dev->last_pass_done[q])
 		CK(cudaStreamWaitEvent(fs, dev->last_pass_done[q], 0));
-	// Texture loads that may read what the previous pass (the other parity) renders wait for it as well.
-	if (hazard && dev->last_pass_done[q ^ 1u])
-		CK(cudaStreamWaitEvent(fs, dev->last_pass_done[q ^ 1u], 0));
 	return 0;
 }
 
@@ -1654,22 +1681,23 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	{
 		// op.count = primitives, op.count2 = uploads, op.flag = replay texture loads / re-snapshot TMEM
 		const uint32_t tmem_blocks = op.flag ? kTmemBlocks : 0u;
-		const uint32_t setup_blocks = (op.count + kFrontThreads - 1) / kFrontThreads;
+		const uint32_t setup_blocks = (op.count + kSetupPrimsPerBlock - 1) / kSetupPrimsPerBlock;
 		if (tmem_blocks + setup_blocks == 0)
 			break;
 		// Set-up runs on the front stream, ahead of the compute stream: it waits for the scratch set's previous user
 		// (two passes back), for host writes into RDRAM (texture sources), and -- only when the host saw that this
 		// pass's texture loads may read the previous pass's render target -- for the previous pass.
 		cudaStream_t fs = dev->stream_front;
-		const uint32_t q = op.parity & 1u;
+		const uint32_t q = op.parity % kScratchSets;
 		if (fs != dev->stream)
 		{
 			// (Live, rdpb_pass_upload already put this wait in front of the pass's uploads.)
-			if (!dev->front_gate_passed && front_gate(dev, q, false) != 0)
+			if (!dev->front_gate_passed && front_gate(dev, q) != 0)
 				return -1;
 			dev->front_gate_passed = false;
-			if (op.hazard && dev->last_pass_done[q ^ 1u] &&
-			    !check(dev, cudaStreamWaitEvent(fs, dev->last_pass_done[q ^ 1u], 0), "cudaStreamWaitEvent"))
+			// Texture loads that may read what the previous pass renders wait for it as well.
+			if (op.hazard && dev->prev_pass_done && dev->prev_pass_done != dev->last_pass_done[q] &&
+			    !check(dev, cudaStreamWaitEvent(fs, dev->prev_pass_done, 0), "cudaStreamWaitEvent"))
 				return -1;
 			if (dev->host_write_pending)
 			{
@@ -1703,7 +1731,19 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		{
 			cudaStream_t fs = dev->stream_front;
 			const int s = prof_begin(dev, RDPB_KERNEL_SPAN_BIN, fs);
-			k_span_bin<false><<<(op.fb.num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, fs>>>(dev->buffers(op), op.fb);
+			{
+				cudaLaunchConfig_t cfg = {};
+				cfg.gridDim = dim3((op.fb.num_jobs + warps_per_block - 1) / warps_per_block);
+				cfg.blockDim = dim3(warps_per_block * 32);
+				cfg.stream = fs;
+				cudaLaunchAttribute attr[1];
+				attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+				attr[0].val.programmaticStreamSerializationAllowed = 1;
+				cfg.attrs = attr;
+				cfg.numAttrs = dev->use_pdl ? 1u : 0u;
+				if (!check(dev, cudaLaunchKernelEx(&cfg, k_span_bin<false>, dev->buffers(op), op.fb), "cudaLaunchKernelEx"))
+					return -1;
+			}
 			prof_end(dev, s, fs);
 			// The native span launch is the last front-stream operation of a pass.
 			if (record_front_done(dev, op.slot) != 0)
@@ -1754,7 +1794,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 	{
 		// A pass that launched set-up work but nothing on the compute stream (texture loads only) still has to be
 		// ordered before whatever the compute stream does next; then the scratch set is free for the pass after next.
-		const uint32_t q = op.parity & 1u;
+		const uint32_t q = op.parity % kScratchSets;
 		if (join_front(dev, op.slot) != 0)
 			return -1;
 		if (dev->stream_front != dev->stream)
@@ -1762,6 +1802,7 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 			if (!check(dev, cudaEventRecord(dev->pass_done[op.slot], dev->stream), "cudaEventRecord"))
 				return -1;
 			dev->last_pass_done[q] = dev->pass_done[op.slot];
+			dev->prev_pass_done = dev->pass_done[op.slot];
 		}
 		return 0;
 	}
@@ -1938,6 +1979,7 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	hidden_size = std::max(hidden_size, rdram_size >> 1);
 	dev->hidden_size = hidden_size;
 	dev->debug_summary = getenv("RDP_B200_DEBUG_PASSES") != nullptr;
+	dev->use_pdl = getenv("RDP_B200_NO_PDL") == nullptr;
 
 	bool ok = true;
 	auto need = [&](cudaError_t e, const char *what) { ok = ok && check(dev, e, what); };
@@ -1979,7 +2021,7 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	need(cudaHostAlloc(&dev->tmem_host, kTmemBytes, cudaHostAllocMapped), "cudaHostAlloc tmem");
 	if (ok)
 		need(cudaHostGetDevicePointer(&dev->tmem_dev, dev->tmem_host, 0), "cudaHostGetDevicePointer tmem");
-	need(cudaMalloc(&dev->tmem_instances, 2 * rdpb_device::kTmemSetBytes), "cudaMalloc tmem instances");
+	need(cudaMalloc(&dev->tmem_instances, kScratchSets * rdpb_device::kTmemSetBytes), "cudaMalloc tmem instances");
 	need(cudaMalloc(&dev->blend_lut, 0x8000), "cudaMalloc blend lut");
 	need(cudaMalloc(&dev->gamma_lut, 256 + 256 * 64), "cudaMalloc gamma lut");
 	need(cudaMalloc(&dev->d_counters, kCounterWords * sizeof(unsigned long long)), "cudaMalloc counters");
@@ -1991,14 +2033,14 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		                                       size_t(kMaxUploadsPerPass) * sizeof(TmemUpload) + 1024),
 		     "cudaMalloc pass inputs");
 	}
-	need(cudaMalloc(&dev->d_prims, 2 * size_t(kMaxPrimsPerPass) * sizeof(PrimSetup)), "cudaMalloc prims");
-	need(cudaMalloc(&dev->d_spans, 2 * size_t(kMaxSpansPerPass) * sizeof(Span)), "cudaMalloc spans");
-	const size_t fine_bytes = 2 * rdpb_device::kFineWords * 4;
-	const size_t coarse_bytes = 2 * rdpb_device::kCoarseWords * 4;
+	need(cudaMalloc(&dev->d_prims, kScratchSets * size_t(kMaxPrimsPerPass) * sizeof(PrimSetup)), "cudaMalloc prims");
+	need(cudaMalloc(&dev->d_spans, kScratchSets * size_t(kMaxSpansPerPass) * sizeof(Span)), "cudaMalloc spans");
+	const size_t fine_bytes = kScratchSets * rdpb_device::kFineWords * 4;
+	const size_t coarse_bytes = kScratchSets * rdpb_device::kCoarseWords * 4;
 	need(cudaMalloc(&dev->d_fine, fine_bytes), "cudaMalloc fine masks");
 	need(cudaMalloc(&dev->d_coarse, coarse_bytes), "cudaMalloc coarse masks");
-	need(cudaMalloc(&dev->d_jobs, 2 * size_t(kMaxJobsPerPass) * 4), "cudaMalloc span jobs");
-	need(cudaMalloc(&dev->d_job_counter, 2 * 256), "cudaMalloc job counter");
+	need(cudaMalloc(&dev->d_jobs, kScratchSets * size_t(kMaxJobsPerPass) * 4), "cudaMalloc span jobs");
+	need(cudaMalloc(&dev->d_job_counter, kScratchSets * 256), "cudaMalloc job counter");
 	need(cudaMalloc(&dev->vi_filtered, size_t(kViStageWidth) * kViStageHeight * 2 * 4), "cudaMalloc vi filtered");
 	const size_t max_out = size_t(640) * 576 * 4;
 	need(cudaMalloc(&dev->vi_out[0], max_out), "cudaMalloc vi out");
@@ -2020,11 +2062,11 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 		need(cudaMemsetAsync(dev->hidden, 0, hidden_size, dev->stream), "memset hidden");
 		need(cudaMemsetAsync(dev->d_fine, 0, fine_bytes, dev->stream), "memset fine");
 		need(cudaMemsetAsync(dev->d_coarse, 0, coarse_bytes, dev->stream), "memset coarse");
-		need(cudaMemsetAsync(dev->d_job_counter, 0, 2 * 256, dev->stream), "memset job counter");
+		need(cudaMemsetAsync(dev->d_job_counter, 0, kScratchSets * 256, dev->stream), "memset job counter");
 		need(cudaMemsetAsync(dev->d_counters, 0, kCounterWords * sizeof(unsigned long long), dev->stream), "memset counters");
 		need(cudaMemsetAsync(dev->vi_out[0], 0, max_out, dev->stream), "memset vi out");
 		need(cudaMemsetAsync(dev->vi_out[1], 0, max_out, dev->stream), "memset vi out");
-		need(cudaMemsetAsync(dev->tmem_instances, 0, 2 * rdpb_device::kTmemSetBytes, dev->stream), "memset tmem instances");
+		need(cudaMemsetAsync(dev->tmem_instances, 0, kScratchSets * rdpb_device::kTmemSetBytes, dev->stream), "memset tmem instances");
 		memset(dev->tmem_host, 0, kTmemBytes);
 
 		static uint8_t lut[0x8000]; // large enough for both tables (32768 >= 256 + 256 * 64)
@@ -2229,7 +2271,7 @@ void *rdpb_hidden_device_ptr(rdpb_device *dev) { return dev->hidden; }
 int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
 {
 	use_device(dev);
-	dev->cur_parity ^= 1u;
+	dev->cur_parity = (dev->cur_parity + 1u) % kScratchSets;
 	dev->staging_index = (dev->staging_index + 1) % kStagingSlots;
 	const unsigned i = dev->staging_index;
 	if (dev->front_in_flight[i])
@@ -2269,9 +2311,10 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 
 	uint32_t *words = dev->d_words[i];
 	uint8_t *block = dev->d_inputs[i];
-	// The device-side input slot was last read by the pass four back, the scratch set by the pass two back: the front
-	// stream waits for the latter (the compute stream is in order, so that covers both) before the uploads.
-	if (front_gate(dev, dev->cur_parity & 1u, false) != 0)
+	// The device-side input slot was last read by the pass four back, the scratch set this pass's set-up kernels will
+	// overwrite by the pass kScratchSets back.  The compute stream is in order, so one wait for the latter in front of
+	// the uploads covers both -- and the uploads still run while the tile kernels of the passes in between compute.
+	if (front_gate(dev, dev->cur_parity % kScratchSets) != 0)
 		return -1;
 	dev->front_gate_passed = true;
 	if (dev->recording)
@@ -2321,7 +2364,7 @@ int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, u
 	use_device(dev);
 	// The host keeps one "snapshot 0 is current" flag; there are two snapshot sets here.  Refresh this pass's set when
 	// asked to, or when the pass samples TMEM and the set was last refreshed in an earlier TMEM epoch.
-	const uint32_t q = dev->cur_parity & 1u;
+	const uint32_t q = dev->cur_parity % kScratchSets;
 	bool refresh = (update_tmem & 1) != 0;
 	if (refresh)
 		dev->tmem_epoch++; // asked without uploads: the host changed live TMEM; with uploads: harmless

@@ -168,7 +168,7 @@ const char *rdp_b200_backend_name(void) { return rdpb_backend_name(); }
 uint64_t rdp_b200_launch_count(rdp_b200_processor *p) { return p->impl.get_backend_device() ? rdpb_launch_count(p->impl.get_backend_device()) : 0; }
 uint64_t rdp_b200_primitive_count(rdp_b200_processor *p) { return p->impl.get_primitive_counter(); }
 uint64_t rdp_b200_pass_count(rdp_b200_processor *p) { return p->impl.get_pass_counter(); }
-void rdp_b200_host_timing(rdp_b200_processor *p, double out3[3]) { p->impl.get_host_timing(out3); }
+void rdp_b200_host_timing(rdp_b200_processor *p, double out4[4]) { p->impl.get_host_timing(out4); }
 void *rdp_b200_backend_device(rdp_b200_processor *p) { return p->impl.get_backend_device(); }
 int rdp_b200_set_command_thread_affinity(rdp_b200_processor *p, const int *cpus, unsigned num_cpus)
 {

@@ -746,8 +746,9 @@ uint64_t CommandProcessor::scanout_async(void *rgba, size_t capacity_pixels, uns
 	return fence;
 }
 
-void CommandProcessor::get_host_timing(double out[3]) const
+void CommandProcessor::get_host_timing(double out[4]) const
 {
+	out[3] = 1e-9 * double(renderer.get_backpressure_ns());
 	out[0] = 1e-9 * double(ring_busy_ns.load(std::memory_order_relaxed));
 	out[1] = 1e-9 * double(renderer.get_flush_ns());
 	out[2] = 1e-9 * double(scanout_ns.load(std::memory_order_relaxed));

@@ -137,8 +137,9 @@ public:
 	uint32_t get_upscaling_log2() const { return renderer.get_upscaling_log2(); }
 	uint64_t get_upscaled_pass_count() const { return renderer.get_upscaled_pass_count(); }
 	// Seconds the command thread spent [0] executing ring records in total, [1] inside pass submission
-	// (Renderer::flush_queues), [2] inside queued scan-outs.  [0] - [1] - [2] is command parsing / pass recording.
-	void get_host_timing(double out[3]) const;
+	// (Renderer::flush_queues), [2] inside queued scan-outs, [3] blocked on a staging slot the GPU has not released yet
+	// (back-pressure).  [0] - [1] - [2] - [3] is command parsing / pass recording.
+	void get_host_timing(double out[4]) const;
 	void set_command_thread_affinity(const std::vector<int> &cpus) { ring.set_affinity(cpus); }
 	void add_ring_busy_ns(uint64_t ns) { ring_busy_ns.fetch_add(ns, std::memory_order_relaxed); }
 

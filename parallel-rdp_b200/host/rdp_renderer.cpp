@@ -213,7 +213,13 @@ void Renderer::ensure_pass()
 {
 	if (pass_open)
 		return;
-	rdpb_pass_begin(device, &pass);
+	{
+		// May block until the staging slot's previous uploads (four passes ago) have left host memory: time spent here
+		// is back-pressure from the GPU, not command-thread work, and is reported apart (get_backpressure_ns).
+		const auto t0 = std::chrono::steady_clock::now();
+		rdpb_pass_begin(device, &pass);
+		backpressure_ns += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+	}
 	pass_open = true;
 	num_words = num_prims = num_states = num_uploads = num_spans = num_jobs = 0;
 	staged_words = 0;

@@ -119,6 +119,7 @@ public:
 	uint64_t get_primitive_counter() const { return base_primitive_index; }
 	uint64_t get_pass_counter() const { return pass_counter; }
 	uint64_t get_flush_ns() const { return flush_ns; }
+	uint64_t get_backpressure_ns() const { return backpressure_ns; }
 
 private:
 	rdpb_device *device = nullptr;
@@ -176,6 +177,7 @@ private:
 	uint32_t upscale_log2 = 0;
 	bool super_sampled_readback = false, super_sampled_dither = false;
 	uint64_t flush_ns = 0; // time spent submitting passes (written by the thread that drives the renderer)
+	uint64_t backpressure_ns = 0; // time blocked waiting for a staging slot (the GPU is behind)
 	bool tmem_snapshot_valid = false;
 
 	RdramMirror *mirror = nullptr;
