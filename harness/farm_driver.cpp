@@ -118,7 +118,7 @@ struct InFlight
 
 struct StreamRunner
 {
-	const farm_stream *s;
+	const farm_stream *s = nullptr;
 	std::vector<InFlight> ring;
 	uint32_t issued = 0;
 
@@ -231,8 +231,8 @@ int farm_run_pool(const farm_slot *slots, uint32_t num_slots, const farm_job *jo
 
 	struct SlotState
 	{
-		const farm_slot *slot;
-		farm_stream stream;
+		const farm_slot *slot = nullptr;
+		farm_stream stream = {};
 		StreamRunner runner;
 		const farm_job *job = nullptr;
 		uint32_t frame = 0;
