@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIBRARY = os.path.join(_HERE, "librdp_b200.so")
+# RDP_B200_LIBRARY: kernel experiments only (tools/build_variant.py builds alternative .so files next to the product).
+PRODUCT_LIBRARY = os.environ.get("RDP_B200_LIBRARY") or os.path.join(_HERE, "librdp_b200.so")
 
 VI_REG = {name: i for i, name in enumerate(
     ["Control", "Origin", "Width", "Intr", "VCurrentLine", "Timing", "VSync", "HSync", "Leap", "HStart", "VStart",

@@ -29,6 +29,7 @@
 
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <deque>
 #include <mutex>
 #include <stdio.h>
@@ -321,7 +322,7 @@ __device__ __forceinline__ void load_prim_for_shading(const PrimSetup *g, uint32
 	p.dstzw_dy[0] = int(tdy.x); p.dstzw_dy[1] = int(tdy.y); p.dstzw_dy[2] = int(tdy.z); p.dstzw_dy[3] = int(tdy.w);
 	p.span_base = span_base;
 	p.state_id = uint16_t(ids);
-	p.tmem_instance = uint16_t(ids >> 16);
+	p.tmem_instance = uint16_t((ids >> 16) & 0xffu); // (bits 30, 31 carry per-entry flags in the deferred walker)
 	p.line_lo = int16_t(lines);
 	p.line_hi = int16_t(lines >> 16);
 	p.dz = uint16_t(dzw);
@@ -502,6 +503,7 @@ __device__ __forceinline__ unsigned long long *counter_slot(const PassBuffers &b
 // covers a third of an 8x4 tile on average); here the expensive phases A and C run converged over dense slots and
 // only the two cheap ordered phases B and D depend on how many fragments one pixel has.
 constexpr uint32_t kDeferCapacity = 256; // fragment slots per batch (>= 32: one list entry always fits)
+constexpr uint32_t kEntryFill = 1u << 31, kEntryAa = 1u << 30; // DeferWarp::ids flag bits (state id: bits 0-15, TMEM snapshot: 16-23)
 
 // Second word of a shaded result (shade alpha + dither pattern): only states that dither or feed shade alpha to
 // the blender read it, so specialisations that cannot do either do not pay the shared memory for it.
@@ -525,6 +527,9 @@ struct alignas(16) DeferWarp
 	uint32_t cand[kDeferCapacity]; // A -> B: candidate word; B -> C, D: survivor record
 	uint32_t desc[kDeferCapacity]; // slot -> entry << 5 | pixel; after compaction: survivor -> slot << 16 | entry << 5 | pixel
 	uint32_t pixmask[32], base[32], prim[32], span_base[32], ids[32], lines[32], dzw[32]; // per list entry of the chunk
+	// What phase A needs of an entry's primitive and state besides the header, fetched once per entry by the mask phase
+	// instead of once per fragment: dz/dx, dz/dy, and (in ids, bits 31 / 30) whether the state is fill mode / anti-aliased.
+	int32_t dzdx[32], dzdy[32];
 	uint16_t list[kTileListCapacity];
 };
 static_assert(kDeferCapacity >= 32u * kGatherWords, "the next tile's mask words are staged in DeferWarp::desc (NextTilePrefetch::stage_masks)");
@@ -597,6 +602,10 @@ struct DeferredWalker
 				{
 					prefetch_l1(pp);
 					prefetch_l1(reinterpret_cast<const uint8_t *>(pp) + 128);
+					const uint32_t state_rf = __ldg(&b.states[hdr.y & 0xffffu].raster_flags);
+					hdr.y = (hdr.y & 0x00ffffffu) | ((state_rf & RF_FILL) ? kEntryFill : 0u) | ((state_rf & RF_AA) ? kEntryAa : 0u);
+					w.dzdx[lane] = __ldg(&pp->dstzw_dx[2]);
+					w.dzdy[lane] = __ldg(&pp->dstzw_dy[2]);
 				}
 			}
 			w.pixmask[lane] = pixmask;
@@ -665,19 +674,23 @@ struct DeferredWalker
 					const int fx = x0 + int(pix & 7u), fy = y0 + int(pix >> 3);
 					const int line_lo = int(int16_t(w.lines[j] & 0xffffu));
 					const Span *gs = b.spans + (w.span_base[j] + uint32_t(fy - line_lo));
-					const PrimSetup *gp = b.prims + w.prim[j];
+					const uint32_t ids = w.ids[j];
 					const uint4 *q = reinterpret_cast<const uint4 *>(gs);
-					const uint4 e = __ldg(q + 2), h = __ldg(q + 3);
-					Span sp;
-					sp.stzw[2] = __ldg(&gs->stzw[2]);
-					sp.xl[0] = uint16_t(e.x); sp.xl[1] = uint16_t(e.x >> 16); sp.xl[2] = uint16_t(e.y); sp.xl[3] = uint16_t(e.y >> 16);
-					sp.xr[0] = uint16_t(e.z); sp.xr[1] = uint16_t(e.z >> 16); sp.xr[2] = uint16_t(e.w); sp.xr[3] = uint16_t(e.w >> 16);
-					sp.start_x = int16_t(h.x); sp.end_x = int16_t(h.x >> 16);
-					sp.base_x = int(h.z);
-					PrimSetup p;
-					p.dstzw_dx[2] = __ldg(&gp->dstzw_dx[2]);
-					p.dstzw_dy[2] = __ldg(&gp->dstzw_dy[2]);
-					w.cand[k] = defer_candidate<S>(b.states[w.ids[j] & 0xffffu], p, sp, fx);
+					const uint4 h = __ldg(q + 3);
+					uint32_t cand;
+					if (ids & kEntryFill)
+						cand = (fx >= int(int16_t(h.x)) && fx <= int(int16_t(h.x >> 16))) ? (DC_VALID | DC_FILL) : 0u;
+					else
+					{
+						const uint4 e = __ldg(q + 2);
+						Span sp;
+						sp.stzw[2] = __ldg(&gs->stzw[2]);
+						sp.xl[0] = uint16_t(e.x); sp.xl[1] = uint16_t(e.x >> 16); sp.xl[2] = uint16_t(e.y); sp.xl[3] = uint16_t(e.y >> 16);
+						sp.xr[0] = uint16_t(e.z); sp.xr[1] = uint16_t(e.z >> 16); sp.xr[2] = uint16_t(e.w); sp.xr[3] = uint16_t(e.w >> 16);
+						sp.base_x = int(h.z);
+						cand = defer_candidate_shaded<S>((ids & kEntryAa) != 0u, w.dzdx[j], w.dzdy[j], sp, fx);
+					}
+					w.cand[k] = cand;
 				}
 				__syncwarp();
 
@@ -1495,6 +1508,9 @@ struct rdpb_device
 	uint32_t tile_blocks_per_sm_override = 0;
 	bool debug_summary = false;
 	bool bench_report = false; // PARALLEL_RDP_BENCH: per-kernel timing table on destroy
+	// Host time spent inside the backend's entry points, by kind (what the command thread pays for driver calls).
+	enum { HT_PASS_BEGIN, HT_UPLOAD, HT_FRONT, HT_SPAN, HT_TILES, HT_PASS_END, HT_VI, HT_READBACK, HT_COUNT };
+	uint64_t host_ns[HT_COUNT] = {}, host_calls[HT_COUNT] = {};
 	bool use_pdl = true;       // span kernel launched as a programmatic dependent of the set-up kernel (RDP_B200_NO_PDL turns it off)
 	std::string error;
 
@@ -1548,6 +1564,19 @@ static bool check(rdpb_device *dev, cudaError_t err, const char *what)
 }
 
 #define CK(call) do { if (!check(dev, (call), #call)) return -1; } while (0)
+
+struct HostTimer
+{
+	rdpb_device *dev;
+	int kind;
+	std::chrono::steady_clock::time_point t0;
+	HostTimer(rdpb_device *d, int k) : dev(d), kind(k), t0(std::chrono::steady_clock::now()) {}
+	~HostTimer()
+	{
+		dev->host_ns[kind] += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+		dev->host_calls[kind]++;
+	}
+};
 
 static void use_device(const rdpb_device *dev)
 {
@@ -2123,6 +2152,12 @@ void rdpb_device_destroy(rdpb_device *dev)
 			if (rdpb_profile_read(dev, k, &n, &ms) == 0 && n)
 				fprintf(stderr, "[rdp-b200]   %-32s %8u launches %12.3f ms  %9.3f us/launch\n", names[k], n, ms, 1e3 * ms / n);
 		}
+		static const char *host_names[rdpb_device::HT_COUNT] = { "pass_begin (staging wait)", "pass uploads", "launch front", "launch span",
+			                                                     "launch tiles", "pass_end", "vi scan-out", "scan-out read-back" };
+		for (int k = 0; k < rdpb_device::HT_COUNT; k++)
+			if (dev->host_calls[k])
+				fprintf(stderr, "[rdp-b200]   host: %-28s %8llu calls %10.3f ms  %8.3f us/call\n", host_names[k],
+				        (unsigned long long)dev->host_calls[k], 1e-6 * double(dev->host_ns[k]), 1e-3 * double(dev->host_ns[k]) / double(dev->host_calls[k]));
 	}
 	cudaFree(dev->rdram);
 	cudaFree(dev->hidden);
@@ -2270,6 +2305,7 @@ void *rdpb_hidden_device_ptr(rdpb_device *dev) { return dev->hidden; }
 
 int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
 {
+	HostTimer host_timer(dev, rdpb_device::HT_PASS_BEGIN);
 	use_device(dev);
 	dev->cur_parity = (dev->cur_parity + 1u) % kScratchSets;
 	dev->staging_index = (dev->staging_index + 1) % kStagingSlots;
@@ -2291,6 +2327,7 @@ int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
 
 int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 {
+	HostTimer host_timer(dev, rdpb_device::HT_UPLOAD);
 	use_device(dev);
 	const unsigned i = dev->staging_index;
 	const uint8_t *base = dev->staging[i];
@@ -2346,6 +2383,7 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 
 int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_words, uint32_t dst_word_offset)
 {
+	HostTimer host_timer(dev, rdpb_device::HT_UPLOAD);
 	use_device(dev);
 	if (!num_words)
 		return 0;
@@ -2361,6 +2399,7 @@ int rdpb_pass_upload_words(rdpb_device *dev, const uint32_t *src, uint32_t num_w
 
 int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, uint32_t num_prims)
 {
+	HostTimer host_timer(dev, rdpb_device::HT_FRONT);
 	use_device(dev);
 	// The host keeps one "snapshot 0 is current" flag; there are two snapshot sets here.  Refresh this pass's set when
 	// asked to, or when the pass samples TMEM and the set was last refreshed in an earlier TMEM epoch.
@@ -2388,6 +2427,7 @@ int rdpb_launch_front(rdpb_device *dev, int update_tmem, uint32_t num_uploads, u
 
 int rdpb_launch_span_bin(rdpb_device *dev, const void *fb_info)
 {
+	HostTimer host_timer(dev, rdpb_device::HT_SPAN);
 	use_device(dev);
 	GpuOp op = {};
 	op.kind = GOP_SPAN;
@@ -2401,6 +2441,7 @@ const char *rdpb_last_tile_variant(rdpb_device *dev) { return dev->last_variant 
 
 int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary)
 {
+	HostTimer host_timer(dev, rdpb_device::HT_TILES);
 	use_device(dev);
 	GpuOp op = {};
 	op.kind = GOP_TILES;
@@ -2420,6 +2461,7 @@ int rdpb_launch_tiles(rdpb_device *dev, const void *fb_info, const void *summary
 
 int rdpb_pass_end(rdpb_device *dev)
 {
+	HostTimer host_timer(dev, rdpb_device::HT_PASS_END);
 	use_device(dev);
 	if (dev->pass_upload_pending)
 	{
@@ -2503,6 +2545,7 @@ int rdpb_upscaled_read(rdpb_device *dev, void *rdram_dst, void *hidden_dst)
 
 int rdpb_launch_vi_scanout(rdpb_device *dev, const void *frame, const void *lines)
 {
+	HostTimer host_timer(dev, rdpb_device::HT_VI);
 	use_device(dev);
 	GpuOp op = {};
 	op.kind = GOP_VI;
@@ -2582,6 +2625,7 @@ static int signal_on(rdpb_device *dev, uint64_t value, cudaStream_t stream);
 // there: waiting for `fence_value` means the pixels are in `dst`.  The compute stream is never blocked by the copy.
 int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint32_t height, uint64_t fence_value)
 {
+	HostTimer host_timer(dev, rdpb_device::HT_READBACK);
 	use_device(dev);
 	// The copy follows the scan-out kernels on their own stream: nothing to order it behind them, and the next scan-out
 	// into this image (two fields later) queues behind the copy by itself.

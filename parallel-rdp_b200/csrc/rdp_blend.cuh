@@ -614,6 +614,22 @@ RDP_HD uint32_t defer_candidate(const PassState &st, const PrimSetup &p, const S
 	return uint32_t(z) | (uint32_t(coverage) << DC_COV_SHIFT) | DC_VALID;
 }
 
+// The same for a fragment of a state known not to be fill mode, from the few words phase A of the CUDA tile kernel keeps per
+// list entry (whether the state anti-aliases, dz/dx, dz/dy) instead of the state and the primitive themselves.
+template <class S>
+RDP_HD uint32_t defer_candidate_shaded(bool state_aa, int dzdx, int dzdy, const Span &sp, int x)
+{
+	const uint32_t rf = ((state_aa ? uint32_t(RF_AA) : 0u) & S::rf_may) | (S::rf_must & uint32_t(RF_AA));
+	const int coverage = shade_coverage(sp, x, rf);
+	if (coverage == 0)
+		return 0u;
+	PrimSetup p;
+	p.dstzw_dx[2] = dzdx;
+	p.dstzw_dy[2] = dzdy;
+	const int z = interpolate_depth(sp, p, x - sp.base_x, coverage);
+	return uint32_t(z) | (uint32_t(coverage) << DC_COV_SHIFT) | DC_VALID;
+}
+
 // Returns the survivor record, 0 when the fragment is rejected.  Updates depth, delta-Z and coverage of the pixel.
 // Fill fragments never come here (the caller writes them with fill_pixel and forgets the pixel's earlier survivors).
 template <class S>

@@ -105,7 +105,10 @@ struct Spec
 	// 5 (<= 96 registers) for the feature classes and the uber-kernel.
 	static constexpr int min_blocks_per_sm = EXACT ? 8 : 5;
 	// The deferred tile kernel (k_tiles<S, true>) keeps ~5 KiB of fragment slots per warp in shared memory.
-	static constexpr int min_blocks_per_sm_deferred = EXACT ? 8 : 4;
+#ifndef RDPB_DEFERRED_BLOCKS_EXACT
+#define RDPB_DEFERRED_BLOCKS_EXACT 8
+#endif
+	static constexpr int min_blocks_per_sm_deferred = EXACT ? RDPB_DEFERRED_BLOCKS_EXACT : 4;
 	// Whether the blender can read shade alpha (blender input 1B = 2) or the dither pattern: what the deferred
 	// kernel has to carry from its shade phase to its blend phase besides the combined colour.
 	static constexpr bool blend_reads_aux = !EXACT || ((BF_MAY | BF_MUST) & BF_DITHER) != 0u || ((BLEND_MISC >> 2) & 3u) == 2u ||
