@@ -216,7 +216,9 @@ class Stream:
         self.n = n_frames
         self.rdram_t = torch.from_numpy(workload.rdram_image(seed))
         rdram = self.rdram_t.numpy()
-        self.proc = rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, flags=workload.flags, cuda_device=local_rank)
+        # Explicit RDRAM synchronisation: the stream declares what the CPU writes (nothing, after the initial upload) and asks
+        # for rendered memory with signal_timeline when it wants it (the e2e_rdram leg); see include/rdp_b200.h.
+        self.proc = rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, flags=workload.flags | rdp.FLAG_EXPLICIT_RDRAM_SYNC, cuda_device=local_rank)
         hidden = workload.hidden_image(seed)
         self.proc.begin_read_hidden_rdram()[:] = 0 if hidden is None else hidden
         self.proc.end_write_hidden_rdram()
@@ -712,7 +714,8 @@ def run_farm(B: Bench, args):
     for i in range(n_native + n_up):
         up = i >= n_native
         rdram_t = torch.zeros(wl.RDRAM_SIZE, dtype=torch.uint8)
-        p = B.rdp.CommandProcessor(rdram_t.numpy(), wl.HIDDEN_SIZE, flags=farm.UPSCALING_4X if up else 0, cuda_device=B.local_rank)
+        p = B.rdp.CommandProcessor(rdram_t.numpy(), wl.HIDDEN_SIZE, flags=(farm.UPSCALING_4X if up else 0) | B.rdp.FLAG_EXPLICIT_RDRAM_SYNC,
+                                   cuda_device=B.local_rank)
         outs_t = [torch.empty(640 * 576, dtype=torch.int32).pin_memory() for _ in range(args.e2e_depth)]
         op = fn.pointer_array([t.numpy() for t in outs_t])
         slots[i].proc, slots[i].kind, slots[i].depth = p._h, 1 if up else 0, args.e2e_depth
@@ -843,8 +846,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--parity-frames", type=int, default=6, help="frames of stream 0 checked against the oracle before timing")
     ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 sub-results")
-    ap.add_argument("--e2e-depth", type=int, default=3, help="frames in flight per stream in the e2e leg")
-    ap.add_argument("--e2e-threads", type=int, default=4, help="producer threads of the native e2e loop (per rank)")
+    ap.add_argument("--e2e-depth", type=int, default=5, help="frames in flight per stream in the e2e leg")
+    ap.add_argument("--e2e-threads", type=int, default=8, help="producer threads of the native e2e loop (per rank)")
     ap.add_argument("--streams", default="1,2,4,8,16", help="concurrent independent streams per GPU to measure (comma list, divisors "
                                                           "of %d); value/e2e report the best, the sweep is kept in the JSON line" % FRAMES_PER_STEP)
     ap.add_argument("--farm-streams", type=int, default=1024, help="C5: independent streams in the farm (all GPUs together)")

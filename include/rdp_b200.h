@@ -32,7 +32,9 @@ enum
 	RDP_B200_FLAG_UPSCALING_4X = 1 << 3,
 	RDP_B200_FLAG_UPSCALING_8X = 1 << 4,
 	RDP_B200_FLAG_SUPER_SAMPLED_READ_BACK = 1 << 5,
-	RDP_B200_FLAG_SUPER_SAMPLED_DITHER = 1 << 6
+	RDP_B200_FLAG_SUPER_SAMPLED_DITHER = 1 << 6,
+	/* Extension: see "RDRAM coherency" below (rdp_b200_mark_rdram_written). */
+	RDP_B200_FLAG_EXPLICIT_RDRAM_SYNC = 1 << 16
 };
 
 /* VIRegister, rdp_common.hpp:324-341 */
@@ -106,8 +108,18 @@ void rdp_b200_set_quirks(rdp_b200_processor *p, int native_resolution_tex_rect, 
 /* Memory interaction, rdp_device.cpp:997-1036 */
 void *rdp_b200_begin_read_rdram(rdp_b200_processor *p);
 void rdp_b200_end_write_rdram(rdp_b200_processor *p);
-/* Extension (the CUDA replacement for VK_EXT_external_memory_host coherency; the reference's incoherent path tracks
- * 1 KiB pages, rdp_renderer.cpp:2523-2583): the CPU wrote RDRAM bytes [offset, offset + size).  May be called at any
+/* RDRAM coherency (the CUDA replacement for VK_EXT_external_memory_host; the reference's incoherent path,
+ * rdp_renderer.cpp:2523-2907).
+ * Default: `rdram_ptr` behaves like the reference's imported host memory.  The CPU writes it without telling anyone;
+ * whatever a command is about to make the GPU read -- a texture load's source, the colour / depth image of a render
+ * pass, the scan-out's framebuffer -- is uploaded first, except where a pass has rendered and the result has not come
+ * back yet ("GPU wins", as in the reference), and every pass's output is copied back right behind it.  That is two
+ * framebuffers' worth of PCIe traffic per pass: the reference's cost when it cannot import host memory.
+ * RDP_B200_FLAG_EXPLICIT_RDRAM_SYNC: the caller declares CPU writes (rdp_b200_mark_rdram_written, or
+ * rdp_b200_end_write_rdram for "anything") and asks for rendered memory with rdp_b200_signal_timeline(); nothing else
+ * crosses the bus.  The declarations work in the default mode as well.
+ *
+ * rdp_b200_mark_rdram_written: the CPU wrote RDRAM bytes [offset, offset + size).  May be called at any
  * time from the emulator thread.  The range is uploaded -- whole 1 KiB pages inside it, exact bytes at its two ends, so
  * nothing the CPU did not declare ever overwrites what the GPU rendered next to it -- before the next command that
  * makes the GPU read RDRAM (primitive, texture load, scan-out), in command order.  rdp_b200_end_write_rdram() is the

@@ -102,6 +102,7 @@ int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint
 /* Synchronisation. */
 int rdpb_signal(rdpb_device *dev, uint64_t value);   /* records a point in stream order */
 int rdpb_wait(rdpb_device *dev, uint64_t value);     /* blocks the calling thread until that point completed */
+int rdpb_poll(rdpb_device *dev, uint64_t value);     /* non-blocking: 1 = that point has completed, 0 = still pending */
 int rdpb_sync(rdpb_device *dev);
 void *rdpb_stream(rdpb_device *dev);                 /* cudaStream_t for interop/benchmark timing */
 

@@ -19,6 +19,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # RDP_B200_LIBRARY: kernel experiments only (tools/build_variant.py builds alternative .so files next to the product).
 PRODUCT_LIBRARY = os.environ.get("RDP_B200_LIBRARY") or os.path.join(_HERE, "librdp_b200.so")
 
+FLAG_EXPLICIT_RDRAM_SYNC = 1 << 16  # RDP_B200_FLAG_EXPLICIT_RDRAM_SYNC (include/rdp_b200.h, "RDRAM coherency")
+
 VI_REG = {name: i for i, name in enumerate(
     ["Control", "Origin", "Width", "Intr", "VCurrentLine", "Timing", "VSync", "HSync", "Leap", "HStart", "VStart",
      "VBurst", "XScale", "YScale"])}

@@ -41,6 +41,20 @@
 
 using namespace rdpb;
 
+// Unroll factors of the deferred tile kernel's two dense phases (experiment knobs; 1 = as written).
+#define RDPB_PRAGMA_(x) _Pragma(#x)
+#define RDPB_PRAGMA(x) RDPB_PRAGMA_(x)
+#ifdef RDPB_EXP_UNROLL_A
+#define RDPB_UNROLL_A RDPB_PRAGMA(unroll RDPB_EXP_UNROLL_A)
+#else
+#define RDPB_UNROLL_A
+#endif
+#ifdef RDPB_EXP_UNROLL_C
+#define RDPB_UNROLL_C RDPB_PRAGMA(unroll RDPB_EXP_UNROLL_C)
+#else
+#define RDPB_UNROLL_C
+#endif
+
 // Every processor owns three CUDA streams (compute, upload, read-back).  With the driver's default of 8 hardware work
 // queues, eight processors on one GPU make unrelated streams share a queue and wait on each other; ask for more
 // before the context exists.  (Read at context creation: a host that initialises CUDA before loading this library
@@ -667,6 +681,7 @@ struct DeferredWalker
 				__syncwarp();
 
 				// ---- A: coverage + Z of every fragment ----
+				RDPB_UNROLL_A
 				for (uint32_t k = lane; k < count; k += 32u)
 				{
 					const uint32_t d = w.desc[k];
@@ -742,6 +757,7 @@ struct DeferredWalker
 					next.issue(b, fb, view.fmt, lane, !stage_next);
 
 				// ---- C: shade the survivors ----
+				RDPB_UNROLL_C
 				for (uint32_t k2 = lane; k2 < n2; k2 += 32u)
 				{
 					const uint32_t d = w.desc[k2];
@@ -2724,6 +2740,31 @@ int rdpb_wait(rdpb_device *dev, uint64_t value)
 	std::lock_guard<std::mutex> holder{dev->timeline_lock};
 	dev->free_events.push_back(ev);
 	return 0;
+}
+
+// Non-blocking: 1 when the point `value` has completed (or was retired before), 0 while it is pending.
+int rdpb_poll(rdpb_device *dev, uint64_t value)
+{
+	use_device(dev);
+	std::lock_guard<std::mutex> holder{dev->timeline_lock};
+	for (auto &queue : dev->timeline)
+	{
+		for (size_t i = 0; i < queue.size(); i++)
+		{
+			if (queue[i].first != value)
+				continue;
+			const cudaError_t e = cudaEventQuery(queue[i].second);
+			if (e == cudaErrorNotReady)
+				return 0;
+			cudaGetLastError();
+			// Complete: so is everything recorded before it on the same stream.
+			for (size_t k = 0; k <= i; k++)
+				dev->free_events.push_back(queue[k].second);
+			queue.erase(queue.begin(), queue.begin() + long(i) + 1);
+			return 1;
+		}
+	}
+	return 1;
 }
 
 int rdpb_sync(rdpb_device *dev)

@@ -7,6 +7,7 @@
 // Triangles and rectangles are *not* decoded here: their raw words go to the renderer and are decoded on the GPU.
 #include "rdp_device.hpp"
 #include "rdp_setup.cuh"
+#include <algorithm>
 #include <chrono>
 #include <stdio.h>
 #include <stdlib.h>
@@ -48,8 +49,16 @@ CommandProcessor::CommandProcessor(const DeviceConfig &config, void *rdram_ptr, 
 	mirror.init(rdram_size);
 	mirror.mark_all_written();
 	renderer.set_rdram_mirror(&mirror);
+	implicit_coherency = (flags & COMMAND_PROCESSOR_FLAG_EXPLICIT_RDRAM_SYNC_BIT) == 0;
+	if (implicit_coherency)
+		renderer.set_rdram_coherency(this);
 
-	host_hidden.assign(hidden_size, 0x03);
+	// The host-side copy handed out by begin_read_hidden_rdram() is never smaller than the hidden RDRAM of a full 8 MiB
+	// machine, whatever size the caller asked for: the reference's own conformance harness sizes its writes through
+	// this pointer by the *oracle's* hidden array (conformance_utils.hpp:372-381 with replayer_driver_angrylion.cpp:
+	// 70-73: 4 MiB against the 2 MiB it creates the processor with), which the reference survives only because its
+	// pointer leads into a larger mapped allocation.  Only the first hidden_size bytes are ever copied either way.
+	host_hidden.assign(std::max<size_t>(hidden_size, size_t(4) << 20), 0x03);
 	rdpb_hidden_fill(device, 0x03);
 	memset(rdpb_tmem_host_ptr(device), 0, kTmemBytes);
 
@@ -214,6 +223,29 @@ void CommandProcessor::op_load(const uint32_t *w, UploadMode mode)
 	info.tlo = w[0] & 0xfff;
 	info.thi = w[1] & 0xfff;
 	info.mode = mode;
+	if (implicit_coherency)
+	{
+		// The bytes this load can fetch, generously: whole rows from the first to the last for tile / TLUT loads, the texel
+		// run of a block load (at most 2048 texels of 32 bits), a cache line of slack on either side.
+		const uint64_t row = (uint64_t(info.tex_width) << unsigned(info.size)) >> 1;
+		uint64_t lo, hi;
+		if (mode == UploadMode::Block)
+		{
+			lo = info.tex_addr + (((uint64_t(info.tex_width) * info.tlo + info.slo) << unsigned(info.size)) >> 1);
+			hi = lo + (uint64_t((info.shi - info.slo + 1) & 0xfff) << 2) + 8;
+		}
+		else
+		{
+			lo = info.tex_addr + row * (info.tlo >> 2);
+			hi = info.tex_addr + row * ((info.thi >> 2) + 1) + 8;
+		}
+		lo = lo > 64 ? lo - 64 : 0;
+		hi += 64;
+		if (hi > lo && hi - lo < rdram_size)
+			gpu_will_read(uint32_t(lo), uint32_t(hi - lo));
+		else
+			gpu_will_read(0, uint32_t(rdram_size));
+	}
 	renderer.load_tile((w[1] >> 24) & 7, info);
 }
 
@@ -333,7 +365,14 @@ void CommandProcessor::execute_meta(RingMeta kind, const uint32_t *payload, unsi
 		// the rendered ranges travel back behind everything submitted so far; the point is recorded behind the copies.
 		sync_host_rdram_to_device();
 		if (!readback_gpu_writes(value, false))
-			rdpb_signal(device, value);
+		{
+			// Nothing left to send -- but copies started after earlier passes (implicit coherency) may still be in flight:
+			// the point then goes behind them on the read-back stream.
+			if (mirror.has_inflight())
+				rdpb_rdram_read_fenced(device, host_rdram, nullptr, 0, value);
+			else
+				rdpb_signal(device, value);
+		}
 		signalled_timeline.store(value, std::memory_order_release);
 		break;
 	}
@@ -547,6 +586,48 @@ bool CommandProcessor::readback_gpu_writes(uint64_t fence_value, bool wait)
 	return false;
 }
 
+// ---- implicit coherency (default; the reference's incoherent path, rdp_renderer.cpp:2523-2907) ----
+// Host memory is authoritative except where a pass has rendered and the result has not been returned yet: before the GPU
+// reads a range, the host-authoritative parts of it are uploaded (the CPU may have written them without saying so).
+void CommandProcessor::gpu_will_read(uint32_t addr, uint32_t bytes)
+{
+	if (!implicit_coherency || !bytes)
+		return;
+	sync_host_rdram_to_device(); // declared writes first (also resolves "everything may have changed")
+	if (mirror.has_inflight())
+		mirror.retire_inflight([&](uint64_t fence) { return rdpb_poll(device, fence) != 0; });
+	addr &= uint32_t(rdram_size - 1);
+	uint32_t pieces[2][2] = { { addr, uint32_t(std::min<uint64_t>(uint64_t(addr) + bytes, rdram_size)) }, { 0, 0 } };
+	if (uint64_t(addr) + bytes > rdram_size)
+		pieces[1][1] = uint32_t(std::min<uint64_t>(uint64_t(addr) + bytes - rdram_size, addr)); // wrapped tail
+	std::vector<std::pair<uint32_t, uint32_t>> runs;
+	for (auto &piece : pieces)
+		if (piece[1] > piece[0])
+			mirror.host_authoritative_runs(piece[0], piece[1], runs);
+	for (auto &r : runs)
+	{
+		rdpb_rdram_write(device, r.first, host_rdram + r.first, r.second, host_rdram_registered ? 0 : 1);
+		mirror.count_upload(r.second);
+	}
+}
+
+// A rendering pass has been submitted: its output starts travelling back right away, behind it on the read-back
+// stream (the reference copies back on every submit with pending render passes, rdp_renderer.cpp:2437-2458).
+void CommandProcessor::pass_submitted()
+{
+	if (!implicit_coherency || !mirror.has_gpu_writes())
+		return;
+	const uint64_t fence = (1ull << 62) | ++internal_fence_counter;
+	if (!host_rdram_registered)
+	{
+		readback_gpu_writes(0, true);
+		return;
+	}
+	for (auto &r : mirror.pending_gpu_ranges())
+		mirror.add_inflight(r.first, r.second, fence);
+	readback_gpu_writes(fence, false);
+}
+
 void CommandProcessor::mark_rdram_written(size_t offset, size_t size)
 {
 	mirror.mark_written(offset, size);
@@ -696,6 +777,15 @@ ScanoutImage CommandProcessor::scanout(const ScanoutOptions &opts)
 	std::lock_guard<std::mutex> holder{idle_lock};
 	renderer.flush_queues();
 	sync_host_rdram_to_device();
+	if (implicit_coherency)
+	{
+		// ref rdp_device.cpp:1099-1104: the framebuffer the VI is about to read may be CPU-drawn.
+		VideoInterface::RegisterFile file;
+		vi.peek_registers(file);
+		uint32_t offset = 0, length = 0;
+		if (vi.scanout_memory_range(file, offset, length))
+			gpu_will_read(offset, length);
+	}
 	return vi.scanout(opts);
 }
 
@@ -766,6 +856,12 @@ void CommandProcessor::execute_scanout_request(ScanoutRequest *req)
 	std::lock_guard<std::mutex> holder{idle_lock};
 	renderer.flush_queues();
 	sync_host_rdram_to_device();
+	if (implicit_coherency)
+	{
+		uint32_t offset = 0, length = 0;
+		if (vi.scanout_memory_range(req->registers, offset, length))
+			gpu_will_read(offset, length);
+	}
 	const ScanoutImage img = vi.scanout(req->opts, req->registers);
 	unsigned w = img ? img.width : 0, h = img ? img.height : 0;
 	if (!img || size_t(w) * h > req->capacity_pixels)

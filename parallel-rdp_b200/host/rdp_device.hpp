@@ -32,7 +32,15 @@ enum CommandProcessorFlagBits
 	COMMAND_PROCESSOR_FLAG_UPSCALING_4X_BIT = 1 << 3,
 	COMMAND_PROCESSOR_FLAG_UPSCALING_8X_BIT = 1 << 4,
 	COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_READ_BACK_BIT = 1 << 5,
-	COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_DITHER_BIT = 1 << 6
+	COMMAND_PROCESSOR_FLAG_SUPER_SAMPLED_DITHER_BIT = 1 << 6,
+	// Extension (not a reference flag).  By default the caller's RDRAM behaves like the reference's imported host memory:
+	// the CPU writes it without telling anyone and the processor makes the GPU see it -- every range a command is about
+	// to read (texture-load sources, the colour / depth image of a pass, the scan-out's framebuffer) is uploaded first
+	// unless a pass has rendered to it and the result has not been returned yet, and every pass's output is copied
+	// back right after it (the reference's incoherent path: rdp_renderer.cpp:2523-2907).  With this bit the caller
+	// promises to declare CPU writes (mark_rdram_written / end_write_rdram) and to ask for the rendered memory with
+	// signal_timeline(): nothing else crosses the bus.
+	COMMAND_PROCESSOR_FLAG_EXPLICIT_RDRAM_SYNC_BIT = 1 << 16
 };
 using CommandProcessorFlags = uint32_t;
 
@@ -63,7 +71,7 @@ struct DeviceConfig
 	int cuda_device = 0;
 };
 
-class CommandProcessor
+class CommandProcessor : private RdramCoherencyInterface
 {
 public:
 	CommandProcessor(const DeviceConfig &device, void *rdram_ptr, size_t rdram_offset, size_t rdram_size,
@@ -167,6 +175,11 @@ private:
 	void dump_end_frame();
 
 	RdramMirror mirror; // what the CPU wrote since the last upload / what passes rendered since the last read-back
+	bool implicit_coherency = true; // !COMMAND_PROCESSOR_FLAG_EXPLICIT_RDRAM_SYNC_BIT
+	uint64_t internal_fence_counter = 0;
+	// RdramCoherencyInterface (rdp_renderer.hpp): what the renderer tells the processor around every pass.
+	void gpu_will_read(uint32_t addr, uint32_t bytes) override;
+	void pass_submitted() override;
 	std::mutex idle_lock;
 
 	Renderer renderer;

@@ -237,7 +237,10 @@ void RDPDumpWriter::flush_hidden_dram(const void *dram, uint32_t size)
 void RDPDumpWriter::signal_complete()
 {
 	if (fp)
+	{
 		put_u32(uint32_t(DumpCommand::SignalComplete));
+		fflush(fp); // a dump is a debugging aid: keep it usable when the process dies before the writer is closed
+	}
 }
 
 void RDPDumpWriter::emit_command(uint32_t command, const uint32_t *cmd_data, uint32_t cmd_words)
@@ -262,6 +265,9 @@ void RDPDumpWriter::set_vi_register(uint32_t vi_register, uint32_t value)
 void RDPDumpWriter::end_frame()
 {
 	if (fp)
+	{
 		put_u32(uint32_t(DumpCommand::EndFrame));
+		fflush(fp);
+	}
 }
 }

@@ -637,6 +637,15 @@ void Renderer::flush_queues()
 		// With super-sampled read-back (ref rdp_renderer.cpp:2296-2334, 2955-2980) there is no native pass at all: PRE,
 		// the upscaled pass recording which native pixels it stored to, then the resolve that averages those pixels'
 		// samples into native RDRAM (and the shadow).
+		// Implicit RDRAM coherency: what the CPU may have put into the images this pass reads goes up first (ordered on
+		// the compute stream, in front of the tile kernel).
+		if (coherency)
+		{
+			const uint32_t px = info.width * info.height;
+			const uint32_t cbpp = fb.fmt == FBFormat::RGBA8888 ? 4 : ((fb.fmt == FBFormat::RGBA5551 || fb.fmt == FBFormat::IA88) ? 2 : 1);
+			coherency->gpu_will_read(fb.addr, px * cbpp);
+			coherency->gpu_will_read(fb.depth_addr, px * 2);
+		}
 		const bool ssaa = super_sampled_readback && upscale_log2 != 0 && pass_can_super_sample(info, upscale_log2);
 		const bool upscale = ssaa || (upscale_log2 != 0 && pass_wants_upscaling(info, upscale_log2));
 		if (!ssaa)
@@ -680,6 +689,8 @@ void Renderer::flush_queues()
 		rendered_ranges_valid = false; // nothing rendered: nothing for the next pass's loads to collide with
 	uploads_may_read_previous_pass = false;
 	rdpb_pass_end(device);
+	if (need_render && coherency)
+		coherency->pass_submitted();
 	pass_counter++;
 	flush_ns += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - flush_t0).count());
 

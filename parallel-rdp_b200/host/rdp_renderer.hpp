@@ -78,6 +78,16 @@ struct ValidationInterface
 	virtual void report_rdp_crash(ValidationError err, const char *msg) = 0;
 };
 
+// What the renderer tells the owner of the RDRAM mirror around every pass (implicit coherency; rdp_device.hpp).
+struct RdramCoherencyInterface
+{
+	virtual ~RdramCoherencyInterface() = default;
+	// The pass about to be submitted reads RDRAM bytes [addr, addr + bytes) (colour / depth image).
+	virtual void gpu_will_read(uint32_t addr, uint32_t bytes) = 0;
+	// A pass that renders has been submitted (its written ranges have been noted in the mirror).
+	virtual void pass_submitted() = 0;
+};
+
 class Renderer
 {
 public:
@@ -114,6 +124,7 @@ public:
 	void flush_queues();
 	// Where passes note the byte ranges they render to (device -> host side of the RDRAM mirror).
 	void set_rdram_mirror(RdramMirror *m) { mirror = m; }
+	void set_rdram_coherency(RdramCoherencyInterface *c) { coherency = c; }
 	void invalidate_tmem_snapshot() { tmem_snapshot_valid = false; }
 
 	uint64_t get_primitive_counter() const { return base_primitive_index; }
@@ -181,6 +192,7 @@ private:
 	bool tmem_snapshot_valid = false;
 
 	RdramMirror *mirror = nullptr;
+	RdramCoherencyInterface *coherency = nullptr;
 
 	void ensure_pass();
 	void snapshot_state();

@@ -170,6 +170,50 @@ public:
 		gpu_ranges.clear();
 	}
 
+	// ---- read-backs in flight (command thread only): device bytes newer than the host's until the copy has landed ----
+	void add_inflight(uint32_t lo, uint32_t hi, uint64_t fence) { inflight.push_back({ lo, hi, fence }); }
+	// `complete(fence)` -> true once the read-back behind that fence has landed; forgets those.
+	template <class F>
+	void retire_inflight(F &&complete)
+	{
+		size_t out = 0;
+		for (size_t i = 0; i < inflight.size(); i++)
+			if (!complete(inflight[i].fence))
+				inflight[out++] = inflight[i];
+		inflight.resize(out);
+	}
+	bool has_inflight() const { return !inflight.empty(); }
+
+	// The parts of [lo, hi) for which host memory is authoritative: everything except what passes have rendered to and
+	// not yet returned (pending, or a read-back still in flight).  The reference's rule -- "writes made by the GPU which
+	// are not known to be resolved ... will always win over writes made by CPU" (rdp_renderer.cpp:2709-2716) -- at range
+	// instead of byte granularity.
+	void host_authoritative_runs(uint32_t lo, uint32_t hi, std::vector<std::pair<uint32_t, uint32_t>> &out) const
+	{
+		std::vector<std::pair<uint32_t, uint32_t>> owned;
+		for (auto &r : gpu_ranges)
+			if (r.first < hi && lo < r.second)
+				owned.emplace_back(std::max(r.first, lo), std::min(r.second, hi));
+		for (auto &r : inflight)
+			if (r.lo < hi && lo < r.hi)
+				owned.emplace_back(std::max(r.lo, lo), std::min(r.hi, hi));
+		std::sort(owned.begin(), owned.end());
+		uint32_t at = lo;
+		for (auto &o : owned)
+		{
+			if (o.first > at)
+				out.emplace_back(at, o.first - at);
+			at = std::max(at, o.second);
+		}
+		if (at < hi)
+			out.emplace_back(at, hi - at);
+	}
+	void count_upload(uint32_t bytes)
+	{
+		stats.h2d_bytes += bytes;
+		stats.h2d_copies++;
+	}
+
 	Stats get_stats() const { return stats; }
 
 private:
@@ -180,6 +224,8 @@ private:
 	std::vector<uint64_t> dirty_pages;
 	std::vector<std::pair<uint32_t, uint32_t>> fragments; // [lo, hi) byte ranges smaller than a page
 	std::vector<std::pair<uint32_t, uint32_t>> gpu_ranges; // sorted, disjoint
+	struct Inflight { uint32_t lo, hi; uint64_t fence; };
+	std::vector<Inflight> inflight;
 	Stats stats;
 
 	void add_fragment(uint32_t lo, uint32_t hi)

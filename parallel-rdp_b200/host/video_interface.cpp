@@ -238,6 +238,40 @@ void VideoInterface::capture_registers(RegisterFile &out)
 	clear_per_scanline_state();
 }
 
+// RDRAM bytes a scan-out with these registers can read (ref scanout_memory_range, video_interface.cpp:369-396): the
+// displayed rows with a 2-pixel border for the AA / dither filters plus one more column for the divot.
+void VideoInterface::vram_range(const ViRegs &regs, bool divot, int64_t &offset, int64_t &length)
+{
+	const int pixel_size_log2 = (regs.status & VI_CONTROL_TYPE_MASK) == VI_CONTROL_TYPE_RGBA8888_BIT ? 2 : 1;
+	const int aa_width = regs.max_x + 2 + 4 + int(divot) * 2;
+	const int aa_height = regs.max_y + 1 + 4;
+	offset = regs.vi_offset & ~((1 << pixel_size_log2) - 1);
+	offset += int64_t((divot ? -3 : -2) + -2 * regs.vi_width) << pixel_size_log2;
+	length = (int64_t(aa_height) * regs.vi_width + aa_width) << pixel_size_log2;
+}
+
+bool VideoInterface::scanout_memory_range(const RegisterFile &file, uint32_t &offset, uint32_t &length) const
+{
+	ViLine lines[VI_MAX_OUTPUT_SCANLINES];
+	const ViRegs regs = decode_vi_registers(file, lines);
+	if (regs.vi_offset == 0 || (regs.status & VI_CONTROL_TYPE_RGBA5551_BIT) == 0)
+		return false;
+	int64_t o = 0, l = 0;
+	vram_range(regs, true, o, l);
+	if (l <= 0)
+		return false;
+	// Clamp to RDRAM (a range that runs off either end is read modulo the RDRAM size by the kernels: be generous).
+	if (o < 0 || o + l > int64_t(rdram_size))
+	{
+		offset = 0;
+		length = uint32_t(rdram_size);
+		return true;
+	}
+	offset = uint32_t(o);
+	length = uint32_t(l);
+	return true;
+}
+
 ScanoutImage VideoInterface::scanout(const ScanoutOptions &options)
 {
 	RegisterFile file;
@@ -315,11 +349,8 @@ ScanoutImage VideoInterface::scanout(const ScanoutOptions &options, const Regist
 	uint32_t vram_lo = 0, vram_hi = 0;
 	{
 		const int pixel_size_log2 = (regs.status & VI_CONTROL_TYPE_MASK) == VI_CONTROL_TYPE_RGBA8888_BIT ? 2 : 1;
-		const int aa_width = regs.max_x + 2 + 4 + int(divot) * 2;
-		const int aa_height = regs.max_y + 1 + 4;
-		int64_t offset = regs.vi_offset & ~((1 << pixel_size_log2) - 1);
-		offset += int64_t((divot ? -3 : -2) + -2 * regs.vi_width) << pixel_size_log2;
-		const int64_t length = (int64_t(aa_height) * regs.vi_width + aa_width) << pixel_size_log2;
+		int64_t offset = 0, length = 0;
+		vram_range(regs, divot, offset, length);
 		if (offset >= 0 && length > 0 && offset + length <= int64_t(rdram_size))
 		{
 			vram_lo = uint32_t(offset);

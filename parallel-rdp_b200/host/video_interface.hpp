@@ -152,6 +152,10 @@ public:
 	void set_upscaling_log2(uint32_t log2) { scale_log2 = log2; }
 	void set_vi_register(VIRegister reg, uint32_t value);
 	// Copies the register file for one scan-out and resets the per-scanline latches (as scanout() always did).
+	// The registers as capture_registers() would hand them out, without consuming the per-scanline state.
+	void peek_registers(RegisterFile &out) const { out = regfile; }
+	// RDRAM byte range a scan-out with these registers can read; false when nothing would be scanned out.
+	bool scanout_memory_range(const RegisterFile &file, uint32_t &offset, uint32_t &length) const;
 	void capture_registers(RegisterFile &out);
 	ScanoutImage scanout(const ScanoutOptions &options, const RegisterFile &file);
 	ScanoutImage scanout(const ScanoutOptions &options);
@@ -175,6 +179,7 @@ private:
 	unsigned prev_result_width = 0, prev_result_height = 0; // what scanout() returned (after downscale steps)
 
 	rdpb::ViRegs decode_vi_registers(const RegisterFile &file, rdpb::ViLine *lines) const;
+	static void vram_range(const rdpb::ViRegs &regs, bool divot, int64_t &offset, int64_t &length);
 	void clear_per_scanline_state();
 };
 }

@@ -678,6 +678,7 @@ int rdpb_vi_read_output_fenced(rdpb_device *dev, void *dst, uint32_t width, uint
 int rdpb_vi_join(rdpb_device *) { return 0; }
 int rdpb_signal(rdpb_device *, uint64_t) { return 0; }
 int rdpb_wait(rdpb_device *, uint64_t) { return 0; }
+int rdpb_poll(rdpb_device *, uint64_t) { return 1; }
 int rdpb_sync(rdpb_device *) { return 0; }
 void *rdpb_stream(rdpb_device *) { return nullptr; }
 uint64_t rdpb_launch_count(rdpb_device *dev) { return dev->launches; }

@@ -26,11 +26,13 @@ COLOR, DEPTH, BETWEEN = 0x100000, 0x140000, 0x130000  # 320x240 RGBA16 = 0x25800
 BACKENDS = [pytest.param(HOSTSIM_LIB, id="hostsim"), pytest.param(None, id="cuda", marks=pytest.mark.gpu)]
 
 
-def _proc(library=HOSTSIM_LIB):
+def _proc(library=HOSTSIM_LIB, explicit=True):
+    """explicit: RDP_B200_FLAG_EXPLICIT_RDRAM_SYNC -- CPU writes are declared, nothing else crosses the bus (what the byte
+    counts below are about); False: the default, the reference's imported-host-memory behaviour."""
     if library is not None:
         build_hostsim()
     rdram = np.zeros(wl.RDRAM_SIZE, dtype=np.uint8)
-    p = rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, library=library)
+    p = rdp.CommandProcessor(rdram, wl.HIDDEN_SIZE, flags=rdp.FLAG_EXPLICIT_RDRAM_SYNC if explicit else 0, library=library)
     p.begin_read_hidden_rdram()[:] = 0
     p.end_write_hidden_rdram()
     p.end_write_rdram()
@@ -227,3 +229,47 @@ def test_scanout_fence_survives_interleaved_idle(library):
         assert w == 640 and h in (240, 480) and buf[: w * h].any()
     finally:
         p.close()
+
+
+@pytest.mark.parametrize("library", BACKENDS)
+def test_default_mode_sees_undeclared_cpu_writes(library):
+    """The reference's contract (integration_example.cpp:490, rdp_conformance.cpp:609-665): the emulator writes RDRAM through
+    the pointer it handed over and calls nothing.  By default a texture load's source, a pass's colour / depth image and
+    the scan-out's framebuffer are uploaded before the GPU reads them, and rendered memory comes back by itself."""
+    p = _proc(library, explicit=False)
+    o = angrylion.Oracle(wl.RDRAM_SIZE)
+    try:
+        o.rdram[:] = 0
+        o.hidden[:] = 0
+        rng = np.random.RandomState(9)
+        for it in range(3):
+            # undeclared: a texture, and a CPU-drawn background in the colour image
+            tex = rng.randint(0, 256, 2048).astype(np.uint8)
+            back = rng.randint(0, 256, 320 * 8 * 2).astype(np.uint8)
+            for mem in (p.rdram, o.rdram):
+                mem[BETWEEN:BETWEEN + 2048] = tex
+                mem[COLOR + 320 * 2 * 100:COLOR + 320 * 2 * 108] = back
+            b = rb.Builder()
+            b.set_color_image(rb.FMT_RGBA, rb.SIZE_16, COLOR, 320)
+            b.set_depth_image(DEPTH)
+            b.set_scissor(0, 0, 320, 240)
+            b.set_texture_image(BETWEEN, rb.FMT_RGBA, rb.SIZE_16, 32)
+            b.set_tile(0, rb.FMT_RGBA, rb.SIZE_16, 64, 0, mask_s=5, mask_t=5)
+            b.load_tile(0, 0, 0, 32, 32)
+            b.set_tile_size(0, 0, 0, 32, 32)
+            b.om.__init__()
+            b.om.cycle_type = rb.CYCLE_COPY
+            b.touch_other_modes()
+            b.tex_rect(0, (16 + 40 * it) << 2, 16 << 2, 32 << 2, 32 << 2, 0, 0, 4 << 10, 1 << 10)
+            b.sync_full()
+            words = b.words()
+            p.enqueue_command_stream(words)
+            o.command_stream(words)
+            # no idle(): wait for the timeline the way an emulator does after SyncFull
+            p.wait_for_timeline(p.signal_timeline())
+            assert np.array_equal(p.rdram, o.rdram), f"iteration {it}: RDRAM differs from the oracle"
+        st = p.rdram_mirror_stats()
+        assert st["h2d_bytes"] > 0 and st["d2h_bytes"] > 0
+    finally:
+        p.close()
+        o.close()
