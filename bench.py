@@ -392,15 +392,21 @@ class Bench:
             st.proc.idle()
         self.barrier()
         host_t0 = [st.proc.host_timing() for st in streams]
+        cpu0 = time.process_time()
         t0 = time.perf_counter()
         if self.farm.farm_run(arr, S, 0, frames_per_stream, threads, flags) != 0:
             raise SystemExit("bench.py: scan-out failed in the e2e leg")
         for st in streams:
             st.proc.idle()
         self.torch.cuda.synchronize()
-        ms = self.max_over_ranks((time.perf_counter() - t0) * 1e3)
+        wall = time.perf_counter() - t0
+        cpu = time.process_time() - cpu0
+        ms = self.max_over_ranks(wall * 1e3)
         host_t1 = [st.proc.host_timing() for st in streams]
         host_us = {k: round(1e6 * sum(b[k] - a[k] for a, b in zip(host_t0, host_t1)) / (frames_per_stream * S), 2) for k in host_t1[0]}
+        # CPU time of the whole process (command threads, producer threads, driver threads) per frame, and cores kept busy.
+        host_us["process_cpu_us"] = round(1e6 * cpu / (frames_per_stream * S), 2)
+        host_us["cores_busy"] = round(cpu / wall, 2)
         self.barrier()
         return ms, host_us, threads
 

@@ -69,6 +69,11 @@ void *rdpb_tmem_host_ptr(rdpb_device *dev);
 void *rdpb_rdram_device_ptr(rdpb_device *dev);
 void *rdpb_hidden_device_ptr(rdpb_device *dev);
 
+/* Brackets a batch of submission calls (a whole pass, a scan-out + its read-back): the CUDA backend serialises the
+ * batches of all processors on one GPU so that their command threads do not contend call by call for the driver. */
+void rdpb_submit_begin(rdpb_device *dev);
+void rdpb_submit_end(rdpb_device *dev);
+
 /* Pass recording and submission. */
 int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out);
 /* Uploads records / states / texture-load descriptors of the pass from the staging area; command words follow as

@@ -862,6 +862,7 @@ void CommandProcessor::execute_scanout_request(ScanoutRequest *req)
 		if (vi.scanout_memory_range(req->registers, offset, length))
 			gpu_will_read(offset, length);
 	}
+	rdpb_submit_begin(device);
 	const ScanoutImage img = vi.scanout(req->opts, req->registers);
 	unsigned w = img ? img.width : 0, h = img ? img.height : 0;
 	if (!img || size_t(w) * h > req->capacity_pixels)
@@ -871,6 +872,7 @@ void CommandProcessor::execute_scanout_request(ScanoutRequest *req)
 	if (req->height)
 		*req->height = h;
 	rdpb_vi_read_output_fenced(device, req->rgba, w, h, req->fence);
+	rdpb_submit_end(device);
 	recorded_scanout_fence.store(req->fence & ~(1ull << 63), std::memory_order_release);
 	delete req;
 }

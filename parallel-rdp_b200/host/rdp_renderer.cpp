@@ -586,6 +586,12 @@ void Renderer::flush_queues()
 		return;
 
 	const auto flush_t0 = std::chrono::steady_clock::now();
+	struct SubmitBatch
+	{
+		rdpb_device *d;
+		explicit SubmitBatch(rdpb_device *d_) : d(d_) { rdpb_submit_begin(d); }
+		~SubmitBatch() { rdpb_submit_end(d); }
+	} submit_batch{device};
 	rdpb_pass_counts counts = {};
 	counts.num_words = num_words;
 	counts.num_prims = num_prims;

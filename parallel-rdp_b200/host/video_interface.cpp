@@ -1,5 +1,12 @@
 // video_interface.cpp -- VI register decode and scan-out sequencing; see video_interface.hpp.
 //
+// decode_vi_registers() and the first part of scanout() follow the reference's VideoInterface::decode_vi_registers /
+// scanout (parallel-rdp/video_interface.cpp:177-330, Copyright (c) 2020 Themaister, MIT licence -- notice in
+// video_interface.hpp) closely, statement for statement in places: the VI's register arithmetic (start / end clamps,
+// PAL / NTSC geometry, the guard band, per-line scaling) is a list of hardware facts with one right answer, and the
+// host side of this project stays C++ in the reference's shape by design.  Everything downstream of the decoded
+// per-line parameters (kernels, staging, streams) is this project's own.
+//
 // Reference behaviour re-implemented here: parallel-rdp/video_interface.cpp
 //   register decode   :177-367       per-scanline registers :1126-1213
 //   scan-out control  :1215-1426     scale pass geometry    :719-999

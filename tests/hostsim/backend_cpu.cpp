@@ -679,6 +679,8 @@ int rdpb_vi_join(rdpb_device *) { return 0; }
 int rdpb_signal(rdpb_device *, uint64_t) { return 0; }
 int rdpb_wait(rdpb_device *, uint64_t) { return 0; }
 int rdpb_poll(rdpb_device *, uint64_t) { return 1; }
+void rdpb_submit_begin(rdpb_device *) {}
+void rdpb_submit_end(rdpb_device *) {}
 int rdpb_sync(rdpb_device *) { return 0; }
 void *rdpb_stream(rdpb_device *) { return nullptr; }
 uint64_t rdpb_launch_count(rdpb_device *dev) { return dev->launches; }

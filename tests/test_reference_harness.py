@@ -8,7 +8,7 @@ std::mt19937{1337} command streams, the reference's comparisons, the reference's
 pairs are its ctest registrations (tests/golden/reference_ctest_list.txt).
 
 CPU suite: every registered test, a few iterations each, against the test-only host simulator (same device code, same
-host code).  GPU suite: every registered test through librdp_b200.so at 2 % of the reference's depth; the full depth
+host code).  GPU suite: every registered test through librdp_b200.so, five iterations each; the full depth
 (--range 0 1000) is tools/run_reference_conformance.py --scale 1, run once per round with the log under profiles/."""
 import os
 import subprocess
@@ -54,5 +54,6 @@ def test_every_reference_ctest_passes_on_the_host_simulator():
 @pytest.mark.gpu
 @pytest.mark.timeout(1800)
 def test_every_reference_ctest_passes_on_the_gpu():
-    r = _run("--scale", "0.02", "--jobs", str(max(2, min(12, (os.cpu_count() or 4) - 2))))
+    # A few processes only: contexts sharing a GPU are time-sliced (14 at once cost ~50 s of start-up each on B200).
+    r = _run("--scale", "0.005", "--jobs", "4")
     assert r.returncode == 0 and "255 / 255" in r.stdout, r.stdout[-3000:]
