@@ -609,7 +609,9 @@ def run_ours(args):
                     "streams": {str(S): v["frames_per_s"] for S, v in e2e_sweep.items()},
                     "command_thread_us_per_frame_by_streams": {str(S): v["command_thread_us_per_frame"] for S, v in e2e_sweep.items()},
                     "path": "rdp_b200_enqueue_command_stream_borrowed + rdp_b200_set_vi_registers + rdp_b200_scanout_async/_wait "
-                            "(pinned host buffers, %d frames in flight per stream), called from harness/farm_driver.cpp" % args.e2e_depth},
+                            "(pinned host buffers, %d frames in flight per stream), called from harness/farm_driver.cpp; processors created with "
+                            "RDP_B200_FLAG_EXPLICIT_RDRAM_SYNC (the stream writes no RDRAM after start-up, so no RDRAM bytes cross the bus; "
+                            "e2e_rdram adds the per-frame read-back of the rendered images)" % args.e2e_depth},
             "e2e_rdram": e2e_rdram,
             "gpu_launches": b["launches"],
             "roofline": roofline,

@@ -69,8 +69,8 @@ void *rdpb_tmem_host_ptr(rdpb_device *dev);
 void *rdpb_rdram_device_ptr(rdpb_device *dev);
 void *rdpb_hidden_device_ptr(rdpb_device *dev);
 
-/* Brackets a batch of submission calls (a whole pass, a scan-out + its read-back): the CUDA backend serialises the
- * batches of all processors on one GPU so that their command threads do not contend call by call for the driver. */
+/* Brackets a batch of submission calls (a whole pass, a scan-out + its read-back): the CUDA backend admits only a few
+ * such batches at a time per GPU, so that the command threads of many processors do not stampede the driver. */
 void rdpb_submit_begin(rdpb_device *dev);
 void rdpb_submit_end(rdpb_device *dev);
 

@@ -54,6 +54,6 @@ def test_every_reference_ctest_passes_on_the_host_simulator():
 @pytest.mark.gpu
 @pytest.mark.timeout(1800)
 def test_every_reference_ctest_passes_on_the_gpu():
-    # A few processes only: contexts sharing a GPU are time-sliced (14 at once cost ~50 s of start-up each on B200).
-    r = _run("--scale", "0.005", "--jobs", "4")
+    # One process per program: contexts sharing a GPU are time-sliced, and 255 start-ups cost more than the suites.
+    r = _run("--single-process", "5")
     assert r.returncode == 0 and "255 / 255" in r.stdout, r.stdout[-3000:]

@@ -67,6 +67,31 @@ def run_one(prog, name, iterations, library, timeout):
     return prog, name, iterations, ok and ran, time.time() - t0, tail
 
 
+def run_single_process(prog, iterations, library, timeout):
+    """All suites of one program in ONE process (how the reference's binaries run without --suite): one CUDA context, one
+    pair of processors.  Returns [(suite, ok)] in run order; the program stops at the first failing suite."""
+    env = dict(os.environ)
+    if library:
+        env["RDP_B200_LIBRARY"] = library
+    try:
+        r = subprocess.run([BIN[prog], "--range", "0", str(iterations)], capture_output=True, text=True, env=env, timeout=timeout)
+        text = r.stdout + r.stderr
+    except subprocess.TimeoutExpired as e:
+        text = ((e.stdout or b"").decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")) + "\n[ERROR]: timeout\n"
+    results, current = [], None
+    for line in text.splitlines():
+        m = re.search(r"Running suite: (\S+)", line)
+        if m:
+            current = m.group(1)
+        elif "====== PASSED ======" in line and current:
+            results.append((current, True, ""))
+            current = None
+    if current:
+        tail = "\n".join(l for l in text.splitlines() if "Skipping" not in l and "completely zero" not in l)[-800:]
+        results.append((current, False, tail))
+    return results
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--library", default=None)
@@ -79,6 +104,9 @@ def main():
     ap.add_argument("--timeout", type=float, default=3600.0)
     ap.add_argument("--skip-passed-in", default=None, help="log of an earlier run: tests it lists as PASS are not run again")
     ap.add_argument("--regenerate-list", action="store_true")
+    ap.add_argument("--single-process", type=int, default=0, metavar="N",
+                    help="run every suite of each program in one process with --range 0 N (one CUDA context instead of 255: "
+                         "processes sharing a GPU are time-sliced and every synchronous call then waits for its turn)")
     args = ap.parse_args()
     if args.regenerate_list:
         print(regenerate_list(), "tests listed")
@@ -86,6 +114,28 @@ def main():
     if not available():
         print("oracle/_ref conformance programs are not built (make -C oracle, needs /root/reference)")
         return 2
+    if args.single_process:
+        t0 = time.time()
+        registered = {(p, n) for p, n, _ in registered_tests()}
+        lines, failed, passed = [], [], 0
+        for prog in ("rdp", "vi"):
+            for name, ok, tail in run_single_process(prog, args.single_process, args.library, args.timeout):
+                tag = "" if (prog, name) in registered else " (not registered with ctest)"
+                lines.append(f"{'PASS' if ok else 'FAIL'} {prog}-test-{name} --range 0 {args.single_process}{tag}")
+                print(lines[-1], flush=True)
+                if ok and (prog, name) in registered:
+                    passed += 1
+                if not ok:
+                    failed.append(name)
+                    print(tail)
+                    lines.append(tail)
+        summary = (f"{passed} / {len(registered)} reference conformance tests passed, {args.single_process} iterations each, one process per "
+                   f"program ({time.time() - t0:.0f} s, library {args.library or 'product'})")
+        print(summary)
+        if args.log:
+            with open(args.log, "w") as f:
+                f.write(summary + "\n" + "\n".join(lines) + "\n")
+        return 1 if failed or passed != len(registered) else 0
     tests = [(p, n, max(1, int(round(c * args.scale)))) for p, n, c in registered_tests() if args.filter in n]
     if args.skip_passed_in:
         done = set(re.findall(r"^PASS (?:rdp|vi)-test-(\S+) --range", open(args.skip_passed_in).read(), re.M))
