@@ -2095,11 +2095,14 @@ rdpb_device *rdpb_device_create(int cuda_ordinal, uint32_t rdram_size, uint32_t 
 	need(cudaMalloc(&dev->d_vi_lines, sizeof(ViLine) * kViMaxLines * rdpb_device::kViLineSets), "cudaMalloc vi lines");
 	need(cudaHostAlloc(&dev->vi_host_staging, sizeof(ViLine) * kViMaxLines * 2, cudaHostAllocDefault), "cudaHostAlloc vi staging");
 	for (auto &e : dev->vi_lines_done)
-		need(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+		need(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync), "cudaEventCreate");
 	for (unsigned i = 0; i < kStagingSlots; i++)
 	{
 		need(cudaHostAlloc(&dev->staging[i], StagingLayout::total, cudaHostAllocDefault), "cudaHostAlloc staging");
-		need(cudaEventCreateWithFlags(&dev->front_done[i], cudaEventDisableTiming), "cudaEventCreate");
+		// The command thread waits on this one when the GPU is behind (staging slot reuse): a blocking wait, so that a
+		// farm of processors under back-pressure sleeps instead of spinning in the driver (measured at 16 processors:
+		// 12 of 16 cores went to that spin).
+		need(cudaEventCreateWithFlags(&dev->front_done[i], cudaEventDisableTiming | cudaEventBlockingSync), "cudaEventCreate");
 		need(cudaEventCreateWithFlags(&dev->pass_done[i], cudaEventDisableTiming), "cudaEventCreate");
 	}
 
@@ -2257,8 +2260,10 @@ const char *rdpb_last_error(rdpb_device *dev) { return dev->error.c_str(); }
 // per-GPU gate that admits a few threads at a time.  Measured on B200 with 16 processors (C2, end to end): ungated, the
 // threads burn 13 cores spinning on the driver's context lock for 73 us of useful calls per frame (885 us of CPU per
 // frame); behind a plain mutex they use 2 cores but the single file of submitters caps the rate (80 us per frame under
-// the lock, plus a sleeping waiter's wake-up after every hand-off).  A few concurrent submitters keep the driver busy
-// without the stampede.  RDP_B200_SUBMIT_CONCURRENCY sets the number of permits (0 = no gate).
+// the lock, plus a sleeping waiter's wake-up after every hand-off); with two or more permits the rate is the ungated
+// one.  The spin turned out to be cudaEventSynchronize on a non-blocking event under back-pressure (front_done is now a
+// blocking-sync event), not the submission calls, so the gate is off by default: RDP_B200_SUBMIT_CONCURRENCY=k admits
+// k submitters at a time (0 = no gate), kept as a knob for hosts with very few cores per GPU.
 namespace
 {
 struct SubmitGate
@@ -2309,7 +2314,7 @@ struct SubmitGate
 SubmitGate g_submit_gates[64];
 const int g_submit_concurrency = []() {
 	const char *e = getenv("RDP_B200_SUBMIT_CONCURRENCY");
-	const int k = e ? atoi(e) : 3;
+	const int k = e ? atoi(e) : 0;
 	for (auto &g : g_submit_gates)
 		g.permits.store(k);
 	return k;
