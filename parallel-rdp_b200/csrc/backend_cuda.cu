@@ -68,7 +68,10 @@ __attribute__((constructor)) static void rdpb_request_work_queues()
 
 namespace
 {
-constexpr unsigned kStagingSlots = 4;
+// Pass inputs are staged in a ring of slots (pinned host memory + the device-side copy): the command thread may record
+// this many passes -- four 3-D frames -- ahead of the GPU before it has to wait for a slot.  Deep enough that the
+// wake-up latency of that (blocking) wait never drains the GPU's queue.
+constexpr unsigned kStagingSlots = 8;
 // Per-pass device scratch (decoded primitives, spans, bin masks, span jobs, TMEM snapshots) exists three times and passes
 // rotate through the sets: the set-up and span kernels of a pass run on the front stream while the tile kernels of the
 // two passes before it may still be reading theirs.  (Two sets are not enough for a 3-D frame: it is a small clear pass
@@ -2410,8 +2413,26 @@ int rdpb_pass_begin(rdpb_device *dev, rdpb_pass_buffers *out)
 	const unsigned i = dev->staging_index;
 	if (dev->front_in_flight[i])
 	{
-		// The slot's host staging memory was last read by the uploads of the pass four back.
-		CK(cudaEventSynchronize(dev->front_done[i]));
+		// The slot's host staging memory was last read by the uploads of the pass kStagingSlots back.  Usually long
+		// done: poll for a few tens of microseconds, then sleep (front_done is a blocking-sync event).
+		bool done = false;
+		const auto t0 = std::chrono::steady_clock::now();
+		for (;;)
+		{
+			const cudaError_t e = cudaEventQuery(dev->front_done[i]);
+			if (e == cudaSuccess)
+			{
+				done = true;
+				break;
+			}
+			if (e != cudaErrorNotReady)
+				break;
+			if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(30))
+				break;
+		}
+		cudaGetLastError();
+		if (!done)
+			CK(cudaEventSynchronize(dev->front_done[i]));
 		dev->front_in_flight[i] = false;
 	}
 	dev->front_gate_passed = false;
@@ -2446,7 +2467,7 @@ int rdpb_pass_upload(rdpb_device *dev, const rdpb_pass_counts *c)
 
 	uint32_t *words = dev->d_words[i];
 	uint8_t *block = dev->d_inputs[i];
-	// The device-side input slot was last read by the pass four back, the scratch set this pass's set-up kernels will
+	// The device-side input slot was last read by the pass kStagingSlots back, the scratch set this pass's set-up kernels will
 	// overwrite by the pass kScratchSets back.  The compute stream is in order, so one wait for the latter in front of
 	// the uploads covers both -- and the uploads still run while the tile kernels of the passes in between compute.
 	if (front_gate(dev, dev->cur_parity % kScratchSets) != 0)
