@@ -624,9 +624,11 @@ def run_ours(args):
 
     # --- the other BASELINE configs, bounded batches ----------------------------------------------------------------------
     configs = {}
-    if not args.no_configs:
-        for kind in ("c3", "c4i", "c4ii"):
+    wanted = [] if args.no_configs else [c.strip().lower() for c in args.configs.split(",") if c.strip()]
+    for kind in ("c3", "c4i", "c4ii"):
+        if kind in wanted:
             configs[kind.upper()] = run_config(B, Workload(kind, args.triangles), args)
+    if "c5" in wanted:
         configs["C5"] = run_farm(B, args)
     clocks = sampler.stop() if sampler else None
 
@@ -854,6 +856,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--parity-frames", type=int, default=6, help="frames of stream 0 checked against the oracle before timing")
     ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 sub-results")
+    ap.add_argument("--configs", default="c3,c4i,c4ii,c5", help="which of the other BASELINE configs to measure (comma list)")
     ap.add_argument("--e2e-depth", type=int, default=5, help="frames in flight per stream in the e2e leg")
     ap.add_argument("--e2e-threads", type=int, default=8, help="producer threads of the native e2e loop (per rank)")
     ap.add_argument("--streams", default="1,2,4,8,16", help="concurrent independent streams per GPU to measure (comma list, divisors "

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""A few C2 frames (and one C3 frame) through the public API on cuda:0, checked against the oracle: a small, fast driver for
-running the hot kernels under compute-sanitizer (tools/gpu_sanitizer.sh).  usage: c2_few_frames.py [triangles] [frames]"""
+"""C2 frames and C3 frames through the public API on cuda:0, every scan-out image and the final RDRAM / hidden RDRAM checked
+against the oracle: a small driver for running the hot kernels under compute-sanitizer (tools/gpu_sanitizer.sh) and for
+the 100-frame parity run (tools/gpu_r2_final.sh).  usage: c2_few_frames.py [triangles] [c2 frames] [c3 frames]"""
 import importlib
 import os
 import sys
@@ -59,7 +60,8 @@ def main():
     tex, tlut = wl.c3_assets()
     img[wl.TEX_ADDR:wl.TEX_ADDR + tex.size] = tex
     img[wl.TEX_ADDR + 0x1000:wl.TEX_ADDR + 0x1000 + tlut.size] = tlut
-    ok = run("C3", lambda: wl.c3_frame(rng, 6), wl.c3_vi_registers, img, 1) and ok
+    n3 = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    ok = run("C3", lambda: wl.c3_frame(rng, 64 if n3 > 1 else 6), wl.c3_vi_registers, img, n3) and ok
     sys.exit(0 if ok else 1)
 
 
