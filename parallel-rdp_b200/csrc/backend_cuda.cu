@@ -294,7 +294,10 @@ __global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
 //               prefetches of everything the shade phase will read.  32 primitives' dependent loads overlap.
 //   shade phase walks the live primitives in order; header fields arrive by shuffle, so the only loads left on
 //               the critical path hit lines the mask phase already requested.
-constexpr uint32_t kTileWarpsPerBlock = 4;
+#ifndef RDPB_TILE_WARPS
+#define RDPB_TILE_WARPS 4
+#endif
+constexpr uint32_t kTileWarpsPerBlock = RDPB_TILE_WARPS;
 constexpr uint32_t kTileListCapacity = 128;
 
 // The tile counter is bumped with atom.inc (wrap bound 2^31 - 1, far above any tile count, so a plain increment):
@@ -368,7 +371,8 @@ struct NextTilePrefetch
 		const uint32_t words_per_lane = (fb.mask_stride + 31u) / 32u;
 		if (masks && words_per_lane <= kGatherWords && lane * words_per_lane < fb.mask_stride)
 			prefetch_l1(b.fine_mask + size_t(tile) * fb.mask_stride + lane * words_per_lane);
-		const uint32_t ax = (tile % fb.tiles_x) * kTileW + (lane & 7u), ay = (tile / fb.tiles_x) * kTileH + (lane >> 3);
+		const uint32_t trow = fb.tile_row_recip ? __umulhi(tile, fb.tile_row_recip) : tile;
+		const uint32_t ax = (tile - trow * fb.tiles_x) * kTileW + (lane & 7u), ay = trow * kTileH + (lane >> 3);
 		if (ax < fb.width && ay < fb.height && fb.scale_log2 == 0u)
 		{
 			const uint32_t pix = fb.width * ay + ax;
@@ -521,7 +525,10 @@ __device__ __forceinline__ unsigned long long *counter_slot(const PassBuffers &b
 // The in-order walker runs ~11 of 32 lanes through texturing on the small triangles of a 3-D scene (a triangle
 // covers a third of an 8x4 tile on average); here the expensive phases A and C run converged over dense slots and
 // only the two cheap ordered phases B and D depend on how many fragments one pixel has.
-constexpr uint32_t kDeferCapacity = 256; // fragment slots per batch (>= 32: one list entry always fits)
+#ifndef RDPB_DEFER_CAPACITY
+#define RDPB_DEFER_CAPACITY 256
+#endif
+constexpr uint32_t kDeferCapacity = RDPB_DEFER_CAPACITY; // fragment slots per batch (>= 32: one list entry always fits)
 constexpr uint32_t kEntryFill = 1u << 31, kEntryAa = 1u << 30; // DeferWarp::ids flag bits (state id: bits 0-15, TMEM snapshot: 16-23)
 
 // Second word of a shaded result (shade alpha + dither pattern): only states that dither or feed shade alpha to
@@ -544,14 +551,18 @@ struct alignas(16) DeferWarp
 {
 	uint32_t result[kDeferCapacity];  // C -> D: packed shaded colour of a slot (r | g<<8 | b<<16 | a<<24)
 	uint32_t cand[kDeferCapacity]; // A -> B: candidate word; B -> C, D: survivor record
-	uint32_t desc[kDeferCapacity]; // slot -> entry << 5 | pixel; after compaction: survivor -> slot << 16 | entry << 5 | pixel
 	uint32_t pixmask[32], base[32], prim[32], span_base[32], ids[32], lines[32], dzw[32]; // per list entry of the chunk
 	// What phase A needs of an entry's primitive and state besides the header, fetched once per entry by the mask phase
 	// instead of once per fragment: dz/dx, dz/dy, and (in ids, bits 31 / 30) whether the state is fill mode / anti-aliased.
 	int32_t dzdx[32], dzdy[32];
+	// desc and list are adjacent: both are dead once the last batch of a tile has been shaded, and together they take the
+	// next tile's mask words (NextTilePrefetch::stage_masks) while phase D runs.
+	uint32_t desc[kDeferCapacity]; // slot -> entry << 5 | pixel; after compaction: survivor -> slot << 16 | entry << 5 | pixel
 	uint16_t list[kTileListCapacity];
 };
-static_assert(kDeferCapacity >= 32u * kGatherWords, "the next tile's mask words are staged in DeferWarp::desc (NextTilePrefetch::stage_masks)");
+static_assert(offsetof(DeferWarp, list) == offsetof(DeferWarp, desc) + 4u * kDeferCapacity, "desc and list form one staging area");
+static_assert(kDeferCapacity + kTileListCapacity / 2u >= 32u * kGatherWords, "the next tile's mask words are staged in DeferWarp::desc + list (NextTilePrefetch::stage_masks)");
+static_assert(kDeferCapacity >= 32u && kDeferCapacity <= 256u, "one list entry always fits a batch");
 
 // Per-warp shared memory of the tile kernel: just the primitive list for the in-order walker.
 template <class S, bool DEFERRED>
@@ -598,6 +609,12 @@ struct DeferredWalker
 				my_prim = list[c + lane];
 				const PrimSetup *pp = b.prims + my_prim;
 				hdr = *reinterpret_cast<const uint4 *>(&pp->span_base);
+#ifndef RDPB_EXP_LATE_ENTRY_LOADS
+				// What phase A needs of the primitive and the state is requested now, so that it travels together with the
+				// span headers below instead of after them (binning is exact: nearly every entry has pixels here).
+				const int32_t dzdx = __ldg(&pp->dstzw_dx[2]), dzdy = __ldg(&pp->dstzw_dy[2]);
+				const uint32_t state_rf = __ldg(&b.states[hdr.y & 0xffffu].raster_flags);
+#endif
 				const int line_lo = int(int16_t(hdr.z & 0xffffu)), line_hi = int(int16_t(hdr.z >> 16));
 #pragma unroll
 				for (int r = 0; r < int(kTileH); r++)
@@ -617,6 +634,7 @@ struct DeferredWalker
 					prefetch_l1(sp);
 				}
 				pixmask &= inside_mask;
+#ifdef RDPB_EXP_LATE_ENTRY_LOADS
 				if (pixmask)
 				{
 					prefetch_l1(pp);
@@ -626,6 +644,16 @@ struct DeferredWalker
 					w.dzdx[lane] = __ldg(&pp->dstzw_dx[2]);
 					w.dzdy[lane] = __ldg(&pp->dstzw_dy[2]);
 				}
+#else
+				if (pixmask)
+				{
+					prefetch_l1(pp);
+					prefetch_l1(reinterpret_cast<const uint8_t *>(pp) + 128);
+				}
+				hdr.y = (hdr.y & 0x00ffffffu) | ((state_rf & RF_FILL) ? kEntryFill : 0u) | ((state_rf & RF_AA) ? kEntryAa : 0u);
+				w.dzdx[lane] = dzdx;
+				w.dzdy[lane] = dzdy;
+#endif
 			}
 			w.pixmask[lane] = pixmask;
 			w.prim[lane] = my_prim;
@@ -743,6 +771,7 @@ struct DeferredWalker
 				}
 				__syncwarp();
 
+#ifdef RDPB_EXP_SLOT_COMPACT
 				// ---- compact the survivors (stable: still ordered by primitive, then pixel) ----
 				uint32_t n2 = 0;
 				for (uint32_t k0 = 0; k0 < count; k0 += 32u)
@@ -757,6 +786,30 @@ struct DeferredWalker
 					n2 += uint32_t(__popc(ballot));
 				}
 				__syncwarp();
+#else
+				// ---- list the survivors densely for phase C (which is order-free): every lane appends its own pixel's,
+				// at the exclusive prefix sum of the per-pixel survivor counts ----
+				uint32_t n2;
+				{
+					const uint32_t own = uint32_t(__popc(surv));
+					uint32_t incl = own;
+#pragma unroll
+					for (int off = 1; off < 32; off <<= 1)
+					{
+						const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+						if (lane >= uint32_t(off))
+							incl += v;
+					}
+					n2 = __shfl_sync(0xffffffffu, incl, 31);
+					uint32_t at = incl - own;
+					for (uint32_t t = surv; t; t &= t - 1u)
+					{
+						const uint32_t j = uint32_t(__ffs(int(t)) - 1);
+						w.desc[at++] = (slot_of(j, lt) << 16) | (j << 5) | lane;
+					}
+				}
+				__syncwarp();
+#endif
 
 				if (c + 32u >= n && live == 0u)
 					next.issue(b, fb, view.fmt, lane, !stage_next);
@@ -827,7 +880,7 @@ template <class S>
 __device__ __forceinline__ const uint32_t *staged_words(const TileShared<S, true> &sw) { return sw.desc; }
 
 template <class S, bool DEFERRED = false, bool UPSCALED = false>
-__global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blocks_per_sm_deferred : S::min_blocks_per_sm) k_tiles(PassBuffers b, FbInfo fb)
+__global__ void __launch_bounds__(kTileWarpsPerBlock * 32, (DEFERRED ? S::min_blocks_per_sm_deferred : S::min_blocks_per_sm) * 4 / kTileWarpsPerBlock) k_tiles(PassBuffers b, FbInfo fb)
 {
 	static_assert(!(DEFERRED && UPSCALED), "upscaled passes run the in-order walker");
 	// A literal 0 everywhere but in the upscaled instantiation: the scale shifts fold away.
@@ -858,7 +911,11 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 	const uint32_t words_per_lane = (fb.mask_stride + 31u) / 32u;
 	const bool one_round = words_per_lane <= kGatherWords;
 
-	uint32_t tiles_done = 0, shaded_total = 0;
+	// Metrics (tiles processed, pixels shaded) accumulate in shared memory: two registers fewer across the tile loop.
+	__shared__ uint32_t s_stats[kTileWarpsPerBlock][2];
+	uint32_t *stats = s_stats[threadIdx.x >> 5];
+	if (lane == 0)
+		stats[0] = stats[1] = 0u;
 	uint32_t staged_tile = 0xffffffffu; // tile whose mask words wait in shared memory (deferred walker only)
 	// The tile counter is read one tile ahead: the atomic's round trip overlaps the current tile's work.
 	uint32_t next_tile = 0;
@@ -941,9 +998,8 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 			if (!any)
 				continue;
 		}
-		tiles_done++;
 
-		const uint32_t tx = tile % fb.tiles_x, ty = tile / fb.tiles_x;
+		const uint32_t ty = fb.tile_row_recip ? __umulhi(tile, fb.tile_row_recip) : tile, tx = tile - ty * fb.tiles_x;
 		FbView view;
 		PixelState px;
 		auto walk = make_tile_walker<S>(b, fb, ctx, view, px, sw, lane, int(tx * kTileW), int(ty * kTileH));
@@ -1022,7 +1078,14 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 				__syncwarp();
 			}
 		}
-		shaded_total += walk.shaded;
+		{
+			const uint32_t tile_shaded = __reduce_add_sync(0xffffffffu, walk.shaded);
+			if (lane == 0)
+			{
+				stats[0] += 1u;
+				stats[1] += tile_shaded;
+			}
+		}
 
 		pass_pixel_end(fb, view, px, walk.x, walk.y, sl);
 		if (UPSCALED)
@@ -1035,14 +1098,13 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, DEFERRED ? S::min_blo
 	}
 
 	// One atomic per warp keeps the metrics essentially free.
-	const uint32_t warp_total = __reduce_add_sync(0xffffffffu, shaded_total);
 	if (lane == 0)
 	{
 		unsigned long long *slot = counter_slot(b, blockIdx.x * kTileWarpsPerBlock + (threadIdx.x >> 5));
-		if (tiles_done)
-			atomicAdd(&slot[0], (unsigned long long)tiles_done);
-		if (warp_total)
-			atomicAdd(&slot[1], (unsigned long long)warp_total);
+		if (stats[0])
+			atomicAdd(&slot[0], (unsigned long long)stats[0]);
+		if (stats[1])
+			atomicAdd(&slot[1], (unsigned long long)stats[1]);
 	}
 }
 
@@ -1828,6 +1890,10 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		const size_t vi = up ? 30 + size_t(op.variant - kUpscaledVariants) : size_t(op.variant - kTileVariants);
 		if (!dev->variant_blocks_per_sm[vi])
 		{
+			// RDP_B200_TILE_CARVEOUT=<percent of the SM's shared memory>: experiment switch for the L1 / shared split of the
+			// tile kernels (the driver's default is the smallest carve-out that holds the resident blocks).
+			if (const char *c = getenv("RDP_B200_TILE_CARVEOUT"))
+				cudaFuncSetAttribute(reinterpret_cast<const void *>(op.variant->kernel), cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
 			int n = 0;
 			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, op.variant->kernel, int(kTileWarpsPerBlock * 32), 0) != cudaSuccess || n <= 0)
 				n = 4;
@@ -1835,7 +1901,9 @@ static int issue(rdpb_device *dev, const GpuOp &op)
 		}
 		const uint32_t per_sm = dev->tile_blocks_per_sm_override ? dev->tile_blocks_per_sm_override : dev->variant_blocks_per_sm[vi];
 		const uint32_t blocks = std::min((tiles + kTileWarpsPerBlock - 1) / kTileWarpsPerBlock, dev->num_sms * per_sm);
-		op.variant->kernel<<<blocks, kTileWarpsPerBlock * 32, 0, dev->stream>>>(dev->buffers(op), op.fb);
+		FbInfo kfb = op.fb;
+		kfb.tile_row_recip = kfb.tiles_x > 1u ? 0xffffffffu / kfb.tiles_x + 1u : 0u;
+		op.variant->kernel<<<blocks, kTileWarpsPerBlock * 32, 0, dev->stream>>>(dev->buffers(op), kfb);
 		prof_end(dev, s);
 		dev->launches++;
 		break;

@@ -289,7 +289,10 @@ struct FbInfo
 	// Super-sampled read-back: the upscaled pass also records which native pixels it stored to (2 bits per native
 	// pixel, 4x4 pixels per word, behind the last RDRAM slice; ref memory_interfacing.h:305-337).
 	uint32_t write_mask;
-	uint32_t pad;
+	// ceil(2^32 / tiles_x), 0 when tiles_x == 1: tile / tiles_x == umulhi(tile, tile_row_recip) for every tile index below
+	// 2^32 / tiles_x.  Filled in by the CUDA backend at launch (the tile kernels read it from the constant bank, so the
+	// tile index -> (column, row) split costs a multiply instead of a division per tile); zero elsewhere.
+	uint32_t tile_row_recip;
 };
 
 // Which passes are worth rendering upscaled: the reference's heuristic (rdp_renderer.cpp:3000-3012: only 16/32-bit
