@@ -815,6 +815,9 @@ struct DeferredWalker
 					next.issue(b, fb, view.fmt, lane, !stage_next);
 
 				// ---- C: shade the survivors ----
+#ifdef RDPB_EXP_SKIP_SHADE // timing experiment only (wrong pictures): what the kernel costs without phases C and D
+				if (n2 == 0xffffffffu)
+#endif
 				RDPB_UNROLL_C
 				for (uint32_t k2 = lane; k2 < n2; k2 += 32u)
 				{
@@ -839,6 +842,10 @@ struct DeferredWalker
 					next.stage_masks(b, fb, lane, w.desc);
 
 				// ---- D: ordered blend stage, one pixel per lane ----
+#ifdef RDPB_EXP_SKIP_SHADE
+				px.r += int(n2);
+				if (n2 == 0xffffffffu)
+#endif
 				for (uint32_t t = surv; t; t &= t - 1u)
 				{
 					const uint32_t j = uint32_t(__ffs(int(t)) - 1);
