@@ -273,3 +273,17 @@ def test_state_snapshots_are_interned_per_pass():
         assert sbs.gpu.pass_count() - before == 1
     finally:
         sbs.close()
+
+
+def test_tile_row_reciprocal_is_exact_over_every_frame_shape():
+    """FbInfo::tile_row_recip (rdp_types.h; filled in by the CUDA backend at launch): the tile kernels split a tile index
+    into (row, column) as umulhi(tile, ceil(2^32 / tiles_x)).  Exact for every tile index below 2^32 / tiles_x -- checked
+    here for every tiles_x a native or upscaled pass can have (upscaled width < 8192 pixels -> at most 1024 tile columns)
+    at the indices where a rounded-up reciprocal fails first: the last tile of the largest image and the row boundaries."""
+    for tiles_x in range(2, 1025):
+        recip = 0xFFFFFFFF // tiles_x + 1
+        rows = 8192 // 4  # tile rows of the tallest upscaled image (1024 lines at 8x, 4 lines per tile)
+        r = np.arange(rows, dtype=np.uint64)
+        for tile in (r * tiles_x, r * tiles_x + (tiles_x - 1)):  # first and last tile of every row
+            got = (tile * np.uint64(recip)) >> np.uint64(32)
+            assert np.array_equal(got, tile // np.uint64(tiles_x)), tiles_x

@@ -1,10 +1,11 @@
 #!/bin/bash
-# Round-end set: full GPU suite, smoke, default bench (all configs + cpu_baseline), reference arm, launch list, full ncu captures.
+# Round-end set, part A: full GPU suite, smoke, default bench (all configs + cpu_baseline), reference arm, launch list,
+# one frame's kernels under ncu --set full with source.  (Part B: tools/gpu_r2_final_b.sh.)
 tag=${1:-r2z}
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/${tag}_pytest.log
+( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/${tag}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${tag}_smoke.log
-timeout 1200 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/${tag}_bench.err
+( time timeout 1200 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err ); echo "bench rc=$?"; tail -3 gpurun_out/${tag}_bench.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; echo "reference rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 1 --warmup 1 --small --no-parity --no-cpu-baseline --no-configs --streams 1 > gpurun_out/${tag}_ncu2.log 2>&1
@@ -19,9 +20,3 @@ for k,v in d.get('configs',{}).items(): print(k, v.get('frames_per_s'), v.get('e
 r=json.loads(open('gpurun_out/${tag}_bench_reference.json').read().strip().splitlines()[-1])
 print('reference', r['value'], r['cpu_baseline'])
 PY
-# --- long parity beyond the reference's ctest depth: forced-deferred generic kernel through the reference's suites, 100 benchmark frames
-RDP_B200_FORCE_DEFERRED=1 timeout 1200 python tools/run_reference_conformance.py --single-process 60 --log gpurun_out/${tag}_reference_conformance_forced_deferred.log > gpurun_out/${tag}_refconf_fd.out 2>&1; echo "forced-deferred conformance rc=$?"; tail -1 gpurun_out/${tag}_refconf_fd.out
-timeout 900 python tools/c2_few_frames.py 5000 100 30 > gpurun_out/${tag}_c2_c3_100_frames.log 2>&1; echo "100 frames rc=$?"; cat gpurun_out/${tag}_c2_c3_100_frames.log
-# --- C4-ii kernels under ncu (the one byte-heavy config): upscaled tile kernel, upscale sync
-timeout 600 ncu --set full --clock-control none -k regex:"k_tiles|k_upscale|k_span_bin|k_vi" --launch-skip 40 -c 14 -f -o gpurun_out/${tag}_c4ii \
-  python bench.py --steps 1 --warmup 1 --small --no-parity --no-cpu-baseline --streams 1 --configs c4ii > gpurun_out/${tag}_ncu_c4ii.log 2>&1; echo "ncu c4ii rc=$?"
