@@ -395,14 +395,14 @@ struct NextTilePrefetch
 			return;
 		const uint32_t first = lane * words_per_lane;
 		const uint32_t *src = b.fine_mask + size_t(tile) * fb.mask_stride + first;
-		const uint32_t sdst = uint32_t(__cvta_generic_to_shared(dst + lane * kGatherWords));
+		const uint32_t sdst = uint32_t(__cvta_generic_to_shared(dst + lane));
 #pragma unroll
 		for (uint32_t i = 0; i < kGatherWords; i++)
 		{
 			if (i < words_per_lane && first + i < fb.mask_stride)
-				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 4u * i), "l"(src + i) : "memory");
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 128u * i), "l"(src + i) : "memory");
 			else
-				dst[lane * kGatherWords + i] = 0u;
+				dst[i * 32u + lane] = 0u;
 		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
 		staged = tile;
@@ -952,7 +952,7 @@ __global__ void __launch_bounds__(kTileWarpsPerBlock * 32, (DEFERRED ? S::min_bl
 #pragma unroll
 				for (uint32_t i = 0; i < kGatherWords; i++)
 				{
-					wv[i] = staged_words(sw)[lane * kGatherWords + i];
+					wv[i] = staged_words(sw)[i * 32u + lane];
 					n += uint32_t(__popc(wv[i]));
 				}
 				__syncwarp();
