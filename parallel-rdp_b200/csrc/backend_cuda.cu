@@ -518,7 +518,7 @@ __device__ __forceinline__ unsigned long long *counter_slot(const PassBuffers &b
 //   enumerate  every fragment of the batch gets a slot; slots are ordered by primitive, then pixel
 //   A          lane k <-> slot k: coverage mask + Z                      -- full lanes whatever the triangle shapes
 //   B          lane p <-> pixel p walks its own fragments in order: depth test, Z / coverage update
-//   compact    surviving slots are packed (warp ballot prefix)
+//   list       every lane appends its pixel's surviving slots to a dense list (warp prefix sum of the per-pixel counts)
 //   C          lane k <-> survivor k: texture + combiner                 -- full lanes, and nothing hidden is shaded
 //   D          lane p <-> pixel p walks its survivors in order: blender against the running memory colour
 //
@@ -557,7 +557,7 @@ struct alignas(16) DeferWarp
 	int32_t dzdx[32], dzdy[32];
 	// desc and list are adjacent: both are dead once the last batch of a tile has been shaded, and together they take the
 	// next tile's mask words (NextTilePrefetch::stage_masks) while phase D runs.
-	uint32_t desc[kDeferCapacity]; // slot -> entry << 5 | pixel; after compaction: survivor -> slot << 16 | entry << 5 | pixel
+	uint32_t desc[kDeferCapacity]; // slot -> entry << 5 | pixel; then the survivor list: survivor -> slot << 16 | entry << 5 | pixel
 	uint16_t list[kTileListCapacity];
 };
 static_assert(offsetof(DeferWarp, list) == offsetof(DeferWarp, desc) + 4u * kDeferCapacity, "desc and list form one staging area");
@@ -771,22 +771,6 @@ struct DeferredWalker
 				}
 				__syncwarp();
 
-#ifdef RDPB_EXP_SLOT_COMPACT
-				// ---- compact the survivors (stable: still ordered by primitive, then pixel) ----
-				uint32_t n2 = 0;
-				for (uint32_t k0 = 0; k0 < count; k0 += 32u)
-				{
-					const uint32_t k = k0 + lane;
-					const bool alive = k < count && (w.cand[k] & DR_SURVIVE) != 0u;
-					const uint32_t d = alive ? w.desc[k] : 0u;
-					const uint32_t ballot = __ballot_sync(0xffffffffu, alive);
-					__syncwarp(); // every lane has read its descriptor before any slot below is overwritten
-					if (alive)
-						w.desc[n2 + uint32_t(__popc(ballot & lt))] = (k << 16) | d;
-					n2 += uint32_t(__popc(ballot));
-				}
-				__syncwarp();
-#else
 				// ---- list the survivors densely for phase C (which is order-free): every lane appends its own pixel's,
 				// at the exclusive prefix sum of the per-pixel survivor counts ----
 				uint32_t n2;
@@ -809,7 +793,6 @@ struct DeferredWalker
 					}
 				}
 				__syncwarp();
-#endif
 
 				if (c + 32u >= n && live == 0u)
 					next.issue(b, fb, view.fmt, lane, !stage_next);
