@@ -77,7 +77,10 @@ constexpr unsigned kStagingSlots = 8;
 // two passes before it may still be reading theirs.  (Two sets are not enough for a 3-D frame: it is a small clear pass
 // followed by the big scene pass, so with two sets every scene pass lands on the same set as the previous frame's scene
 // pass and its set-up cannot start before that tile kernel has finished.)
-constexpr unsigned kScratchSets = 3;
+#ifndef RDPB_SCRATCH_SETS
+#define RDPB_SCRATCH_SETS 3
+#endif
+constexpr unsigned kScratchSets = RDPB_SCRATCH_SETS;
 
 struct StagingLayout
 {
