@@ -284,9 +284,9 @@ __global__ void __launch_bounds__(128) k_span_bin(PassBuffers b, FbInfo fb)
 	}
 }
 
-// One warp per 8x4 tile, one thread per pixel; warps never synchronise with each other and pull tiles from a
-// global counter until none are left (persistent warps: the grid is sized to the machine, not to the frame, so
-// heavy tiles do not leave a ragged tail).
+// One warp per 8x4 tile, one thread per pixel; warps never synchronise with each other.  Persistent warps: the grid is
+// sized to the machine, not to the frame; every warp starts on the tile of its own index and then pulls tiles from a
+// global counter until none are left, so heavy tiles do not leave a ragged tail.
 //
 // Per tile:
 //   gather      lanes read the tile's fine-mask words 32 at a time (coalesced), zero them for the next pass, and
